@@ -1,0 +1,242 @@
+/*
+ * rbslam.h -- C ABI of librbslam.so: the B200 (sm_100a) implementation of the
+ * Rao-Blackwellized particle filter / smoother hot path of
+ * manonkok/Rao-Blackwellized-SLAM-smoothing.
+ *
+ * This header is the drop-in boundary.  The reference has no FFI of its own (it
+ * is interpreted MATLAB); the entry points below are what a MEX gateway binds so
+ * that the three reference functions keep their MATLAB signatures:
+ *
+ *   particleFilter(...)                  src/particleFilter.m:1-3
+ *   particleSmoother(...)                src/particleSmoother.m:1-2
+ *   particleSmootherInformationForm(...) src/particleSmootherInformationForm.m:1-2
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the boundary;
+ *   - every matrix is fp64, column-major, exactly as MATLAB stores it (mxGetDoubles);
+ *   - the caller owns all host buffers; the library never keeps a host pointer
+ *     after a call returns and owns all device memory inside the context;
+ *   - indices returned to the caller are 0-based int32 (MATLAB shims add 1);
+ *   - every function returns an rbslam_status; rbslam_last_error() gives text;
+ *   - a context is not thread-safe (MATLAB calls mexFunction on one thread).
+ *
+ * The MATLAB function handles dynModel / measModel / dynResNorm cannot be called
+ * from CUDA.  The caller names one of the model families below and passes the
+ * constants its closures captured (rbslam_config); an unknown family is
+ * RBSLAM_EMODEL -- there is no CPU fallback.
+ */
+#ifndef RBSLAM_H
+#define RBSLAM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBSLAM_VERSION 1
+
+#if defined(__GNUC__)
+#define RBSLAM_API __attribute__((visibility("default")))
+#else
+#define RBSLAM_API
+#endif
+
+typedef struct rbslam_ctx rbslam_ctx;
+
+typedef enum {
+  RBSLAM_OK = 0,
+  RBSLAM_EARG = 1,    /* bad argument / shape / unsupported size */
+  RBSLAM_ECUDA = 2,   /* CUDA or NCCL failure */
+  RBSLAM_ENOTPD = 3,  /* innovation covariance not PD even after jitter
+                         (MATLAB would throw from chol, src/particleFilter.m:147) */
+  RBSLAM_EMODEL = 4   /* unsupported model family */
+} rbslam_status;
+
+/* Model families = the closures the reference's runners pass as handles. */
+typedef enum {
+  /* examples/slam-dense-mag/run_dense3D_magfield.m:265-279,301-308,202-203
+     xn=[pos(3);quat(4)], odometry [dpos(3) dquat(4)], d=3, M=m_basis+3, 6 normals */
+  RBSLAM_MODEL_DENSE_MAG3D = 1,
+  /* examples/slam-dense-radio/run_dense2D_withHeading.m:75-77,168
+     xn=[pos(2);heading], d=1, M=m_basis, 1 normal */
+  RBSLAM_MODEL_DENSE_RADIO2D = 2,
+  /* examples/slam-sparse-visual/pfslam.m:81-82, measurement.m:32-84
+     xn=[pos(2);heading], d=m_basis landmarks, M=2*m_basis, 3 normals, dynResNorm=[] */
+  RBSLAM_MODEL_SPARSE_VISUAL2D = 3
+} rbslam_model;
+
+typedef enum {
+  RBSLAM_RNG_INJECTED = 0, /* caller supplies U,Z (compat mode: MATLAB pre-draws them) */
+  RBSLAM_RNG_PHILOX = 1    /* device Philox4x32-10, counter=(particle,step,block,sweep) */
+} rbslam_rng;
+
+typedef struct {
+  int32_t struct_size;     /* sizeof(rbslam_config), for ABI checks */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t model;           /* rbslam_model */
+  int32_t N;               /* N_P particles (global count) */
+  int32_t T;               /* N_T time steps (capacity; inputs may use fewer) */
+  int32_t m_basis;         /* eigenfunctions (dense) or landmarks (sparse) */
+  const int32_t *NN;       /* [m_basis x dim] column-major eigenfunction indices (dense) */
+  const double *L;         /* [dim] domain half-widths (dense) */
+  double cam_f, cam_fp, cam_fw; /* pinhole constants (sparse), measurement.m:32 */
+  int32_t rng_mode;        /* rbslam_rng */
+  uint64_t seed;           /* Philox key */
+  int32_t ld;              /* leading dimension of covariance slabs, 0 = auto */
+  int32_t information_form;/* also carry ivec/Imat/halfLogDetP (information-form smoother) */
+  int32_t keep_history;    /* 1: keep xn history for xn_traj / traj_sample outputs */
+  int32_t rank, world;     /* particle sharding: this context owns N/world particles */
+  int32_t kalman_variant;  /* 0 = auto; >0 selects a specific kernel (profiling) */
+} rbslam_config;
+
+typedef struct {
+  int32_t T;               /* N_T = rows of y */
+  const double *odometry;  /* [odo_rows x n_odo]; row t-1 is used at step t */
+  int32_t odo_rows;        /* leading dimension of odometry (>= T-1) */
+  const double *y;         /* [T x d]; NaN = unobserved (sparse family) */
+  const double *x0_nonLin; /* [n] */
+  const double *x0_lin;    /* [M x x0_lin_cols] */
+  int32_t x0_lin_cols;     /* 1 or N (src/particleFilter.m:60-64) */
+  const double *P0_lin;    /* [M x M] */
+  const double *Q;         /* [nw x nw x Q_pages] */
+  int32_t Q_pages;         /* 1 or >= T-1 (src/particleFilter.m:75-77) */
+  const double *R;         /* [d x d] */
+  const double *dt;        /* [dt_len] */
+  int32_t dt_len;          /* 1 or >= T-1 (src/particleFilter.m:80-82) */
+  /* injected streams (RBSLAM_RNG_INJECTED), MATLAB layouts: */
+  const double *U;         /* [N x T x K] uniforms of sample(); column t=0 unused */
+  const double *Z;         /* [nz x N x T x K] normals of dynModel */
+  const double *Uend;      /* [K] sweep-end uniforms (smoothers) */
+  /* teacher forcing for parity tests (optional, 0-based) */
+  const int32_t *forced_ancestors; /* [N x T x K] */
+  const int32_t *forced_ak;        /* [K] */
+} rbslam_inputs;
+
+typedef struct {          /* any pointer may be NULL = not wanted */
+  double *traj_max;        /* [n x T] */
+  double *traj_mean;       /* [n x T] */
+  double *xl_max;          /* [M] */
+  double *xl_mean;         /* [M] */
+  double *P_max;           /* [M x M] */
+  double *P_mean;          /* [M x M] (reference quirk: last particle's term only) */
+  double *traj_sample_iwmax; /* [n x T] */
+  double *xn_traj;         /* [n x N x T] */
+  /* taps for parity tests */
+  double *logw_hist;       /* [N x T] unnormalised log-weights */
+  double *w_hist;          /* [N x T] normalised weights */
+  int32_t *ancestors;      /* [N x T] 0-based, column 0 unused */
+} rbslam_filter_outputs;
+
+typedef struct {
+  double *XNK;             /* [n x T x N_K] */
+  double *XLK;             /* [M x N_K] */
+  double *PK;              /* [M x M x N_K] */
+  double *AI;              /* [N x T x N_K] ancestor probabilities of the reference
+                              particle (the reference's debugging matrix AI(:,t)) */
+  int32_t *ak;             /* [N_K] sampled trajectory index per sweep, 0-based */
+} rbslam_smoother_outputs;
+
+typedef void (*rbslam_step_fn)(void *user, int32_t sweep, int32_t t);
+
+/* ---- life cycle --------------------------------------------------------- */
+RBSLAM_API int rbslam_version(void);
+RBSLAM_API int rbslam_device_count(void);
+RBSLAM_API int rbslam_create(rbslam_ctx **out, const rbslam_config *cfg);
+RBSLAM_API void rbslam_destroy(rbslam_ctx *ctx);
+RBSLAM_API const char *rbslam_last_error(const rbslam_ctx *ctx); /* ctx may be NULL: last create error */
+/* derived sizes: n, d, M, nz, nw, n_odo, ld (in that order) */
+RBSLAM_API int rbslam_dims(const rbslam_ctx *ctx, int32_t out7[7]);
+
+/* ---- whole-run entry points (host buffers in, host buffers out) --------- */
+/* replaces the body of src/particleFilter.m:52-233 */
+RBSLAM_API int rbslam_filter_run(rbslam_ctx *ctx, const rbslam_inputs *in, rbslam_filter_outputs *out);
+/* replaces src/particleSmoother.m:48-366 (form=0) and
+   src/particleSmootherInformationForm.m:54-361 (form=1) */
+RBSLAM_API int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N_K, int32_t form,
+                        rbslam_smoother_outputs *out);
+/* per-step callback (the makePlots hook, src/particleFilter.m:215-217); the
+   callback may call rbslam_read_particles */
+RBSLAM_API int rbslam_step_callback(rbslam_ctx *ctx, rbslam_step_fn fn, void *user);
+
+/* ---- stepwise filter (tests, benchmarks, makePlots-style taps) ---------- */
+RBSLAM_API int rbslam_filter_begin(rbslam_ctx *ctx, const rbslam_inputs *in);
+RBSLAM_API int rbslam_filter_step(rbslam_ctx *ctx);              /* advances one time step, asynchronous */
+RBSLAM_API int rbslam_filter_end(rbslam_ctx *ctx, rbslam_filter_outputs *out);
+RBSLAM_API int rbslam_sync(rbslam_ctx *ctx);                     /* wait for enqueued work, report errors */
+/* logical-order copies of the particle state (any pointer may be NULL):
+   xn [n x N], xl [M x N], P [M x M x N], logw [N], w [N], ai [N] */
+RBSLAM_API int rbslam_read_particles(rbslam_ctx *ctx, double *xn, double *xl, double *P, double *logw,
+                          double *w, int32_t *ai);
+/* information-form extras: ivec [M x N], Imat [M x M x N], halfLogDetP [N] */
+RBSLAM_API int rbslam_read_information(rbslam_ctx *ctx, double *ivec, double *Imat, double *halfLogDetP);
+/* counters since context creation: kernels launched by this library, bytes copied */
+RBSLAM_API int rbslam_counters(rbslam_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes,
+                    int64_t *d2h_bytes);
+/* CUDA-event timing on the context's own stream (torch.cuda.Event cannot see it).
+   rbslam_event_record marks slot 0..15; rbslam_event_elapsed syncs and returns ms. */
+RBSLAM_API int rbslam_event_record(rbslam_ctx *ctx, int32_t slot);
+RBSLAM_API int rbslam_event_elapsed(rbslam_ctx *ctx, int32_t slot_a, int32_t slot_b, float *ms);
+/* per-phase device time: enable, run steps, then read accumulated ms per phase:
+   [0] resample+plan [1] propagate [2] measurement Jacobian [3] Kalman update
+   (gather + log-weight + downdate) [4] normalise [5] ancestor weights
+   [6] information-form update [7] reserved.  Reading syncs and resets. */
+RBSLAM_API int rbslam_phase_timing(rbslam_ctx *ctx, int32_t enable);
+RBSLAM_API int rbslam_phase_times(rbslam_ctx *ctx, double ms8[8]);
+/* raw stream handle (cudaStream_t) for hosts that enqueue their own collectives */
+RBSLAM_API void *rbslam_stream(rbslam_ctx *ctx);
+
+/* ---- kernel-level entry points (host buffers; parity tests) ------------- */
+/* tools/sample.m:30-32 for a vector of uniforms: ai[j] = sum(cumsum(w) < u[j]) (0-based,
+   clamped to N-1) */
+RBSLAM_API int rbslam_op_resample(rbslam_ctx *ctx, int32_t N, const double *w, int32_t n_draws,
+                       const double *u, int32_t *ai);
+/* src/particleFilter.m:153-159: w = exp(logw - lse), iw_max = first argmax */
+RBSLAM_API int rbslam_op_normalize(rbslam_ctx *ctx, int32_t N, const double *logw, double *w,
+                        int32_t *iw_max);
+/* dynModel for N particles: xn_out(:,i) = dynModel(xn_in(:,ai(i)), dx, dt, Q) with
+   normals Z [nz x N] */
+RBSLAM_API int rbslam_op_propagate(rbslam_ctx *ctx, int32_t N, const double *xn_in, const int32_t *ai,
+                        const double *dx, double dt, const double *Q, const double *Z,
+                        double *xn_out);
+/* measModel: dy [N x d x M] (MATLAB layout, particle index fastest); for the
+   sparse family xl [M x N] is required and yhat [d x N] is also returned */
+RBSLAM_API int rbslam_op_meas_jacobian(rbslam_ctx *ctx, int32_t N, const double *xn, const double *xl,
+                            double *dy, double *yhat);
+/* fused log-weight + Kalman update (src/particleFilter.m:126-151,164-204):
+   in/out xl [M x N], P [M x M x N]; H [N x d x M] MATLAB layout (NULL = evaluate the
+   model's measModel at xn); out logw [N] */
+RBSLAM_API int rbslam_op_kalman_update(rbslam_ctx *ctx, int32_t N, const double *xn, const double *H,
+                            const double *y_t, const double *R, double jitter, double *xl,
+                            double *P, double *logw);
+/* dynResNorm log-density: logwDyn[i] = -0.5*||dynResNorm(xnk_t, xn(:,i), dx, dt, Q)||^2 */
+RBSLAM_API int rbslam_op_dyn_logweight(rbslam_ctx *ctx, int32_t N, const double *xnk_t, const double *xn,
+                            const double *dx, double dt, const double *Q, int32_t use_default,
+                            double *logwDyn);
+
+/* ---- multi-GPU sharding (one process per GPU) --------------------------- */
+/* Host-only planner: given the ancestors of all N new particles and the owner
+   rank of every old particle, assign new particles to ranks so that offspring
+   stay on their ancestor's rank up to the per-rank capacity N/world; the rest
+   migrates.  Deterministic, identical on every rank.  Outputs: new_owner [N],
+   n_migrate (total). */
+RBSLAM_API int rbslam_plan_migration(int32_t N, int32_t world, const int32_t *ai, const int32_t *old_owner,
+                          int32_t *new_owner, int32_t *n_migrate);
+/* CUDA-IPC export of this rank's covariance slab allocation (64-byte handle) and
+   import of a peer's; after all peers are imported the resampling gather reads
+   ancestor slabs straight from peer HBM over NVLink. */
+RBSLAM_API int rbslam_ipc_export(rbslam_ctx *ctx, void *handle64);
+RBSLAM_API int rbslam_ipc_import(rbslam_ctx *ctx, int32_t peer_rank, const void *handle64);
+/* collective hooks supplied by the host (torch.distributed/NCCL in Python, NCCL in
+   the MEX gateway): all-gather of the per-rank log-weight blocks and a barrier.
+   Both are called with DEVICE pointers on the context's stream. */
+typedef int (*rbslam_allgather_fn)(void *user, const void *send_dev, void *recv_dev,
+                                   int64_t bytes_per_rank, void *cuda_stream);
+typedef int (*rbslam_barrier_fn)(void *user, void *cuda_stream);
+RBSLAM_API int rbslam_set_collectives(rbslam_ctx *ctx, rbslam_allgather_fn ag, rbslam_barrier_fn bar,
+                           void *user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBSLAM_H */

@@ -1,0 +1,86 @@
+// Engine state behind rbslam_ctx (one context = one GPU = one shard of particles).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/rbslam.h"
+#include "models.cuh"
+
+enum { RB_PH_RESAMPLE = 0, RB_PH_PROPAGATE, RB_PH_MEAS, RB_PH_KALMAN, RB_PH_NORMALIZE,
+       RB_PH_ANCESTOR, RB_PH_INFO, RB_PH_COUNT };
+
+struct rbslam_ctx {
+  rbslam_config cfg{};
+  rb::ModelConsts mc{};
+  int N = 0, T = 0, M = 0, d = 0, n = 0, nz = 0, nw = 0, n_odo = 0, ld = 0, ldh = 0;
+  size_t slab = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int num_sms = 148;
+  size_t smem_optin = 0;
+
+  // model constants on device
+  int *d_NN = nullptr;
+
+  // particle state
+  double *d_P = nullptr;         // [N][M cols][ld rows] covariance slabs
+  double *d_Imat = nullptr;      // information-form slabs (same slot map)
+  double *d_xl[2] = {nullptr, nullptr};     // [N][M] logical order, ping-pong
+  double *d_ivec[2] = {nullptr, nullptr};
+  double *d_hld[2] = {nullptr, nullptr};    // halfLogDetP
+  int *d_slot[2] = {nullptr, nullptr};      // logical -> physical slab
+  int *d_src_slot = nullptr, *d_first_child = nullptr, *d_free_list = nullptr;
+  int *d_listA = nullptr, *d_listB = nullptr, *d_counts = nullptr;
+  double *d_H = nullptr, *d_yhat = nullptr;
+  double *d_PHpart = nullptr, *d_G = nullptr, *d_KS = nullptr;
+  double *d_logw = nullptr, *d_w = nullptr, *d_wc = nullptr;
+  double *d_Xhist = nullptr;     // [T_hist][N][n]
+  int *d_Ahist = nullptr;        // [T_hist][N]
+  int T_hist = 2;
+  double *d_traj_max = nullptr, *d_traj_mean = nullptr;   // [T][n]
+  int *d_iwmax = nullptr;        // [T]
+  double *d_logw_hist = nullptr, *d_w_hist = nullptr;     // [T][N] optional taps
+  rb::DevStatus *d_status = nullptr;
+  double *d_scratch = nullptr;   // misc outputs (xl_mean, P_mean, ...)
+  size_t scratch_doubles = 0;
+
+  // run inputs on device
+  double *d_odo = nullptr;       // [T-1][n_odo] row-major
+  double *d_y = nullptr;         // [T][d] row-major
+  double *d_Q = nullptr;         // [pages][nw*nw]
+  double *d_R = nullptr;         // [d*d]
+  double *d_P0 = nullptr;        // [M*M]
+  double *d_x0lin = nullptr;     // [M x cols]
+  double *d_U = nullptr, *d_Z = nullptr;   // injected streams
+  int *d_forced = nullptr;
+  std::vector<double> h_dt, h_Uend;
+  std::vector<int> h_forced_ak;
+  std::vector<double> h_x0n, h_y, h_R;
+  int Q_pages = 1, x0_cols = 1, run_T = 0, run_K = 1;
+  bool have_U = false, have_Z = false, have_forced = false;
+  double jitter = 1e-3;
+
+  // progress
+  int t = 0, sweep = 0;
+  int cs = 0;   // d_slot[cs]: current logical->physical slab map
+  int cx = 0;   // d_xl[cx] (and d_ivec/d_hld): current linear-state means
+  bool running = false;
+
+  // callback / counters / timing
+  rbslam_step_fn step_fn = nullptr;
+  void *step_user = nullptr;
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  bool phase_timing = false;
+  std::vector<cudaEvent_t> ph_events;   // pairs per recorded phase
+  std::vector<int> ph_ids;
+  double phase_ms[RB_PH_COUNT] = {0};
+  cudaEvent_t user_events[16] = {nullptr};
+
+  // collectives (multi-GPU)
+  rbslam_allgather_fn ag_fn = nullptr;
+  rbslam_barrier_fn bar_fn = nullptr;
+  void *coll_user = nullptr;
+
+  void fail_cuda(cudaError_t e, const char *what, const char *file, int line);
+  int fail(int code, const std::string &msg) { err = msg; return code; }
+};

@@ -1,0 +1,51 @@
+// Internal functions shared between engine.cu (filter) and smoother.cu.
+#pragma once
+#include "engine.h"
+#include <cstdio>
+
+template <typename T>
+static inline int dev_alloc(rbslam_ctx *c, T **p, size_t count) {
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    c->fail_cuda(e, "cudaMalloc", __FILE__, __LINE__);
+    char buf[128];
+    snprintf(buf, sizeof buf, " (requested %.3f GB)", count * sizeof(T) / 1e9);
+    c->err += buf;
+    return RBSLAM_ECUDA;
+  }
+  return RBSLAM_OK;
+}
+#define RB_ALLOC(ptr, count)                                   \
+  do {                                                         \
+    int rc__ = dev_alloc(ctx, &(ptr), (size_t)(count));        \
+    if (rc__) return rc__;                                     \
+  } while (0)
+#define CK(call)                                               \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) {                                  \
+      ctx->fail_cuda(e__, #call, __FILE__, __LINE__);          \
+      return RBSLAM_ECUDA;                                     \
+    }                                                          \
+  } while (0)
+
+
+
+int rb_h2d(rbslam_ctx *ctx, void *dst, const void *src, size_t bytes);
+int rb_d2h(rbslam_ctx *ctx, void *dst, const void *src, size_t bytes);
+void rb_phase_begin(rbslam_ctx *ctx, int id);
+void rb_phase_end(rbslam_ctx *ctx);
+int rb_check_status(rbslam_ctx *ctx);
+int rb_upload_inputs(rbslam_ctx *ctx, const rbslam_inputs *in, int K);
+int rb_init_state(rbslam_ctx *ctx, bool info_form);
+int rb_resample_phase(rbslam_ctx *ctx, int n_draws);
+int rb_plan_phase(rbslam_ctx *ctx);
+int rb_propagate_phase(rbslam_ctx *ctx, int n_prop);
+int rb_meas_phase(rbslam_ctx *ctx, bool resampled);
+int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled);
+int rb_normalize_phase(rbslam_ctx *ctx);
+int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host);
+// smoother.cu
+int rb_info_init(rbslam_ctx *ctx);
+void rb_smoother_free(rbslam_ctx *ctx);

@@ -1,0 +1,389 @@
+// Per-step O(N) kernels: multinomial resampling (tools/sample.m), in-place slot
+// planning for the covariance slabs, pose propagation, measurement Jacobians and
+// log-sum-exp normalisation.
+#pragma once
+#include "models.cuh"
+
+namespace rb {
+
+// ---------------------------------------------------------------------------
+// K5a  resample: wc = cumsum(w) in strict left-to-right fp64 order (bit-exact
+// with MATLAB's cumsum / tools/sample.m:30), then ind = sum(wc < u) per draw.
+// Single CTA: the scan is a serial dependency chain by contract.
+// ---------------------------------------------------------------------------
+struct RngSrc {
+  const double *U;   // injected uniforms for this (sweep, step): [N], or nullptr
+  uint64_t seed;
+  uint32_t sweep, t;
+};
+
+__global__ void __launch_bounds__(1024)
+k_resample(int N, int n_draws, const double *__restrict__ w, double *__restrict__ wc,
+           RngSrc rng, const int *__restrict__ forced, int *__restrict__ ai,
+           DevStatus *status) {
+  extern __shared__ double s_wc[];   // N doubles if it fits, else unused (use_smem=false)
+  __shared__ int use_smem;
+  if (threadIdx.x == 0) {
+    unsigned dyn;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    use_smem = dyn >= (unsigned)N * sizeof(double);
+  }
+  __syncthreads();
+  double *buf = use_smem ? s_wc : wc;
+  if (use_smem) {
+    for (int j = threadIdx.x; j < N; j += blockDim.x) buf[j] = w[j];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // serial fp64 chain; loads are independent of the chain so they pipeline
+    double acc = 0.0;
+    const double *src = use_smem ? buf : w;
+    int j = 0;
+    for (; j + 4 <= N; j += 4) {
+      const double a0 = src[j], a1 = src[j + 1], a2 = src[j + 2], a3 = src[j + 3];
+      acc += a0; buf[j] = acc;
+      acc += a1; buf[j + 1] = acc;
+      acc += a2; buf[j + 2] = acc;
+      acc += a3; buf[j + 3] = acc;
+    }
+    for (; j < N; ++j) { acc += src[j]; buf[j] = acc; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_draws; i += blockDim.x) {
+    int idx;
+    if (forced != nullptr) {
+      idx = forced[i];
+    } else {
+      const double u = rng.U ? rng.U[i] : philox_uniform(rng.seed, rng.sweep, rng.t, i);
+      // count of wc < u == lower bound (wc is non-decreasing)
+      int lo = 0, hi = N;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (buf[mid] < u) lo = mid + 1; else hi = mid;
+      }
+      idx = lo;
+      if (idx >= N) {  // reference would raise an index error (u > wc(end))
+        idx = N - 1;
+        atomicAdd(&status->clamp_sample, 1);
+      }
+    }
+    ai[i] = idx;
+  }
+  if (use_smem && wc != nullptr) {
+    for (int j = threadIdx.x; j < N; j += blockDim.x) wc[j] = buf[j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5b  slot planning.  Covariance slabs are resampled IN PLACE: the first
+// offspring (smallest i) of an ancestor keeps the ancestor's physical slab
+// (src == dst); every further offspring is assigned the slab of a particle that
+// died (src != dst).  Lists:  listA = offspring that copy (processed first, they
+// only read surviving slabs and write dead ones), listB = offspring in place.
+// Single CTA, deterministic.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int block_excl_scan(int v, int *s_tmp, int &total) {
+  // exclusive scan of one int per thread across the block (blockDim <= 1024)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_tmp[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int t = (lane < (int)((blockDim.x + 31) >> 5)) ? s_tmp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
+    }
+    s_tmp[32 + lane] = t;  // inclusive
+  }
+  __syncthreads();
+  const int base = wid == 0 ? 0 : s_tmp[32 + wid - 1];
+  total = s_tmp[32 + ((blockDim.x + 31) >> 5) - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+__global__ void __launch_bounds__(1024)
+k_plan_slots(int N, const int *__restrict__ ai, const int *__restrict__ slot_old,
+             int *__restrict__ slot_new, int *__restrict__ src_slot, int *__restrict__ first_child,
+             int *__restrict__ free_list, int *__restrict__ listA, int *__restrict__ listB,
+             int *__restrict__ counts) {
+  __shared__ int s_tmp[64];
+  for (int a = threadIdx.x; a < N; a += blockDim.x) first_child[a] = 0x7fffffff;
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) atomicMin(&first_child[ai[i]], i);
+  __syncthreads();
+  // contiguous chunk per thread so ranks are ordered by index
+  const int per = (N + blockDim.x - 1) / blockDim.x;
+  const int b = min(N, (int)threadIdx.x * per), e = min(N, b + per);
+  int n_free = 0, n_copy = 0;
+  for (int a = b; a < e; ++a) n_free += (first_child[a] == 0x7fffffff);
+  for (int i = b; i < e; ++i) n_copy += (first_child[ai[i]] != i);
+  int tot_free, tot_copy;
+  int off_free = block_excl_scan(n_free, s_tmp, tot_free);
+  int off_copy = block_excl_scan(n_copy, s_tmp, tot_copy);
+  for (int a = b; a < e; ++a)
+    if (first_child[a] == 0x7fffffff) free_list[off_free++] = slot_old[a];
+  __syncthreads();
+  int off_keep = b - off_copy;  // in-place offspring before this chunk
+  for (int i = b; i < e; ++i) {
+    const int a = ai[i];
+    const int s = slot_old[a];
+    src_slot[i] = s;
+    if (first_child[a] == i) {
+      slot_new[i] = s;
+      listB[off_keep++] = i;
+    } else {
+      slot_new[i] = free_list[off_copy];
+      listA[off_copy++] = i;
+    }
+  }
+  if (threadIdx.x == 0) {
+    counts[0] = tot_copy;       // nA
+    counts[1] = N - tot_copy;   // nB
+  }
+}
+
+// identity plan for the first time step (no resampling): everything in place
+__global__ void k_plan_identity(int N, const int *__restrict__ slot, int *__restrict__ src_slot,
+                                int *__restrict__ listB, int *__restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) { src_slot[i] = slot[i]; listB[i] = i; }
+  if (i == 0) { counts[0] = 0; counts[1] = N; }
+}
+
+// ---------------------------------------------------------------------------
+// K1  propagate: xn_new(:,i) = dynModel(xn_old(:,ai(i)), odometry(t-1,:), dt, Q)
+// (src/particleFilter.m:104-109).  One thread per particle.
+// ---------------------------------------------------------------------------
+struct NormalSrc {
+  const double *Z;   // injected normals for this (sweep, step): [nz x N] or nullptr
+  uint64_t seed;
+  uint32_t sweep, t;
+};
+
+__global__ void k_propagate(ModelConsts mc, int N, int n_prop, const double *__restrict__ xn_old,
+                            const int *__restrict__ ai, const double *__restrict__ dx, double dt,
+                            const double *__restrict__ Q, NormalSrc nsrc,
+                            double *__restrict__ xn_new) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_prop) return;
+  double z[6] = {0, 0, 0, 0, 0, 0};
+  if (nsrc.Z) {
+    for (int j = 0; j < mc.nz; ++j) z[j] = nsrc.Z[j + (size_t)i * mc.nz];
+  } else {
+    for (int p = 0; 2 * p < mc.nz; ++p)
+      philox_normal_pair(nsrc.seed, nsrc.sweep, nsrc.t, i, p, z[2 * p], z[2 * p + 1]);
+  }
+  double xin[7], xo[7], dxl[7];
+  const int a = ai[i];
+  for (int j = 0; j < mc.n; ++j) xin[j] = xn_old[j + (size_t)a * mc.n];
+  for (int j = 0; j < mc.n_odo; ++j) dxl[j] = dx[j];
+  dyn_model(mc, xin, dxl, dt, Q, z, xo);
+  for (int j = 0; j < mc.n; ++j) xn_new[j + (size_t)i * mc.n] = xo[j];
+}
+
+// logwDyn[i] = -0.5*||dynResNorm(xnk_t, xn(:,i), ...)||^2
+__global__ void k_dyn_logweight(ModelConsts mc, int N, const double *__restrict__ xnk_t,
+                                const double *__restrict__ xn, const double *__restrict__ dx,
+                                double dt, const double *__restrict__ Q, int use_default,
+                                double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double xk[7], xi[7], dxl[7];
+  for (int j = 0; j < mc.n; ++j) { xk[j] = xnk_t[j]; xi[j] = xn[j + (size_t)i * mc.n]; }
+  for (int j = 0; j < mc.n_odo; ++j) dxl[j] = dx[j];
+  out[i] = dyn_logweight(mc, xk, xi, dxl, dt, Q, use_default != 0);
+}
+
+// ---------------------------------------------------------------------------
+// K2  measurement Jacobian H_i [d x M] (row-contiguous, leading dim ldh) at each
+// particle's pose.  One CTA per particle.  Separable eigenbasis: sin/cos tables
+// per dimension in shared memory, then one product per basis function.
+//   dense-mag  : H = Rnb(q)' * [I3, dPhi/dx; dPhi/dy; dPhi/dz]  (run_dense3D_magfield.m:265-279)
+//   dense-radio: H = Phi(pos)                                    (run_dense2D_withHeading.m:168)
+//   sparse     : pinhole projection + Jacobian wrt landmarks     (measurement.m:32-84)
+// ---------------------------------------------------------------------------
+#define RB_MAXTAB 96
+__global__ void __launch_bounds__(128)
+k_meas(ModelConsts mc, int N, const double *__restrict__ xn, const double *__restrict__ xl,
+       int ldxl, const int *__restrict__ xl_index, double *__restrict__ H, int ldh,
+       double *__restrict__ yhat) {
+  const int i = blockIdx.x;
+  if (i >= N) return;
+  __shared__ double s_sin[3][RB_MAXTAB], s_cos[3][RB_MAXTAB];
+  __shared__ double s_x[7];
+  if (threadIdx.x < mc.n) s_x[threadIdx.x] = xn[threadIdx.x + (size_t)i * mc.n];
+  __syncthreads();
+  double *Hi = H + (size_t)i * mc.d * ldh;
+  if (mc.family == FAM_SPARSE_VISUAL2D) {
+    // measurement.m:36-50 (projection) and :59-79 (Jacobian wrt map)
+    const double *xli = xl + (size_t)(xl_index ? xl_index[i] : i) * ldxl;
+    double s, c;
+    sincos(s_x[2], &s, &c);
+    for (int idx = threadIdx.x; idx < mc.d * ldh; idx += blockDim.x) Hi[idx] = 0.0;
+    __syncthreads();
+    for (int l = threadIdx.x; l < mc.m; l += blockDim.x) {
+      const double m1 = xli[2 * l], m2 = xli[2 * l + 1];
+      const double p1 = s_x[0], p2 = s_x[1];
+      // u = K*[R' -R'*p]*[map;1],  R = [c -s; s c]
+      const double t1 = -(c * p1 + s * p2), t2 = -(-s * p1 + c * p2);
+      const double lx = c * m1 + s * m2 + t1;
+      const double ly = -s * m1 + c * m2 + t2;
+      const double u1 = mc.cam_f * lx + mc.cam_fp * ly;
+      yhat[l + (size_t)i * mc.d] = u1 / ly;
+      const double dv = m2 * c - p2 * c - m1 * s + p1 * s;
+      const double div = dv * dv;
+      Hi[(size_t)l * ldh + 2 * l] = (mc.cam_f * (m2 - p2)) / div;
+      Hi[(size_t)l * ldh + 2 * l + 1] = -(mc.cam_f * (m1 - p1)) / div;
+    }
+    return;
+  }
+  // sin/cos tables: arg = pi*n*(x+L)/(2L)  (tools/domain_cartesian_dx.m:88-91)
+  for (int idx = threadIdx.x; idx < mc.dim * RB_MAXTAB; idx += blockDim.x) {
+    const int j = idx / RB_MAXTAB, nn = idx % RB_MAXTAB;
+    if (nn >= 1 && nn <= mc.maxn[j]) {
+      const double arg = (RB_PI * (double)nn) * (s_x[j] + mc.L[j]) / (2.0 * mc.L[j]);
+      double s, c;
+      sincos(arg, &s, &c);
+      s_sin[j][nn] = s;
+      s_cos[j][nn] = c;
+    }
+  }
+  __syncthreads();
+  if (mc.family == FAM_DENSE_RADIO2D) {
+    const double r0 = sqrt(mc.L[0]), r1 = sqrt(mc.L[1]);
+    for (int cidx = threadIdx.x; cidx < mc.m; cidx += blockDim.x) {
+      const int n0 = mc.NN[cidx], n1 = mc.NN[cidx + mc.m];
+      double v = 1.0;
+      v = v * 1.0 / r0 * s_sin[0][n0];
+      v = v * 1.0 / r1 * s_sin[1][n1];
+      Hi[cidx] = v;
+    }
+    for (int cidx = mc.m + threadIdx.x; cidx < ldh; cidx += blockDim.x) Hi[cidx] = 0.0;
+    return;
+  }
+  // dense-mag
+  double Rnb[3][3];
+  quat2rmat(s_x + 3, Rnb);
+  const double rL[3] = {sqrt(mc.L[0]), sqrt(mc.L[1]), sqrt(mc.L[2])};
+  for (int cidx = threadIdx.x; cidx < ldh; cidx += blockDim.x) {
+    double g[3];
+    if (cidx < 3) {
+      g[0] = cidx == 0; g[1] = cidx == 1; g[2] = cidx == 2;
+    } else if (cidx < mc.M) {
+      const int b = cidx - 3;
+      const int nn[3] = {mc.NN[b], mc.NN[b + mc.m], mc.NN[b + 2 * mc.m]};
+#pragma unroll
+      for (int di = 0; di < 3; ++di) {
+        double v = 1.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (j == di)  // tools/domain_cartesian_dx.m:153-154
+            v = v * RB_PI * (double)nn[j] / (2.0 * mc.L[j] * rL[j]) * s_cos[j][nn[j]];
+          else          // :157-158
+            v = v * 1.0 / rL[j] * s_sin[j][nn[j]];
+        }
+        g[di] = v;
+      }
+    } else {
+      g[0] = g[1] = g[2] = 0.0;
+    }
+    // H(a, c) = sum_b Rnb(b, a) * g_b   (Rnb' * dPhi)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      Hi[(size_t)a * ldh + cidx] = Rnb[0][a] * g[0] + Rnb[1][a] * g[1] + Rnb[2][a] * g[2];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4  normalise (src/particleFilter.m:153-161): c=max, lse, w=exp(logw-lse),
+// iw_max = first argmax(w), traj_max(:,t), traj_mean(:,t) = sum(xn.*w,2).
+// Single CTA with a fixed reduction tree: the result does not depend on how
+// many GPUs produced logw.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_normalize(int N, int n, const double *__restrict__ logw, double *__restrict__ w,
+            const double *__restrict__ xn, double *__restrict__ traj_max_t,
+            double *__restrict__ traj_mean_t, int *__restrict__ iw_max_out,
+            double *__restrict__ logw_hist_t, double *__restrict__ w_hist_t) {
+  __shared__ double s_red[32];
+  __shared__ int s_idx[32];
+  __shared__ double s_bcast;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double m = -INFINITY;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmax(m, logw[i]);
+  m = warp_max(m);
+  if (lane == 0) s_red[wid] = m;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < nwarp ? s_red[lane] : -INFINITY;
+    v = warp_max(v);
+    if (lane == 0) s_bcast = v;
+  }
+  __syncthreads();
+  const double c = s_bcast;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += exp(logw[i] - c);
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) s_red[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < nwarp ? s_red[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) s_bcast = c + log(v);
+  }
+  __syncthreads();
+  const double lse = s_bcast;
+  double best = -1.0;
+  int bidx = 0x7fffffff;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double wi = exp(logw[i] - lse);
+    w[i] = wi;
+    if (logw_hist_t) logw_hist_t[i] = logw[i];
+    if (w_hist_t) w_hist_t[i] = wi;
+    if (wi > best) { best = wi; bidx = i; }   // strided ascending i: first index kept on ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { s_red[wid] = best; s_idx[wid] = bidx; }
+  __syncthreads();
+  if (wid == 0) {
+    best = lane < nwarp ? s_red[lane] : -1.0;
+    bidx = lane < nwarp ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { s_idx[0] = bidx; if (iw_max_out) *iw_max_out = bidx; }
+  }
+  __syncthreads();
+  const int imax = s_idx[0];
+  if (xn == nullptr) return;
+  if (threadIdx.x < n && traj_max_t) traj_max_t[threadIdx.x] = xn[threadIdx.x + (size_t)imax * n];
+  // weighted mean: one warp per state component, fixed order
+  if (traj_mean_t) {
+    for (int j = wid; j < n; j += nwarp) {
+      double acc = 0.0;
+      for (int i = lane; i < N; i += 32) acc += xn[j + (size_t)i * n] * w[i];
+      acc = warp_sum(acc);
+      if (lane == 0) traj_mean_t[j] = acc;
+    }
+  }
+}
+
+}  // namespace rb

@@ -1,0 +1,433 @@
+"""Host-side mirror of the reference's three inference entry points.
+
+Same names, positional arguments and outputs as
+  src/particleFilter.m:1-3, src/particleSmoother.m:1-2,
+  src/particleSmootherInformationForm.m:1-2
+(the reference's toolchain, MATLAB, is absent from the build image, so the host
+side above the C ABI is Python here; ``matlab/*.m`` + ``mex/rbslam_mex.cpp`` are
+the MATLAB-side twins).  All arithmetic happens in librbslam.so on the GPU.
+
+Differences a caller sees:
+  * ``dynModel`` / ``measModel`` / ``dynResNorm`` are model handles from
+    ``rbslam.models`` (descriptor of one of the reference's closure families);
+  * randomness is explicit: ``rng=<int seed>`` selects the device Philox stream,
+    ``rng=<object with U, Z, Uend arrays>`` injects pre-drawn numbers (what the
+    MATLAB shim does in compat mode so that MATLAB's own rand/randn are used).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from . import models as _models
+
+
+def _as_streams(rng):
+    if rng is None:
+        return _capi.RNG_PHILOX, 0, None
+    if isinstance(rng, (int, np.integer)):
+        return _capi.RNG_PHILOX, int(rng), None
+    if hasattr(rng, "U") and hasattr(rng, "Z"):
+        return _capi.RNG_INJECTED, 0, rng
+    raise TypeError("rng must be an int seed or an object with U/Z/Uend arrays")
+
+
+class Context:
+    """Owns one rbslam_ctx (one GPU)."""
+
+    def __init__(self, model, N, T, device=0, rng_mode=_capi.RNG_PHILOX, seed=0,
+                 information_form=False, keep_history=True, ld=0, kalman_variant=0):
+        self._lib = _capi.lib()
+        self.model = model
+        self.N, self.T = int(N), int(T)
+        cfg = _capi.Config()
+        cfg.struct_size = C.sizeof(_capi.Config)
+        cfg.device = device
+        cfg.model = model.family
+        cfg.N, cfg.T, cfg.m_basis = self.N, self.T, model.m_basis
+        self._keep = [model.NN, model.L]
+        cfg.NN = _capi.iptr(model.NN)
+        cfg.L = _capi.dptr(model.L)
+        cam = getattr(model, "camera", (0.0, 0.0, 0.0))
+        cfg.cam_f, cfg.cam_fp, cfg.cam_fw = cam
+        cfg.rng_mode = rng_mode
+        cfg.seed = seed
+        cfg.ld = ld
+        cfg.information_form = int(information_form)
+        cfg.keep_history = int(keep_history)
+        cfg.rank, cfg.world = 0, 1
+        cfg.kalman_variant = kalman_variant
+        self._h = C.c_void_p()
+        rc = self._lib.rbslam_create(C.byref(self._h), C.byref(cfg))
+        if rc != _capi.OK:
+            msg = self._lib.rbslam_last_error(None) or b""
+            self._h = C.c_void_p()
+            err = _capi.UnsupportedModelError if rc == _capi.EMODEL else _capi.RbslamError
+            raise err(rc, msg.decode())
+        dims = (C.c_int32 * 7)()
+        self._lib.rbslam_dims(self._h, dims)
+        self.n, self.d, self.M, self.nz, self.nw, self.n_odo, self.ld = list(dims)
+        self._cb = None
+
+    # -- life cycle ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.rbslam_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        _capi.check(self._h, rc)
+
+    # -- inputs -------------------------------------------------------------
+    def _inputs(self, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams, K=1,
+                forced_ancestors=None, forced_ak=None):
+        keep = []
+
+        def F(a):
+            a = _capi.fcol(a)
+            keep.append(a)
+            return a
+
+        y = np.asarray(y, dtype=np.float64)
+        if y.ndim == 1:
+            y = y.reshape(-1, 1)
+        T = y.shape[0]
+        if y.shape[1] != self.d:
+            raise ValueError("y must be [N_T x %d]" % self.d)
+        inp = _capi.Inputs()
+        inp.T = T
+        odometry = np.atleast_2d(np.asarray(odometry, dtype=np.float64))
+        if T > 1 and (odometry.shape[1] != self.n_odo or odometry.shape[0] < T - 1):
+            raise ValueError("odometry must be [>=N_T-1 x %d]" % self.n_odo)
+        odo = F(odometry)
+        inp.odometry, inp.odo_rows = _capi.dptr(odo), odo.shape[0]
+        inp.y = _capi.dptr(F(y))
+        x0n = F(np.asarray(x0_nonLin, dtype=np.float64).reshape(-1))
+        if x0n.shape[0] != self.n:
+            raise ValueError("x0_nonLin must have %d entries" % self.n)
+        inp.x0_nonLin = _capi.dptr(x0n)
+        x0l = np.asarray(x0_lin, dtype=np.float64)
+        if x0l.ndim == 1:
+            x0l = x0l.reshape(-1, 1)
+        if x0l.shape[0] != self.M or x0l.shape[1] not in (1, self.N):
+            raise ValueError("x0_lin must be [%d x 1] or [%d x %d]" % (self.M, self.M, self.N))
+        inp.x0_lin, inp.x0_lin_cols = _capi.dptr(F(x0l)), x0l.shape[1]
+        P0 = np.asarray(P0_lin, dtype=np.float64)
+        if P0.shape != (self.M, self.M):
+            raise ValueError("P0_lin must be [%d x %d]" % (self.M, self.M))
+        inp.P0_lin = _capi.dptr(F(P0))
+        Q = np.asarray(Q, dtype=np.float64)
+        if Q.ndim < 2:
+            Q = Q.reshape(1, 1)
+        if Q.ndim == 2:
+            Q = Q[:, :, None]
+        if Q.shape[0] != self.nw or Q.shape[1] != self.nw:
+            raise ValueError("Q must be [%d x %d (x pages)]" % (self.nw, self.nw))
+        inp.Q, inp.Q_pages = _capi.dptr(F(Q)), Q.shape[2]
+        R = np.atleast_2d(np.asarray(R, dtype=np.float64))
+        if R.shape != (self.d, self.d):
+            raise ValueError("R must be [%d x %d]" % (self.d, self.d))
+        inp.R = _capi.dptr(F(R))
+        dtv = F(np.asarray(dt, dtype=np.float64).reshape(-1))
+        inp.dt, inp.dt_len = _capi.dptr(dtv), dtv.shape[0]
+        if streams is not None:
+            U = np.ascontiguousarray(np.asarray(streams.U, dtype=np.float64))      # [K,T,N]
+            Z = np.ascontiguousarray(np.asarray(streams.Z, dtype=np.float64))      # [K,T,N,nz]
+            if U.shape[0] < K or U.shape[1:] != (T, self.N):
+                raise ValueError("streams.U must be [>=%d, %d, %d]" % (K, T, self.N))
+            if Z.shape[0] < K or Z.shape[1:] != (T, self.N, self.nz):
+                raise ValueError("streams.Z must be [>=%d, %d, %d, %d]" % (K, T, self.N, self.nz))
+            keep += [U, Z]
+            inp.U, inp.Z = _capi.dptr(U), _capi.dptr(Z)
+            Uend = getattr(streams, "Uend", None)
+            if Uend is not None:
+                Uend = np.ascontiguousarray(np.asarray(Uend, dtype=np.float64))
+                keep.append(Uend)
+                inp.Uend = _capi.dptr(Uend)
+        if forced_ancestors is not None:
+            fa = np.ascontiguousarray(np.asarray(forced_ancestors, dtype=np.int32))
+            if fa.ndim == 2:
+                fa = fa[None]
+            if fa.shape[0] < K or fa.shape[1:] != (T, self.N):
+                raise ValueError("forced_ancestors must be [K, T, N]")
+            keep.append(fa)
+            inp.forced_ancestors = _capi.iptr(fa)
+        if forced_ak is not None:
+            fk = np.ascontiguousarray(np.asarray(forced_ak, dtype=np.int32).reshape(-1))
+            keep.append(fk)
+            inp.forced_ak = _capi.iptr(fk)
+        return inp, keep, T
+
+    # -- filter -------------------------------------------------------------
+    def _filter_outputs(self, T, want_xn_traj=True, taps=False):
+        n, N, M = self.n, self.N, self.M
+        o = dict(traj_max=np.zeros((n, T), order="F"), traj_mean=np.zeros((n, T), order="F"),
+                 xl_max=np.zeros(M), xl_mean=np.zeros(M), P_max=np.zeros((M, M), order="F"),
+                 P_mean=np.zeros((M, M), order="F"),
+                 traj_sample_iwmax=np.zeros((n, T), order="F"))
+        if want_xn_traj:
+            o["xn_traj"] = np.zeros((n, N, T), order="F")
+        if taps:
+            o["logw_hist"] = np.zeros((N, T), order="F")
+            o["w_hist"] = np.zeros((N, T), order="F")
+            o["ancestors"] = np.zeros((N, T), dtype=np.int32, order="F")
+        out = _capi.FilterOutputs()
+        for k, v in o.items():
+            setattr(out, k, _capi.iptr(v) if v.dtype == np.int32 else _capi.dptr(v))
+        return out, o
+
+    def filter_run(self, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams=None,
+                   forced_ancestors=None, want_xn_traj=True, taps=False):
+        inp, keep, T = self._inputs(odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams,
+                                    forced_ancestors=forced_ancestors)
+        out, o = self._filter_outputs(T, want_xn_traj, taps)
+        self._ck(self._lib.rbslam_filter_run(self._h, C.byref(inp), C.byref(out)))
+        return o
+
+    def filter_begin(self, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams=None,
+                     forced_ancestors=None):
+        inp, keep, T = self._inputs(odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams,
+                                    forced_ancestors=forced_ancestors)
+        self._ck(self._lib.rbslam_filter_begin(self._h, C.byref(inp)))
+        self._run_T = T
+
+    def filter_step(self):
+        self._ck(self._lib.rbslam_filter_step(self._h))
+
+    def filter_end(self, T=None, want_xn_traj=False):
+        out, o = self._filter_outputs(self._run_T if T is None else T, want_xn_traj, False)
+        o.pop("traj_sample_iwmax")
+        out.traj_sample_iwmax = None
+        self._ck(self._lib.rbslam_filter_end(self._h, C.byref(out)))
+        return o
+
+    def sync(self):
+        self._ck(self._lib.rbslam_sync(self._h))
+
+    def read_particles(self, P=True):
+        n, N, M = self.n, self.N, self.M
+        xn = np.zeros((n, N), order="F")
+        xl = np.zeros((M, N), order="F")
+        Pm = np.zeros((M, M, N), order="F") if P else None
+        logw, w = np.zeros(N), np.zeros(N)
+        ai = np.zeros(N, dtype=np.int32)
+        self._ck(self._lib.rbslam_read_particles(self._h, _capi.dptr(xn), _capi.dptr(xl),
+                                                 _capi.dptr(Pm), _capi.dptr(logw), _capi.dptr(w),
+                                                 _capi.iptr(ai)))
+        return dict(xn=xn, xl=xl, P=Pm, logw=logw, w=w, ai=ai)
+
+    def read_information(self):
+        N, M = self.N, self.M
+        ivec = np.zeros((M, N), order="F")
+        Imat = np.zeros((M, M, N), order="F")
+        hld = np.zeros(N)
+        self._ck(self._lib.rbslam_read_information(self._h, _capi.dptr(ivec), _capi.dptr(Imat),
+                                                   _capi.dptr(hld)))
+        return dict(ivec=ivec, Imat=Imat, halfLogDetP=hld)
+
+    def set_step_callback(self, fn):
+        """fn(sweep, t) is called after every time step (the makePlots hook)."""
+        if fn is None:
+            self._cb = _capi.STEP_FN()
+        else:
+            self._cb = _capi.STEP_FN(lambda user, k, t: fn(k, t))
+        self._ck(self._lib.rbslam_step_callback(self._h, self._cb, None))
+
+    # -- smoother -----------------------------------------------------------
+    def smoother_run(self, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, dt, N_K, form=0,
+                     streams=None, forced_ancestors=None, forced_ak=None, want_AI=False):
+        inp, keep, T = self._inputs(odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams,
+                                    K=N_K, forced_ancestors=forced_ancestors, forced_ak=forced_ak)
+        n, N, M = self.n, self.N, self.M
+        o = dict(XNK=np.zeros((n, T, N_K), order="F"), XLK=np.zeros((M, N_K), order="F"),
+                 PK=np.zeros((M, M, N_K), order="F"), ak=np.zeros(N_K, dtype=np.int32))
+        if want_AI:
+            o["AI"] = np.full((N, T, N_K), np.nan, order="F")
+        out = _capi.SmootherOutputs()
+        out.XNK, out.XLK, out.PK = _capi.dptr(o["XNK"]), _capi.dptr(o["XLK"]), _capi.dptr(o["PK"])
+        out.ak = _capi.iptr(o["ak"])
+        out.AI = _capi.dptr(o.get("AI"))
+        self._ck(self._lib.rbslam_smoother_run(self._h, C.byref(inp), N_K, form, C.byref(out)))
+        return o
+
+    # -- timing / counters ---------------------------------------------------
+    def event_record(self, slot):
+        self._ck(self._lib.rbslam_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._ck(self._lib.rbslam_event_elapsed(self._h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def phase_timing(self, enable):
+        self._ck(self._lib.rbslam_phase_timing(self._h, int(enable)))
+
+    def phase_times(self):
+        ms = np.zeros(8)
+        self._ck(self._lib.rbslam_phase_times(self._h, _capi.dptr(ms)))
+        return dict(zip(["resample", "propagate", "meas", "kalman", "normalize", "ancestor",
+                         "info", "reserved"], ms.tolist()))
+
+    def counters(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self._lib.rbslam_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
+
+    # -- kernel-level ops (parity tests) --------------------------------------
+    def op_resample(self, w, u):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        ai = np.zeros(u.shape[0], dtype=np.int32)
+        self._ck(self._lib.rbslam_op_resample(self._h, w.shape[0], _capi.dptr(w), u.shape[0],
+                                              _capi.dptr(u), _capi.iptr(ai)))
+        return ai
+
+    def op_normalize(self, logw):
+        logw = np.ascontiguousarray(logw, dtype=np.float64)
+        w = np.zeros_like(logw)
+        im = C.c_int32()
+        self._ck(self._lib.rbslam_op_normalize(self._h, logw.shape[0], _capi.dptr(logw),
+                                               _capi.dptr(w), C.byref(im)))
+        return w, int(im.value)
+
+    def op_propagate(self, xn_in, ai, dx, dt, Q, Z=None):
+        xn_in = _capi.fcol(xn_in)
+        N = xn_in.shape[1]
+        ai = np.ascontiguousarray(ai, dtype=np.int32)
+        dx = np.ascontiguousarray(dx, dtype=np.float64)
+        Q = _capi.fcol(np.atleast_2d(Q))
+        Zc = None if Z is None else np.ascontiguousarray(Z, dtype=np.float64)   # [N, nz]
+        out = np.zeros_like(xn_in, order="F")
+        self._ck(self._lib.rbslam_op_propagate(self._h, N, _capi.dptr(xn_in), _capi.iptr(ai),
+                                               _capi.dptr(dx), float(dt), _capi.dptr(Q),
+                                               _capi.dptr(Zc), _capi.dptr(out)))
+        return out
+
+    def op_meas_jacobian(self, xn, xl=None):
+        xn = _capi.fcol(xn)
+        N = xn.shape[1]
+        xlc = None if xl is None else _capi.fcol(xl)
+        dy = np.zeros((N, self.d, self.M), order="F")
+        yhat = np.zeros((self.d, N), order="F")
+        self._ck(self._lib.rbslam_op_meas_jacobian(self._h, N, _capi.dptr(xn), _capi.dptr(xlc),
+                                                   _capi.dptr(dy), _capi.dptr(yhat)))
+        return dy, yhat
+
+    def op_kalman_update(self, xl, P, y_t, R, jitter=1e-3, H=None, xn=None):
+        """xl [M x N], P [M x M x N] (MATLAB layout), H [N x d x M]; returns updated copies."""
+        xl = np.array(xl, dtype=np.float64, order="F")
+        P = np.array(P, dtype=np.float64, order="F")
+        N = xl.shape[1]
+        Hc = None if H is None else _capi.fcol(H)
+        xnc = None if xn is None else _capi.fcol(xn)
+        y_t = np.ascontiguousarray(y_t, dtype=np.float64)
+        R = _capi.fcol(np.atleast_2d(R))
+        logw = np.zeros(N)
+        self._ck(self._lib.rbslam_op_kalman_update(self._h, N, _capi.dptr(xnc), _capi.dptr(Hc),
+                                                   _capi.dptr(y_t), _capi.dptr(R), float(jitter),
+                                                   _capi.dptr(xl), _capi.dptr(P), _capi.dptr(logw)))
+        return xl, P, logw
+
+    def op_dyn_logweight(self, xnk_t, xn, dx, dt, Q, use_default=False):
+        xn = _capi.fcol(xn)
+        N = xn.shape[1]
+        xk = np.ascontiguousarray(xnk_t, dtype=np.float64)
+        dx = np.ascontiguousarray(dx, dtype=np.float64)
+        Q = _capi.fcol(np.atleast_2d(Q))
+        out = np.zeros(N)
+        self._ck(self._lib.rbslam_op_dyn_logweight(self._h, N, _capi.dptr(xk), _capi.dptr(xn),
+                                                   _capi.dptr(dx), float(dt), _capi.dptr(Q),
+                                                   int(use_default), _capi.dptr(out)))
+        return out
+
+
+def plan_migration(ai, old_owner, world):
+    """Host-only planner (rbslam_plan_migration): returns (new_owner [N], n_migrate)."""
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    oo = np.ascontiguousarray(old_owner, dtype=np.int32)
+    no = np.zeros_like(ai)
+    nm = C.c_int32()
+    rc = _capi.lib().rbslam_plan_migration(ai.shape[0], int(world), _capi.iptr(ai), _capi.iptr(oo),
+                                           _capi.iptr(no), C.byref(nm))
+    if rc != _capi.OK:
+        raise _capi.RbslamError(rc, "plan_migration: bad arguments")
+    return no, int(nm.value)
+
+
+# ---------------------------------------------------------------------------
+# the three drop-in entry points
+# ---------------------------------------------------------------------------
+def particleFilter(dynModel, measModel, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P, dt,
+                   sparseFeatures=None, makePlots=None, *, rng=None, device=0, **ctx_kw):
+    """Rao-Blackwellized particle filter; signature of src/particleFilter.m:1-3.
+
+    Returns (traj_max, traj_mean, xl_max, xl_mean, P_max, P_mean, traj_sample_iwmax, xn_traj).
+    """
+    model = _models.resolve(dynModel, measModel)
+    if sparseFeatures is None or (isinstance(sparseFeatures, (list, tuple)) and not sparseFeatures):
+        sparseFeatures = False        # src/particleFilter.m:85
+    if bool(sparseFeatures) != bool(model.sparse):
+        raise _capi.UnsupportedModelError(_capi.EMODEL, "sparseFeatures does not match the model family")
+    mode, seed, streams = _as_streams(rng)
+    yy = np.asarray(y, dtype=np.float64)
+    T = yy.shape[0]
+    with Context(model, N_P, T, device=device, rng_mode=mode, seed=seed, **ctx_kw) as ctx:
+        if makePlots is not None:
+            def _cb(k, t, ctx=ctx):
+                st = ctx.read_particles()
+                makePlots(t, st)
+            ctx.set_step_callback(_cb)
+        o = ctx.filter_run(odometry, yy, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams)
+    return (o["traj_max"], o["traj_mean"], o["xl_max"], o["xl_mean"], o["P_max"], o["P_mean"],
+            o["traj_sample_iwmax"], o["xn_traj"])
+
+
+def _smoother(form, dynModel, measModel, dynResNorm, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R,
+              N_P, N_K, dt, sparseFeatures, makePlots, rng, device, ctx_kw):
+    model = _models.resolve(dynModel, measModel, dynResNorm)
+    if sparseFeatures is None:
+        sparseFeatures = False
+    if bool(sparseFeatures) != bool(model.sparse):
+        raise _capi.UnsupportedModelError(_capi.EMODEL, "sparseFeatures does not match the model family")
+    if form == 1 and sparseFeatures:
+        # src/particleSmootherInformationForm.m:77-80
+        print("This code has only been implemented for dense features")
+        return None
+    mode, seed, streams = _as_streams(rng)
+    yy = np.asarray(y, dtype=np.float64)
+    T = yy.shape[0]
+    with Context(model, N_P, T, device=device, rng_mode=mode, seed=seed,
+                 information_form=(form == 1), **ctx_kw) as ctx:
+        o = ctx.smoother_run(odometry, yy, x0_nonLin, x0_lin, P0_lin, Q, R, dt, N_K, form, streams)
+    if makePlots is not None:
+        for k in range(N_K):
+            makePlots(o["XNK"][:, :, k], o["XLK"][:, k], k, o["XNK"], o["XLK"], o["PK"])
+    return o["XNK"], o["XLK"], o["PK"]
+
+
+def particleSmoother(dynModel, measModel, dynResNorm, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R,
+                     N_P, N_K, dt, sparseFeatures=None, makePlots=None, *, rng=None, device=0,
+                     **ctx_kw):
+    """Rao-Blackwellized particle smoother; signature of src/particleSmoother.m:1-2."""
+    return _smoother(0, dynModel, measModel, dynResNorm, odometry, y, x0_nonLin, x0_lin, P0_lin, Q,
+                     R, N_P, N_K, dt, sparseFeatures, makePlots, rng, device, ctx_kw)
+
+
+def particleSmootherInformationForm(dynModel, measModel, dynResNorm, odometry, y, x0_nonLin, x0_lin,
+                                    P0_lin, Q, R, N_P, N_K, dt, sparseFeatures=None, makePlots=None,
+                                    *, rng=None, device=0, **ctx_kw):
+    """Information-form RBPS; signature of src/particleSmootherInformationForm.m:1-2."""
+    return _smoother(1, dynModel, measModel, dynResNorm, odometry, y, x0_nonLin, x0_lin, P0_lin, Q,
+                     R, N_P, N_K, dt, sparseFeatures, makePlots, rng, device, ctx_kw)
