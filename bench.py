@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the Rao-Blackwellized particle filter hot path.
+
+Workload (config C4 of BASELINE.json, the one the metric and the >=70 % target are
+quoted on): dense-mag 3-D SLAM, N = 10^4 particles, m = 1024 basis functions
+(M = 1027 linear states, 84.8 GB of fp64 covariance slabs), synthetic bean-6D
+trajectory.  One "step" is one time step of the filter recursion over all N
+particles (resample + propagate + basis/Jacobian + fused gather/log-weight/Kalman
+update + normalise).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
+    python bench.py --impl reference --steps K --warmup W    # CPU oracle port
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "rao-blackwellized-slam-smoothing_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "particle-steps/sec (N*T/s) at m basis fns"
+UNIT = "particle-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--particles", type=int, default=10000, help="N_P per GPU (C4: 10^4)")
+    ap.add_argument("--basis", type=int, default=1024, help="m eigenfunctions (C4: 1024)")
+    ap.add_argument("--variant", type=int, default=0, help="kalman kernel variant (0=auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-particles", type=int, default=64)
+    ap.add_argument("--cpu-sample-steps", type=int, default=4)
+    return ap.parse_args()
+
+
+def make_problem(m, n_steps):
+    """C4 synthetic inputs: bean-6D path, 10 laps over T=2000, theta/Q of the example."""
+    from rbslam import synth
+    T_full = 2000
+    pr = synth.dense_mag_problem(N_T=T_full, m=m, seed=1, n_laps=10, m_sim=2000)
+    T = min(T_full, n_steps)
+    pr["y"] = pr["y"][:T].copy()
+    pr["odometry"] = pr["odometry"][:T].copy()
+    return pr, T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(M):
+    """DRAM bytes per Kalman-update launch set from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d.get(str(M))
+        except Exception:
+            pass
+    return None
+
+
+def cpu_baseline(pr, m, n_particles, n_steps):
+    """Oracle port timed on the host cores, bounded sample of the same workload."""
+    import oracle
+    from oracle.parallel_filter import filter_steps_timed
+    om = oracle.DenseMag3D(pr["NN"], pr["L"])
+    T = n_steps + 2
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(0), 1, T, n_particles, om.nz)
+    secs, cores = filter_steps_timed(om, pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"],
+                                     pr["P0_lin"], pr["Q"], pr["R"], n_particles, pr["dt"], st,
+                                     n_steps=n_steps, warmup=1)
+    return {"value": n_particles * n_steps / secs, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "N=%d particles x %d steps at M=%d (oracle NumPy/OpenBLAS port of "
+                      "src/particleFilter.m, thread per particle chunk, 1 BLAS thread each)"
+                      % (n_particles, n_steps, m + 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Np = args.cpu_sample_particles
+    K, W = args.steps, args.warmup
+    pr, _ = make_problem(args.basis, K + W + 2)
+    import oracle
+    from oracle.parallel_filter import filter_steps_timed
+    om = oracle.DenseMag3D(pr["NN"], pr["L"])
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(0), 1, K + W + 1, Np, om.nz)
+    secs, cores = filter_steps_timed(om, pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"],
+                                     pr["P0_lin"], pr["Q"], pr["R"], Np, pr["dt"], st,
+                                     n_steps=K, warmup=max(W, 1))
+    val = Np * K / secs
+    sample = ("each step = %d particles of the C4 workload (M=%d); oracle NumPy/OpenBLAS port of "
+              "src/particleFilter.m on %d host threads; MATLAB/Octave are not installed"
+              % (Np, args.basis + 3, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 dense-mag scale-up, m=%d (M=%d), bounded sample of %d particles"
+                                   % (args.basis, args.basis + 3, Np)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args):
+    import rbslam
+    from rbslam import _capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if _capi.lib().rbslam_device_count() < 1:
+        raise RuntimeError("no CUDA device: the product path has no CPU fallback")
+
+    K, W = args.steps, max(args.warmup, 3)
+    N, m = args.particles, args.basis
+    # step 0 has no resampling (src/particleFilter.m:103) and is always part of the warm-up
+    T = 1 + W + K
+    pr, T = make_problem(m, T)
+    gm = rbslam.models.from_problem(pr)
+    fargs = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
+    seed = 1 + rank
+
+    def barrier():
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    ctx = rbslam.Context(gm, N, T, device=local_rank, rng_mode=_capi.RNG_PHILOX, seed=seed,
+                         keep_history=True, kalman_variant=args.variant)
+    M, d = ctx.M, ctx.d
+    # ---- device-resident measurement ------------------------------------------------
+    ctx.filter_begin(*fargs, pr["dt"])
+    for _ in range(1 + W):
+        ctx.filter_step()
+    ctx.sync()
+    c0 = ctx.counters()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.phase_timing(True)
+    ctx.event_record(0)
+    for _ in range(K):
+        ctx.filter_step()
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1)
+    ctx.sync()
+    clocks = sampler.stop()
+    phases = ctx.phase_times()
+    ctx.phase_timing(False)
+    c1 = ctx.counters()
+    barrier()
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    ctx.filter_end(T=None)
+    # ---- end to end through the public C-ABI call, host buffers -----------------------
+    ctx.sync()
+    barrier()
+    cA = ctx.counters()
+    t0 = time.perf_counter()
+    ctx.filter_run(*fargs, pr["dt"], want_xn_traj=False)
+    e2e_s = time.perf_counter() - t0
+    cB = ctx.counters()
+    ctx.close()
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+        e2e_s = e2e_ms / 1e3
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    if rank == 0:
+        total_particles = N * world
+        value = total_particles * K / (ms / 1e3)
+        bytes_alg_step = N * (16.0 * M * M + 8.0 * M * (2 * d + 2))
+        kal_ms = phases["kalman"] / K
+        peak, peak_src = measured_peak()
+        achieved = bytes_alg_step / (kal_ms / 1e3) / 1e9 if kal_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 synthetic 3D dense-mag scale-up (BASELINE.json configs[3])",
+                       "N_particles_per_gpu": N, "m_basis": m, "M_linear_states": M, "d_meas": d,
+                       "state_bytes_per_gpu": N * ctx.ld * M * 8,
+                       "parallelism": "replicas" if world > 1 else "single",
+                       "l2": "inputs (%.1f GB of covariance slabs per step) far larger than L2"
+                             % (N * ctx.ld * M * 8 / 1e9),
+                       "rng": "device Philox4x32-10"},
+            "clocks": clocks,
+            "e2e": {"value": total_particles * T / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": (cB["h2d_bytes"] - cA["h2d_bytes"]) / T,
+                    "d2h_bytes_per_step": (cB["d2h_bytes"] - cA["d2h_bytes"]) / T,
+                    "what": "rbslam_filter_run from host buffers: upload, init of %d slabs, %d steps, "
+                            "final extraction, download" % (N, T)},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(M),
+                         "kernel": "Kalman update phase (gather + log-weight + rank-%d downdate)" % d,
+                         "algorithmic_bytes_per_launch": bytes_alg_step,
+                         "kernel_ms_per_step": kal_ms, "peak_source": peak_src,
+                         "phases_ms_per_step": {k: v / K for k, v in phases.items() if v > 0}},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(pr, m, args.cpu_sample_particles,
+                                                args.cpu_sample_steps)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

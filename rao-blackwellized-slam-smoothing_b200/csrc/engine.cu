@@ -240,7 +240,7 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 
-  const bool small = kalman_small_smem(M, d) <= ctx->smem_optin;
+  const bool small = kalman_small_smem(M, d) + 1024 <= ctx->smem_optin;
   if (!small && d > 4)
     return ctx->fail(RBSLAM_EARG, "unsupported size: d>4 needs M*M*8 B to fit shared memory");
 
@@ -274,7 +274,7 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   RB_ALLOC(ctx->d_listA, N); RB_ALLOC(ctx->d_listB, N); RB_ALLOC(ctx->d_counts, 8);
   RB_ALLOC(ctx->d_H, (size_t)N * d * ctx->ldh);
   RB_ALLOC(ctx->d_yhat, (size_t)N * d);
-  if (!small) {
+  if ((!small || cfg->kalman_variant == 2) && d <= 4) {
     const int nsplit = (M + 127) / 128;
     RB_ALLOC(ctx->d_PHpart, (size_t)N * nsplit * d * ctx->ld);
     RB_ALLOC(ctx->d_G, (size_t)N * d * ctx->ld);
@@ -290,10 +290,15 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   ctx->scratch_doubles = 2 * (size_t)M * M + 4 * (size_t)M + 64;
   RB_ALLOC(ctx->d_scratch, ctx->scratch_doubles);
   CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(DevStatus), ctx->stream));
-  CK(cudaFuncSetAttribute(k_kalman_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)std::min(ctx->smem_optin, (size_t)232448)));
-  CK(cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)std::min(ctx->smem_optin, (size_t)232448)));
+  {
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k_kalman_small));
+    ctx->smem_small_max = ctx->smem_optin - fa.sharedSizeBytes;
+    CK(cudaFuncSetAttribute(k_kalman_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_small_max));
+    CK(cudaFuncGetAttributes(&fa, k_resample));
+    ctx->smem_resample_max = ctx->smem_optin - fa.sharedSizeBytes;
+    CK(cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_resample_max));
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   return RBSLAM_OK;
 }
@@ -563,7 +568,7 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled) {
   a.status = ctx->d_status;
   a.t = ctx->t;
   const size_t smem = kalman_small_smem(M, d);
-  const bool small = smem <= ctx->smem_optin && ctx->cfg.kalman_variant != 2;
+  const bool small = smem <= ctx->smem_small_max && ctx->cfg.kalman_variant != 2;
   if (small) {
     const int grid = std::min(N, 8 * ctx->num_sms);
     for (int phase = 0; phase < 2; ++phase) {
@@ -598,7 +603,7 @@ int rb_resample_phase(rbslam_ctx *ctx, int n_draws) {
   rs.seed = ctx->cfg.seed; rs.sweep = ctx->sweep; rs.t = t;
   const int *forced = ctx->have_forced ? ctx->d_forced + soff : nullptr;
   size_t smem = sizeof(double) * (size_t)N;
-  if (smem > std::min(ctx->smem_optin, (size_t)232448)) smem = 0;
+  if (smem > ctx->smem_resample_max) smem = 0;
   k_resample<<<1, 1024, smem, ctx->stream>>>(N, n_draws, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
   ctx->launches += 1;
   CK(cudaGetLastError());

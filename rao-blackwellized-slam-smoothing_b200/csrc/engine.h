@@ -17,7 +17,7 @@ struct rbslam_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int num_sms = 148;
-  size_t smem_optin = 0;
+  size_t smem_optin = 0, smem_small_max = 0, smem_resample_max = 0;
 
   // model constants on device
   int *d_NN = nullptr;

@@ -75,46 +75,74 @@ __device__ __forceinline__ void dyn_model(const ModelConsts &mc, const double *x
   }
 }
 
+// ||r' / chol(dt*Q,'lower')||^2 for a fixed size: x L = r  ->  L' x' = r' (back substitution)
+template <int NW>
+__device__ __forceinline__ double whitened_sq(const double *r, double dt, const double *Q) {
+  double L[NW * NW];
+#pragma unroll
+  for (int q = 0; q < NW * NW; ++q) L[q] = dt * Q[q];
+#pragma unroll
+  for (int j = 0; j < NW; ++j) {
+    double s = L[j + j * NW];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j + k * NW] * L[j + k * NW];
+    const double ljj = sqrt(s);
+    L[j + j * NW] = ljj;
+#pragma unroll
+    for (int i = j + 1; i < NW; ++i) {
+      double v = L[i + j * NW];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i + k * NW] * L[j + k * NW];
+      L[i + j * NW] = v / ljj;
+    }
+  }
+  double x[NW];
+  double ss = 0.0;
+#pragma unroll
+  for (int j = NW - 1; j >= 0; --j) {
+    double v = r[j];
+#pragma unroll
+    for (int k = j + 1; k < NW; ++k) v -= L[k + j * NW] * x[k];
+    x[j] = v / L[j + j * NW];
+    ss += x[j] * x[j];
+  }
+  return ss;
+}
+
 // -0.5*||dynResNorm(xnk, xni, dx, dt, Q)||^2  (src/particleSmoother.m:175-182).
 // use_default: the reference's form for dynResNorm == [] (:175-177).
 __device__ __forceinline__ double dyn_logweight(const ModelConsts &mc, const double *xnk,
                                                 const double *xni, const double *dx, double dt,
                                                 const double *Q, bool use_default) {
-  double r[8];
-  int nr;
-  if (use_default || mc.family == FAM_SPARSE_VISUAL2D) {
-    nr = mc.n;
-    for (int j = 0; j < nr; ++j) r[j] = xnk[j] - xni[j] - dx[j];
-  } else if (mc.family == FAM_DENSE_MAG3D) {
-    // run_dense3D_magfield.m:202-203
-    nr = 6;
-    for (int j = 0; j < 3; ++j) r[j] = xnk[j] - xni[j] - dx[j];
-    double dqi[4] = {dx[3], -dx[4], -dx[5], -dx[6]};
-    double qii[4] = {xni[3], -xni[4], -xni[5], -xni[6]};
-    double t1[4], t2[4];
-    qmul(dqi, qii, t1);
-    qmul(t1, xnk + 3, t2);
-    logq(t2, r + 3);
-  } else {
+  if (mc.family == FAM_DENSE_RADIO2D && !use_default) {
     // run_dense2D_withHeading.m:77: heading residual only
-    const double e = (xnk[2] - xni[2] - dx[2]) / sqrt(dt * Q[0]);
-    return -0.5 * e * e;
+    const double r0 = xnk[2] - xni[2] - dx[2];
+    return -0.5 * whitened_sq<1>(&r0, dt, Q);
   }
-  // row / chol(dt*Q,'lower'):  x L = r  ->  L' x' = r'  (back substitution)
-  double Lc[36];
-  const int nw = mc.nw;
-  for (int c = 0; c < nw; ++c)
-    for (int rr = 0; rr < nw; ++rr) Lc[rr + c * nw] = dt * Q[rr + c * nw];
-  chol_small(Lc, nw, nw);
-  double x[8];
-  double ss = 0.0;
-  for (int j = nr - 1; j >= 0; --j) {
-    double v = r[j];
-    for (int k = j + 1; k < nr; ++k) v -= Lc[k + j * nw] * x[k];
-    x[j] = v / Lc[j + j * nw];
-    ss += x[j] * x[j];
+  if (mc.family == FAM_DENSE_MAG3D && !use_default) {
+    // run_dense3D_magfield.m:202-203
+    double r[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[j] = xnk[j] - xni[j] - dx[j];
+    const double dqi[4] = {dx[3], -dx[4], -dx[5], -dx[6]};
+    const double qii[4] = {xni[3], -xni[4], -xni[5], -xni[6]};
+    const double qk[4] = {xnk[3], xnk[4], xnk[5], xnk[6]};
+    double t1[4], t2[4], lq[3];
+    qmul(dqi, qii, t1);
+    qmul(t1, qk, t2);
+    logq(t2, lq);
+    r[3] = lq[0]; r[4] = lq[1]; r[5] = lq[2];
+    return -0.5 * whitened_sq<6>(r, dt, Q);
   }
-  return -0.5 * ss;
+  // default form (src/particleSmoother.m:175-177): (x'_t - x_i - odo')' / chol(dt*Q); it
+  // needs n == nw, which only the 3-state families satisfy (MATLAB would raise otherwise)
+  if (mc.nw == 3) {
+    double r[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[j] = xnk[j] - xni[j] - dx[j];
+    return -0.5 * whitened_sq<3>(r, dt, Q);
+  }
+  return nan("");
 }
 
 }  // namespace rb
