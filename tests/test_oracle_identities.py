@@ -1,0 +1,269 @@
+"""CPU tests that pin the oracle as far as the reference allows.
+
+The reference ships no tests or golden vectors (parity unpinned), so the oracle is
+checked against the analytical identities the reference itself states and against
+independent extended-precision re-derivations."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import tools
+from oracle.particle_filter import innovation, log_weight, kalman_gain, normalise
+from conftest import assert_close_norm, PKG  # noqa: F401
+
+from rbslam import synth, basis
+
+
+# ---------------------------------------------------------------- sample.m
+def test_sample_is_count_of_cumsum_below_u():
+    rng = np.random.default_rng(0)
+    w = rng.random(37)
+    w /= w.sum()
+    for u in rng.random(200):
+        wc = 0.0
+        cnt = 0
+        for wi in w:              # literal restatement: sum(cumsum(w) < u) + 1, left to right
+            wc += wi
+            cnt += wc < u
+        assert tools.sample(w, u) == min(cnt, 36)
+    assert np.array_equal(tools.sample_many(w, [0.0, 1.0 - 1e-17, 0.5]),
+                          [tools.sample(w, 0.0), tools.sample(w, 1.0 - 1e-17), tools.sample(w, 0.5)])
+
+
+def test_sample_frequencies_selftest():
+    """tools/sample.m:36-64 (commented-out self test): empirical frequency ~ w."""
+    rng = np.random.default_rng(1)
+    w = rng.random(10)
+    w /= w.sum()
+    idx = tools.sample_many(w, rng.random(100000))
+    assert np.max(np.abs(np.bincount(idx, minlength=10) / 1e5 - w)) < 5e-3
+
+
+# ---------------------------------------------------------------- quaternions
+def test_quaternion_identities():
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        phi = rng.standard_normal(3) * 0.3
+        assert np.linalg.norm(phi) < np.pi / 2
+        q = tools.expq(phi)
+        assert abs(np.linalg.norm(q) - 1) < 1e-14
+        assert_close_norm(tools.logq(q), phi, 1e-12)           # log(exp(phi)) = phi (|phi|<pi/2)
+        R = tools.quat2rmat(q)
+        assert_close_norm(R @ R.T, np.eye(3), 1e-13)
+        assert abs(np.linalg.det(R) - 1) < 1e-13
+        p = tools.expq(rng.standard_normal(3))
+        # rotation of a product = product of rotations; qLeft(q)*qInv(q) = identity
+        assert_close_norm(tools.quat2rmat(tools.qLeft(q) @ p), R @ tools.quat2rmat(p), 1e-13)
+        assert_close_norm(tools.qLeft(q) @ tools.qInv(q), [1, 0, 0, 0], 1e-14)
+    assert np.array_equal(tools.expq(np.zeros(3)), [1, 0, 0, 0])   # mag_phi == 0 guard
+    assert tools.expq(np.array([0, 0, 2.0]))[0] > 0                # sign flip when cos < 0
+    v = rng.standard_normal(3)
+    u = rng.standard_normal(3)
+    assert_close_norm(tools.mcross(v) @ u, np.cross(v, u), 1e-15)
+
+
+# ---------------------------------------------------------------- eigenbasis
+def test_domain_cartesian_dx_matches_package_and_is_sorted():
+    LL = np.array([[-3.0, -2.0, -1.0], [5.0, 2.5, 1.0]])
+    L, NN = tools.domain_cartesian_dx(100, 3, LL)
+    L2, NN2 = basis.domain_cartesian_dx(100, 3, LL)
+    assert np.array_equal(NN, NN2) and np.allclose(L, L2)
+    lam = tools.eigenval(NN, L)
+    assert np.all(np.diff(lam) >= 0)
+    assert len({tuple(r) for r in NN.astype(int)}) == 100
+    # C1/C4 claims of SURVEY 8a row A12: max index (18,18,3) for m=512 and (22,22,4) for m=1024
+    pr_LL = np.array([[-12.02, -12.02, -2.4], [12.02, 12.02, 2.4]])
+    assert tuple(basis.domain_cartesian_dx(512, 3, pr_LL)[1].max(0)) == (18, 18, 3)
+    assert tuple(basis.domain_cartesian_dx(1024, 3, pr_LL)[1].max(0)) == (22, 22, 4)
+
+
+def test_eigenfun_dx_is_gradient_and_basis_is_orthonormal():
+    LL = np.array([[-2.0, -1.5], [2.0, 1.5]])
+    L, NN = tools.domain_cartesian_dx(12, 2, LL)
+    rng = np.random.default_rng(3)
+    x = (rng.random((5, 2)) - 0.5) * L
+    h = 1e-6
+    for di in range(2):
+        e = np.zeros(2)
+        e[di] = h
+        fd = (tools.eigenfun(NN, x + e, L) - tools.eigenfun(NN, x - e, L)) / (2 * h)
+        assert_close_norm(tools.eigenfun_dx(NN, x, di, L), fd, 1e-8)
+    g = np.linspace(-1, 1, 401)
+    X, Y = np.meshgrid(g * L[0], g * L[1], indexing="ij")
+    Phi = tools.eigenfun(NN, np.stack([X.ravel(), Y.ravel()], 1), L)
+    wq = np.ones(401)
+    wq[0] = wq[-1] = 0.5
+    W = np.outer(wq, wq).ravel() * (2 * L[0] / 400) * (2 * L[1] / 400)
+    assert_close_norm(Phi.T @ (Phi * W[:, None]), np.eye(12), 1e-3)
+
+
+# ---------------------------------------------------------------- Kalman update / log-weight
+def _rand_spd(rng, M):
+    A = rng.standard_normal((M, M))
+    return A @ A.T / M + 0.3 * np.eye(M)
+
+
+def test_logweight_matches_direct_formula():
+    """The formula the reference leaves as a comment: -.5*log(det(SS)) - .5*(e'*(SS\\e))
+    (src/particleSmoother.m:228,285) minus the 2*pi term."""
+    rng = np.random.default_rng(4)
+    for d in (1, 3, 7):
+        M = 11
+        H = rng.standard_normal((d, M))
+        P = _rand_spd(rng, M)
+        R = _rand_spd(rng, d) * 0.1
+        xl = rng.standard_normal(M)
+        y = rng.standard_normal(d)
+        e, SS, _ = innovation(y, H, xl, P, R)
+        lw, _ = log_weight(e, SS, 1e-3)
+        direct = -0.5 * np.log(np.linalg.det(SS)) - 0.5 * e @ np.linalg.solve(SS, e) \
+            - 0.5 * d * np.log(2 * np.pi)
+        assert abs(lw - direct) < 1e-11 * max(1, abs(direct))
+
+
+def test_kalman_update_extended_precision():
+    """Independent re-derivation of src/particleFilter.m:184-198 in 50-digit arithmetic:
+    P+ = P - P H'(H P H' + R)^-1 H P,  xl+ = xl + P H' (..)^-1 e."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    rng = np.random.default_rng(5)
+    M, d = 6, 3
+    H = rng.standard_normal((d, M))
+    P = _rand_spd(rng, M)
+    R = 0.2 * np.eye(d)
+    xl = rng.standard_normal(M)
+    y = rng.standard_normal(d)
+    e, SS, ind = innovation(y, H, xl, P, R)
+    _, cS = log_weight(e, SS, 1e-3)
+    K = kalman_gain(P, H, cS)
+    xl_new = xl + K @ e
+    P_new = P - K @ SS @ K.T
+    mH, mP, mR = mp.matrix(H.tolist()), mp.matrix(P.tolist()), mp.matrix(R.tolist())
+    mS = mH * mP * mH.T + mR
+    mK = mP * mH.T * mp.inverse(mS)
+    me = mp.matrix(y.tolist()) - mH * mp.matrix(xl.tolist())
+    ref_xl = np.array((mp.matrix(xl.tolist()) + mK * me).tolist(), dtype=float).ravel()
+    ref_P = np.array((mP - mK * mS * mK.T).tolist(), dtype=float)
+    assert_close_norm(xl_new, ref_xl, 1e-13)
+    assert_close_norm(P_new, ref_P, 1e-13)
+
+
+def test_sequential_filter_equals_batch_gp():
+    """Closed-form anchor (tools/gp_scalar_potential_fast.m:190-193): with one particle,
+    fixed poses and no process noise the sequential Kalman updates of
+    src/particleFilter.m:184-198 reproduce the batch reduced-rank GP posterior
+    mean (Phi'Phi + s2 diag(1/k))^-1 Phi' y  and covariance  s2 (Phi'Phi + s2 diag(1/k))^-1."""
+    pr = synth.dense_radio_problem("line_3D", m=24, seed=7, m_sim=200)
+    model = oracle.DenseRadio2D(pr["NN"], pr["L"])
+    T = pr["y"].shape[0]
+    # exact odometry, negligible process noise -> the single particle follows the true path
+    pos = pr["truth"]["pos"]
+    odo = np.vstack([np.hstack([np.diff(pos.T, axis=0), np.zeros((T - 1, 1))]), np.zeros((1, 3))])
+    st = oracle.Streams(np.full((1, T, 1), 0.5), np.zeros((1, T, 1, 1)))
+    x0 = np.array([pos[0, 0], pos[1, 0], 0.0])
+    out = oracle.particleFilter(model, odo, pr["y"], x0, pr["x0_lin"], pr["P0_lin"],
+                                1e-300 * np.ones((1, 1)), pr["R"], 1, 1.0, st)
+    xl_seq, P_seq = out[2], out[4]
+    Phi = tools.eigenfun(pr["NN"], pos.T, pr["L"])
+    s2 = pr["R"][0, 0]
+    k = np.diag(pr["P0_lin"])
+    A = Phi.T @ Phi + s2 * np.diag(1.0 / k)
+    assert_close_norm(xl_seq, np.linalg.solve(A, Phi.T @ pr["y"][:, 0]), 1e-8)
+    assert_close_norm(P_seq, s2 * np.linalg.inv(A), 1e-8)
+
+
+def test_normalise_and_quirk_Q1():
+    lw = np.array([-1000.0, -1001.0, -1000.0])
+    w = normalise(lw)
+    assert abs(w.sum() - 1) < 1e-12 and np.argmax(w) == 0   # lse loses ~|c|*eps
+    pr = synth.dense_radio_problem("line_3D", m=10, seed=1, m_sim=100)
+    model = oracle.DenseRadio2D(pr["NN"], pr["L"])
+    N, T = 5, 4
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(0), 1, T, N, 1)
+    taps = {}
+    out = oracle.particleFilter(model, pr["odometry"][:T], pr["y"][:T], pr["x0_nonLin"], pr["x0_lin"],
+                                pr["P0_lin"], pr["Q"], pr["R"], N, pr["dt"], st,
+                                tap=lambda t, d: taps.__setitem__(t, d))
+    last = taps[T - 1]
+    dxl = out[3] - last["xl"][:, N - 1]
+    # P_mean is ASSIGNED in the loop (src/particleFilter.m:228-230): last particle's term only
+    assert_close_norm(out[5], last["w"][N - 1] * (last["P"][N - 1] + np.outer(dxl, dxl)), 1e-14)
+
+
+# ---------------------------------------------------------------- smoothers
+@pytest.mark.parametrize("fam", ["radio", "mag"])
+def test_information_form_equals_covariance_form(fam):
+    """src/particleSmootherInformationForm.m:34-37 claims identity with particleSmoother.m:
+    the ancestor probabilities AI(:,t) and all outputs must agree (diagonal P0)."""
+    if fam == "radio":
+        pr = synth.dense_radio_problem("line_3D", m=20, seed=3, m_sim=200)
+        model = oracle.DenseRadio2D(pr["NN"], pr["L"])
+        N, K = 12, 3
+    else:
+        pr = synth.dense_mag_problem(N_T=10, m=20, seed=3, m_sim=100)
+        model = oracle.DenseMag3D(pr["NN"], pr["L"])
+        N, K = 8, 2
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(11), K, T, N, model.nz)
+    args = (model, pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"],
+            pr["R"], N, K, pr["dt"], st)
+    ta, tb = {}, {}
+    A = oracle.particleSmoother(*args, tap=lambda k, t, d: ta.__setitem__((k, t), d["paNt"]))
+    B = oracle.particleSmootherInformationForm(*args, tap=lambda k, t, d: tb.__setitem__((k, t), d["paNt"]))
+    n_checked = 0
+    for key, pa in ta.items():
+        if pa is not None:
+            assert_close_norm(tb[key], pa, 1e-6, "paNt %s" % (key,))
+            n_checked += 1
+    assert n_checked == (K - 1) * (T - 1)
+    for a, b in zip(A, B):
+        assert_close_norm(b, a, 1e-9)
+
+
+def test_smoother_first_sweep_is_a_plain_filter():
+    """Sweep k=1 treats particle N_P like the others (src/particleSmoother.m:145-155)."""
+    pr = synth.dense_radio_problem("line_3D", m=16, seed=5, m_sim=100)
+    model = oracle.DenseRadio2D(pr["NN"], pr["L"])
+    N = 9
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(2), 1, T, N, 1)
+    args = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
+    f = oracle.particleFilter(model, *args, N, pr["dt"], st, jitter=1e-2)
+    XNK, XLK, PK = oracle.particleSmoother(model, *args, N, 1, pr["dt"], st)
+    # the sampled trajectory is one of the filter's genealogies at time T
+    ak = tools.sample(normalise(np.zeros(N)) * 0 + 1.0 / N, st.Uend[0])  # placeholder index range
+    assert any(np.allclose(XNK[:, :, 0], f[7][:, i, :]) for i in range(N))
+    assert 0 <= ak < N
+
+
+def test_sparse_filter_runs_with_unobserved_steps():
+    pr = synth.sparse_visual_problem(N_T=30, n_landmarks=6, N_P=7, seed=1, guess_map_var=0.01)
+    pr["y"][3, :] = np.nan          # a step without any observation: empty-matrix algebra, logw = 0
+    model = oracle.SparseVisual2D(6, *pr["camera"])
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(0), 1, 30, 7, 3)
+    taps = {}
+    oracle.particleFilter(model, pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"],
+                          pr["Q"], pr["R"], 7, pr["dt"], st, tap=lambda t, d: taps.__setitem__(t, d))
+    assert np.all(taps[3]["logw"] == 0.0)
+    assert np.allclose(taps[3]["w"], 1.0 / 7)
+
+
+# ---------------------------------------------------------------- Philox
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    from oracle.streams import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kat:
+        out = philox4x32_10(*[np.array([c]) for c in ctr], *key)
+        assert tuple(int(o[0]) for o in out) == exp
+
+
+def test_philox_streams_are_uniform_and_normal():
+    U, Z = oracle.philox_uniforms_normals(42, 0, 3, 20000, 6)
+    assert abs(U.mean() - 0.5) < 0.01 and U.min() >= 0 and U.max() < 1
+    assert abs(Z.mean()) < 0.01 and abs(Z.std() - 1) < 0.01
+    U2, Z2 = oracle.philox_uniforms_normals(42, 0, 3, 100, 6)
+    assert np.array_equal(U[:100], U2) and np.array_equal(Z[:100], Z2)   # counter-based: N-invariant
