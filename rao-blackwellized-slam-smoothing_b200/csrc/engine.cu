@@ -7,6 +7,7 @@
 #include "engine.h"
 #include "step_kernels.cuh"
 #include "kalman_kernels.cuh"
+#include "kalman_stream.cuh"
 #include "engine_internal.h"
 
 using namespace rb;
@@ -83,17 +84,26 @@ __global__ void k_final_cov(int N, int M, int ld, size_t slab, const double *__r
                             const int *__restrict__ slot, const double *__restrict__ xl,
                             const double *__restrict__ w, const int *__restrict__ iw_max,
                             const double *__restrict__ means, double *__restrict__ Pmax,
-                            double *__restrict__ Pmean) {
+                            double *__restrict__ Pmean, const double *__restrict__ G4,
+                            const double *__restrict__ KS4) {
   const int c = blockIdx.x;
-  const double *Pm = P + (size_t)slot[*iw_max] * slab + (size_t)c * ld;
-  const double *Pl = P + (size_t)slot[N - 1] * slab + (size_t)c * ld;
-  const double *xll = xl + (size_t)(N - 1) * M;
+  const int im = *iw_max, il = N - 1;
+  const double *Pm = P + (size_t)slot[im] * slab + (size_t)c * ld;
+  const double *Pl = P + (size_t)slot[il] * slab + (size_t)c * ld;
+  const double *xll = xl + (size_t)il * M;
   const double *xmean = means + M;
-  const double wl = w[N - 1];
+  const double wl = w[il];
   const double dc = xmean[c] - xll[c];
   for (int r = threadIdx.x; r < M; r += blockDim.x) {
-    Pmax[r + (size_t)c * M] = Pm[r];
-    Pmean[r + (size_t)c * M] = wl * (Pl[r] + (xmean[r] - xll[r]) * dc);
+    double pm = Pm[r], pl = Pl[r];
+    if (G4) {   // deferred downdate of the streaming path: P(r,c) -= KS(r,b) G(c,b)
+      for (int b = 0; b < 4; ++b) {
+        pm = fma(-KS4[((size_t)im * ld + r) * 4 + b], G4[((size_t)im * ld + c) * 4 + b], pm);
+        pl = fma(-KS4[((size_t)il * ld + r) * 4 + b], G4[((size_t)il * ld + c) * 4 + b], pl);
+      }
+    }
+    Pmax[r + (size_t)c * M] = pm;
+    Pmean[r + (size_t)c * M] = wl * (pl + (xmean[r] - xll[r]) * dc);
   }
 }
 
@@ -240,9 +250,25 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 
+  // Kalman-update path: 0 = single pass in shared memory (M*M*8 B fits one CTA),
+  // 1 = streaming pass with deferred downdate (kalman_stream.cuh), 2 = legacy 3-kernel path
   const bool small = kalman_small_smem(M, d) + 1024 <= ctx->smem_optin;
-  if (!small && d > 4)
-    return ctx->fail(RBSLAM_EARG, "unsupported size: d>4 needs M*M*8 B to fit shared memory");
+  const bool can_stream = d <= 4 && ctx->ld <= 4 * 2 * RB_STREAM_THREADS;
+  if (small && cfg->kalman_variant != 2 && cfg->kalman_variant != 3) ctx->kpath = 0;
+  else if (can_stream && cfg->kalman_variant != 3) ctx->kpath = 1;
+  else if (d <= 4 && ctx->ld <= 2048) ctx->kpath = 2;
+  else return ctx->fail(RBSLAM_EARG, "unsupported size: d>4 needs M*M*8 B to fit shared memory; "
+                                     "d<=4 needs M <= 2048");
+  if (ctx->kpath == 1) {
+    ctx->hs_p = (size_t)ctx->ld * 4; ctx->hs_a = 1; ctx->hs_c = 4;
+    int ns = N >= 4096 ? 2 : std::max(1, std::min(8, (4 * 148 + N - 1) / N));
+    if (const char *e = getenv("RBSLAM_NSPLIT")) ns = std::max(1, atoi(e));
+    int cw = ((M + ns - 1) / ns + 3) / 4 * 4;
+    ctx->nsplit = (M + cw - 1) / cw; ctx->cw = cw;
+  } else {
+    ctx->hs_p = (size_t)d * ctx->ldh; ctx->hs_a = ctx->ldh; ctx->hs_c = 1;
+    ctx->nsplit = (M + 127) / 128; ctx->cw = (M + ctx->nsplit - 1) / ctx->nsplit;
+  }
 
   if (mc.dim > 0) {
     if (!cfg->NN || !cfg->L) return ctx->fail(RBSLAM_EARG, "NN and L are required for dense models");
@@ -272,13 +298,18 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   for (int b = 0; b < 2; ++b) { RB_ALLOC(ctx->d_xl[b], (size_t)N * M); RB_ALLOC(ctx->d_slot[b], N); }
   RB_ALLOC(ctx->d_src_slot, N); RB_ALLOC(ctx->d_first_child, N); RB_ALLOC(ctx->d_free_list, N);
   RB_ALLOC(ctx->d_listA, N); RB_ALLOC(ctx->d_listB, N); RB_ALLOC(ctx->d_counts, 8);
-  RB_ALLOC(ctx->d_H, (size_t)N * d * ctx->ldh);
+  RB_ALLOC(ctx->d_H, (size_t)N * ctx->hs_p);
   RB_ALLOC(ctx->d_yhat, (size_t)N * d);
-  if ((!small || cfg->kalman_variant == 2) && d <= 4) {
-    const int nsplit = (M + 127) / 128;
-    RB_ALLOC(ctx->d_PHpart, (size_t)N * nsplit * d * ctx->ld);
+  if (ctx->kpath == 2) {
+    RB_ALLOC(ctx->d_PHpart, (size_t)N * ctx->nsplit * d * ctx->ld);
     RB_ALLOC(ctx->d_G, (size_t)N * d * ctx->ld);
     RB_ALLOC(ctx->d_KS, (size_t)N * d * ctx->ld);
+  } else if (ctx->kpath == 1) {
+    for (int b = 0; b < 2; ++b) {
+      RB_ALLOC(ctx->d_G4[b], (size_t)N * ctx->ld * 4);
+      RB_ALLOC(ctx->d_KS4[b], (size_t)N * ctx->ld * 4);
+    }
+    RB_ALLOC(ctx->d_PHp, (size_t)N * ctx->nsplit * ctx->ld * 4);
   }
   RB_ALLOC(ctx->d_logw, N); RB_ALLOC(ctx->d_w, N); RB_ALLOC(ctx->d_wc, N);
   ctx->T_hist = cfg->keep_history ? T : 2;
@@ -333,6 +364,7 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
                   ctx->d_ivec[1], ctx->d_hld[0], ctx->d_hld[1], ctx->d_slot[0], ctx->d_slot[1],
                   ctx->d_src_slot, ctx->d_first_child, ctx->d_free_list, ctx->d_listA, ctx->d_listB,
                   ctx->d_counts, ctx->d_H, ctx->d_yhat, ctx->d_PHpart, ctx->d_G, ctx->d_KS,
+                  ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_PHp,
                   ctx->d_logw, ctx->d_w, ctx->d_wc, ctx->d_Xhist, ctx->d_Ahist, ctx->d_traj_max,
                   ctx->d_traj_mean, ctx->d_iwmax, ctx->d_status, ctx->d_scratch};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -484,6 +516,11 @@ int rb_init_state(rbslam_ctx *ctx, bool info_form) {
   const int N = ctx->N, M = ctx->M, n = ctx->n;
   CK(cudaSetDevice(ctx->cfg.device));
   ctx->cs = 0; ctx->cx = 0; ctx->t = 0;
+  if (ctx->kpath == 1) {
+    ctx->cg = 0; ctx->pending = false;
+    CK(cudaMemsetAsync(ctx->d_G4[0], 0, sizeof(double) * (size_t)N * ctx->ld * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_KS4[0], 0, sizeof(double) * (size_t)N * ctx->ld * 4, ctx->stream));
+  }
   k_fill_int_iota<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_slot[0], N);
   dim3 g(M, std::min(N, 4 * ctx->num_sms));
   k_init_slabs<<<g, 128, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ctx->ld, M, N, ctx->d_P0, 0);
@@ -522,8 +559,7 @@ static void pick_large_launch(int ld, int &threads, int &R2) {
 template <int D>
 static int launch_large(rbslam_ctx *ctx, const KalmanArgs &a) {
   const int M = ctx->M, N = ctx->N, ld = ctx->ld;
-  const int nsplit = (M + 127) / 128;
-  const int cw = (M + nsplit - 1) / nsplit;
+  const int nsplit = ctx->nsplit, cw = ctx->cw;
   int threads, R2;
   pick_large_launch(ld, threads, R2);
   dim3 g(N, nsplit);
@@ -548,6 +584,76 @@ static int launch_large(rbslam_ctx *ctx, const KalmanArgs &a) {
   return RBSLAM_OK;
 }
 
+// streaming path: one pass per slab with the deferred downdate (kalman_stream.cuh)
+#define RB_KC 4
+#define RB_STAGES 4
+template <int D, int R2>
+static int launch_stream_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  const int N = ctx->N, ld = ctx->ld;
+  StreamArgs sa;
+  sa.M = ctx->M; sa.ld = ld; sa.cw = ctx->cw; sa.nsplit = ctx->nsplit; sa.slab = ctx->slab;
+  sa.P = ctx->d_P; sa.src_slot = a.src_slot; sa.dst_slot = a.dst_slot; sa.anc = a.ai;
+  sa.G4prev = ctx->d_G4[ctx->cg]; sa.KS4prev = ctx->d_KS4[ctx->cg]; sa.H4 = a.H; sa.PHp = ctx->d_PHp;
+  const size_t smem = sizeof(double) * (size_t)RB_STAGES * ((size_t)RB_KC * ld + 8 * RB_KC);
+  auto kern = k_stream_pass<D, R2, RB_KC, RB_STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
+    attr_done = true;
+  }
+  if (smem > ctx->smem_optin - 1024) return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin) / (smem + 2048)));
+  if (const char *e = getenv("RBSLAM_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+  const int grid = std::min(N * ctx->nsplit, per_sm * ctx->num_sms);
+  for (int phase = 0; phase < 2; ++phase) {
+    if (phase == 0 && !resampled) continue;
+    kern<<<grid, RB_STREAM_THREADS, smem, ctx->stream>>>(sa, phase == 0 ? ctx->d_listA : ctx->d_listB,
+                                                         ctx->d_counts + phase);
+    ctx->launches += 1;
+  }
+  Innov4Args ia;
+  ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = ctx->nsplit; ia.PHp = ctx->d_PHp; ia.H4 = a.H;
+  ia.xl_old = a.xl_old; ia.anc = a.ai; ia.xl_new = a.xl_new;
+  ia.G4new = ctx->d_G4[1 - ctx->cg]; ia.KS4new = ctx->d_KS4[1 - ctx->cg];
+  ia.y_t = a.y_t; ia.R = a.R; ia.jitter = a.jitter; ia.logw = a.logw; ia.status = a.status; ia.t = a.t;
+  k_innov4<D><<<N, 128, sizeof(double) * 4 * ld, ctx->stream>>>(ia);
+  ctx->launches += 1;
+  ctx->cg ^= 1;
+  ctx->pending = true;
+  return RBSLAM_OK;
+}
+template <int D>
+static int launch_stream(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  const int npairs = ctx->ld / 2;
+  const int R2 = (npairs + RB_STREAM_THREADS - 1) / RB_STREAM_THREADS;
+  switch (R2) {
+    case 1: return launch_stream_r<D, 1>(ctx, a, resampled);
+    case 2: return launch_stream_r<D, 2>(ctx, a, resampled);
+    case 3: return launch_stream_r<D, 3>(ctx, a, resampled);
+    default: return launch_stream_r<D, 4>(ctx, a, resampled);
+  }
+}
+
+// apply the deferred downdate to every slab (before the state is read out as a whole)
+int rb_flush_pending(rbslam_ctx *ctx) {
+  if (ctx->kpath != 1 || !ctx->pending) return RBSLAM_OK;
+  const int N = ctx->N, M = ctx->M, ld = ctx->ld;
+  dim3 g(std::min(M, 64), N);
+  const double *G4 = ctx->d_G4[ctx->cg], *KS4 = ctx->d_KS4[ctx->cg];
+  switch (ctx->d) {
+    case 1: k_apply_pending<1><<<g, 256, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ld, M, ctx->d_slot[ctx->cs], G4, KS4); break;
+    case 2: k_apply_pending<2><<<g, 256, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ld, M, ctx->d_slot[ctx->cs], G4, KS4); break;
+    case 3: k_apply_pending<3><<<g, 256, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ld, M, ctx->d_slot[ctx->cs], G4, KS4); break;
+    default: k_apply_pending<4><<<g, 256, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ld, M, ctx->d_slot[ctx->cs], G4, KS4); break;
+  }
+  CK(cudaMemsetAsync(ctx->d_G4[ctx->cg], 0, sizeof(double) * (size_t)N * ld * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_KS4[ctx->cg], 0, sizeof(double) * (size_t)N * ld * 4, ctx->stream));
+  ctx->launches += 1;
+  ctx->pending = false;
+  CK(cudaGetLastError());
+  return RBSLAM_OK;
+}
+
 // Kalman phase for the particles in the current plan; xl: cur -> 1-cur
 int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled) {
   const int N = ctx->N, M = ctx->M, d = ctx->d;
@@ -567,9 +673,8 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled) {
   a.logw = ctx->d_logw;
   a.status = ctx->d_status;
   a.t = ctx->t;
-  const size_t smem = kalman_small_smem(M, d);
-  const bool small = smem <= ctx->smem_small_max && ctx->cfg.kalman_variant != 2;
-  if (small) {
+  if (ctx->kpath == 0) {
+    const size_t smem = kalman_small_smem(M, d);
     const int grid = std::min(N, 8 * ctx->num_sms);
     for (int phase = 0; phase < 2; ++phase) {
       if (phase == 0 && !resampled) continue;
@@ -577,6 +682,15 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled) {
                                                        ctx->d_counts + phase);
       ctx->launches += 1;
     }
+  } else if (ctx->kpath == 1) {
+    int rc;
+    switch (d) {
+      case 1: rc = launch_stream<1>(ctx, a, resampled); break;
+      case 2: rc = launch_stream<2>(ctx, a, resampled); break;
+      case 3: rc = launch_stream<3>(ctx, a, resampled); break;
+      default: rc = launch_stream<4>(ctx, a, resampled); break;
+    }
+    if (rc) return rc;
   } else {
     switch (d) {
       case 1: launch_large<1>(ctx, a); break;
@@ -643,7 +757,7 @@ int rb_meas_phase(rbslam_ctx *ctx, bool resampled) {
   const double *xn = ctx->d_Xhist + (size_t)tb * N * ctx->n;
   const int *ai = resampled ? ctx->d_Ahist + (size_t)tb * N : nullptr;
   k_meas<<<N, 128, 0, ctx->stream>>>(ctx->mc, N, xn, ctx->d_xl[ctx->cx], ctx->M, ai, ctx->d_H,
-                                     ctx->ldh, ctx->d_yhat);
+                                     ctx->hs_p, ctx->hs_a, ctx->hs_c, ctx->ld, ctx->d_yhat);
   ctx->launches += 1;
   CK(cudaGetLastError());
   return RBSLAM_OK;
@@ -740,7 +854,9 @@ extern "C" int rbslam_filter_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
   ctx->launches += 1;
   if (out->P_max || out->P_mean) {
     k_final_cov<<<M, 128, 0, ctx->stream>>>(N, M, ctx->ld, ctx->slab, ctx->d_P, ctx->d_slot[ctx->cs], xl,
-                                            ctx->d_w, iw, means, Pmax, Pmean);
+                                            ctx->d_w, iw, means, Pmax, Pmean,
+                                            (ctx->kpath == 1 && ctx->pending) ? ctx->d_G4[ctx->cg] : nullptr,
+                                            (ctx->kpath == 1 && ctx->pending) ? ctx->d_KS4[ctx->cg] : nullptr);
     ctx->launches += 1;
   }
   CK(cudaGetLastError());
@@ -803,6 +919,10 @@ extern "C" int rbslam_filter_run(rbslam_ctx *ctx, const rbslam_inputs *in, rbsla
 // ---------------------------------------------------------------------------
 int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host) {
   const int N = ctx->N, M = ctx->M;
+  if (slabs == ctx->d_P) {
+    int rcf = rb_flush_pending(ctx);
+    if (rcf) return rcf;
+  }
   const size_t per = (size_t)M * M;
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>(N, (64u << 20) / (per * 8) + 1));
   double *tmp = nullptr;

@@ -32,7 +32,14 @@ struct rbslam_ctx {
   int *d_src_slot = nullptr, *d_first_child = nullptr, *d_free_list = nullptr;
   int *d_listA = nullptr, *d_listB = nullptr, *d_counts = nullptr;
   double *d_H = nullptr, *d_yhat = nullptr;
-  double *d_PHpart = nullptr, *d_G = nullptr, *d_KS = nullptr;
+  double *d_PHpart = nullptr, *d_G = nullptr, *d_KS = nullptr;   // legacy 3-kernel path
+  // streaming path (kalman_stream.cuh): pending downdates and partial P H'
+  double *d_G4[2] = {nullptr, nullptr}, *d_KS4[2] = {nullptr, nullptr}, *d_PHp = nullptr;
+  int cg = 0;            // d_G4[cg]/d_KS4[cg]: pending downdate written by the last step
+  bool pending = false;  // a deferred downdate is outstanding
+  int kpath = 0;         // 0 shared-memory single pass, 1 streaming (lazy), 2 legacy 3-kernel
+  int nsplit = 1, cw = 0;
+  size_t hs_p = 0; int hs_a = 0, hs_c = 1;   // layout of d_H: H_i(a,c) at i*hs_p + a*hs_a + c*hs_c
   double *d_logw = nullptr, *d_w = nullptr, *d_wc = nullptr;
   double *d_Xhist = nullptr;     // [T_hist][N][n]
   int *d_Ahist = nullptr;        // [T_hist][N]

@@ -46,6 +46,7 @@ int rb_meas_phase(rbslam_ctx *ctx, bool resampled);
 int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled);
 int rb_normalize_phase(rbslam_ctx *ctx);
 int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host);
+int rb_flush_pending(rbslam_ctx *ctx);
 // smoother.cu
 int rb_info_init(rbslam_ctx *ctx);
 void rb_smoother_free(rbslam_ctx *ctx);

@@ -121,21 +121,22 @@ extern "C" int rbslam_op_meas_jacobian(rbslam_ctx *ctx, int32_t N, const double 
   const bool sparse = ctx->mc.family == FAM_SPARSE_VISUAL2D;
   if (sparse && !xl) return ctx->fail(RBSLAM_EARG, "sparse measModel needs xl");
   CK(cudaSetDevice(ctx->cfg.device));
-  const int n = ctx->n, M = ctx->M, d = ctx->d, ldh = ctx->ldh;
+  const int n = ctx->n, M = ctx->M, d = ctx->d;
   TMP_ALLOC(d_xn, double, (size_t)n * N);
   TMP_ALLOC(d_xl, double, (size_t)M * N);
   int rc;
   if ((rc = rb_h2d(ctx, d_xn, xn, sizeof(double) * n * N))) return rc;
   if (sparse && (rc = rb_h2d(ctx, d_xl, xl, sizeof(double) * (size_t)M * N))) return rc;
-  k_meas<<<N, 128, 0, ctx->stream>>>(ctx->mc, N, d_xn, d_xl, M, nullptr, ctx->d_H, ldh, ctx->d_yhat);
+  k_meas<<<N, 128, 0, ctx->stream>>>(ctx->mc, N, d_xn, d_xl, M, nullptr, ctx->d_H, ctx->hs_p, ctx->hs_a,
+                                     ctx->hs_c, ctx->ld, ctx->d_yhat);
   ctx->launches += 1;
   CK(cudaGetLastError());
-  std::vector<double> h((size_t)N * d * ldh);
+  std::vector<double> h((size_t)N * ctx->hs_p);
   if ((rc = rb_d2h(ctx, h.data(), ctx->d_H, h.size() * 8))) return rc;
   for (int i = 0; i < N; ++i)
     for (int a = 0; a < d; ++a)
       for (int c = 0; c < M; ++c)
-        dy[i + (size_t)N * (a + (size_t)d * c)] = h[((size_t)i * d + a) * ldh + c];
+        dy[i + (size_t)N * (a + (size_t)d * c)] = h[(size_t)i * ctx->hs_p + (size_t)a * ctx->hs_a + (size_t)c * ctx->hs_c];
   if (sparse && yhat && (rc = rb_d2h(ctx, yhat, ctx->d_yhat, sizeof(double) * d * N))) return rc;
   return RBSLAM_OK;
 }
@@ -159,11 +160,16 @@ extern "C" int rbslam_op_kalman_update(rbslam_ctx *ctx, int32_t N, const double 
   if (N != ctx->N) return ctx->fail(RBSLAM_EARG, "op_kalman_update: N must equal the context's N");
   if (!H && !xn) return ctx->fail(RBSLAM_EARG, "op_kalman_update: need H or xn");
   CK(cudaSetDevice(ctx->cfg.device));
-  const int M = ctx->M, d = ctx->d, ldh = ctx->ldh, n = ctx->n;
+  const int M = ctx->M, d = ctx->d, n = ctx->n;
   const bool sparse = ctx->mc.family == FAM_SPARSE_VISUAL2D;
   int rc;
   ctx->cs = 0; ctx->cx = 0; ctx->t = 0;
   ctx->running = false;
+  if (ctx->kpath == 1) {
+    ctx->cg = 0; ctx->pending = false;
+    CK(cudaMemsetAsync(ctx->d_G4[0], 0, sizeof(double) * (size_t)N * ctx->ld * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_KS4[0], 0, sizeof(double) * (size_t)N * ctx->ld * 4, ctx->stream));
+  }
   k_op_iota<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_slot[0], ctx->d_src_slot, ctx->d_listB, ctx->d_counts, N);
   if ((rc = rb_h2d(ctx, ctx->d_xl[0], xl, sizeof(double) * (size_t)M * N))) return rc;
   {  // P -> slabs in chunks
@@ -183,16 +189,17 @@ extern "C" int rbslam_op_kalman_update(rbslam_ctx *ctx, int32_t N, const double 
   if ((rc = rb_h2d(ctx, d_R, R, sizeof(double) * d * d))) return rc;
   if (H) {
     if (sparse) return ctx->fail(RBSLAM_EARG, "sparse family evaluates its own Jacobian (pass H=NULL)");
-    std::vector<double> h((size_t)N * d * ldh, 0.0);
+    std::vector<double> h((size_t)N * ctx->hs_p, 0.0);
     for (int i = 0; i < N; ++i)
       for (int a = 0; a < d; ++a)
         for (int c = 0; c < M; ++c)
-          h[((size_t)i * d + a) * ldh + c] = H[i + (size_t)N * (a + (size_t)d * c)];
+          h[(size_t)i * ctx->hs_p + (size_t)a * ctx->hs_a + (size_t)c * ctx->hs_c] = H[i + (size_t)N * (a + (size_t)d * c)];
     if ((rc = rb_h2d(ctx, ctx->d_H, h.data(), h.size() * 8))) return rc;
   } else {
     TMP_ALLOC(d_xn, double, (size_t)n * N);
     if ((rc = rb_h2d(ctx, d_xn, xn, sizeof(double) * n * N))) return rc;
-    k_meas<<<N, 128, 0, ctx->stream>>>(ctx->mc, N, d_xn, ctx->d_xl[0], M, nullptr, ctx->d_H, ldh, ctx->d_yhat);
+    k_meas<<<N, 128, 0, ctx->stream>>>(ctx->mc, N, d_xn, ctx->d_xl[0], M, nullptr, ctx->d_H, ctx->hs_p,
+                                       ctx->hs_a, ctx->hs_c, ctx->ld, ctx->d_yhat);
     CK(cudaStreamSynchronize(ctx->stream));
   }
   CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(DevStatus), ctx->stream));

@@ -213,21 +213,23 @@ __global__ void k_dyn_logweight(ModelConsts mc, int N, const double *__restrict_
 #define RB_MAXTAB 96
 __global__ void __launch_bounds__(128)
 k_meas(ModelConsts mc, int N, const double *__restrict__ xn, const double *__restrict__ xl,
-       int ldxl, const int *__restrict__ xl_index, double *__restrict__ H, int ldh,
-       double *__restrict__ yhat) {
+       int ldxl, const int *__restrict__ xl_index, double *__restrict__ H, size_t hs_p, int hs_a,
+       int hs_c, int ldpad, double *__restrict__ yhat) {
   const int i = blockIdx.x;
   if (i >= N) return;
   __shared__ double s_sin[3][RB_MAXTAB], s_cos[3][RB_MAXTAB];
   __shared__ double s_x[7];
   if (threadIdx.x < mc.n) s_x[threadIdx.x] = xn[threadIdx.x + (size_t)i * mc.n];
   __syncthreads();
-  double *Hi = H + (size_t)i * mc.d * ldh;
+  // H_i(a, c) lives at Hi[a*hs_a + c*hs_c]; columns M..ldpad-1 are zero padding
+  double *Hi = H + (size_t)i * hs_p;
   if (mc.family == FAM_SPARSE_VISUAL2D) {
     // measurement.m:36-50 (projection) and :59-79 (Jacobian wrt map)
     const double *xli = xl + (size_t)(xl_index ? xl_index[i] : i) * ldxl;
     double s, c;
     sincos(s_x[2], &s, &c);
-    for (int idx = threadIdx.x; idx < mc.d * ldh; idx += blockDim.x) Hi[idx] = 0.0;
+    for (int idx = threadIdx.x; idx < mc.d * ldpad; idx += blockDim.x)
+      Hi[(size_t)(idx / ldpad) * hs_a + (size_t)(idx % ldpad) * hs_c] = 0.0;
     __syncthreads();
     for (int l = threadIdx.x; l < mc.m; l += blockDim.x) {
       const double m1 = xli[2 * l], m2 = xli[2 * l + 1];
@@ -240,8 +242,8 @@ k_meas(ModelConsts mc, int N, const double *__restrict__ xn, const double *__res
       yhat[l + (size_t)i * mc.d] = u1 / ly;
       const double dv = m2 * c - p2 * c - m1 * s + p1 * s;
       const double div = dv * dv;
-      Hi[(size_t)l * ldh + 2 * l] = (mc.cam_f * (m2 - p2)) / div;
-      Hi[(size_t)l * ldh + 2 * l + 1] = -(mc.cam_f * (m1 - p1)) / div;
+      Hi[(size_t)l * hs_a + (size_t)(2 * l) * hs_c] = (mc.cam_f * (m2 - p2)) / div;
+      Hi[(size_t)l * hs_a + (size_t)(2 * l + 1) * hs_c] = -(mc.cam_f * (m1 - p1)) / div;
     }
     return;
   }
@@ -264,16 +266,16 @@ k_meas(ModelConsts mc, int N, const double *__restrict__ xn, const double *__res
       double v = 1.0;
       v = v * 1.0 / r0 * s_sin[0][n0];
       v = v * 1.0 / r1 * s_sin[1][n1];
-      Hi[cidx] = v;
+      Hi[(size_t)cidx * hs_c] = v;
     }
-    for (int cidx = mc.m + threadIdx.x; cidx < ldh; cidx += blockDim.x) Hi[cidx] = 0.0;
+    for (int cidx = mc.m + threadIdx.x; cidx < ldpad; cidx += blockDim.x) Hi[(size_t)cidx * hs_c] = 0.0;
     return;
   }
   // dense-mag
   double Rnb[3][3];
   quat2rmat(s_x + 3, Rnb);
   const double rL[3] = {sqrt(mc.L[0]), sqrt(mc.L[1]), sqrt(mc.L[2])};
-  for (int cidx = threadIdx.x; cidx < ldh; cidx += blockDim.x) {
+  for (int cidx = threadIdx.x; cidx < ldpad; cidx += blockDim.x) {
     double g[3];
     if (cidx < 3) {
       g[0] = cidx == 0; g[1] = cidx == 1; g[2] = cidx == 2;
@@ -298,7 +300,7 @@ k_meas(ModelConsts mc, int N, const double *__restrict__ xn, const double *__res
     // H(a, c) = sum_b Rnb(b, a) * g_b   (Rnb' * dPhi)
 #pragma unroll
     for (int a = 0; a < 3; ++a)
-      Hi[(size_t)a * ldh + cidx] = Rnb[0][a] * g[0] + Rnb[1][a] * g[1] + Rnb[2][a] * g[2];
+      Hi[(size_t)a * hs_a + (size_t)cidx * hs_c] = Rnb[0][a] * g[0] + Rnb[1][a] * g[1] + Rnb[2][a] * g[2];
   }
 }
 

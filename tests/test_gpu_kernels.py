@@ -127,8 +127,9 @@ def _oracle_update(xl, P, H, yt, R, jitter, yhat=None):
 
 
 @pytest.mark.parametrize("fam,m,variant", [("radio", 128, 0), ("radio", 50, 0), ("mag", 64, 0),
-                                           ("mag", 64, 2), ("mag", 253, 0), ("mag", 512, 0),
-                                           ("radio", 300, 0)])
+                                           ("mag", 64, 2), ("mag", 64, 3), ("mag", 253, 0),
+                                           ("mag", 253, 3), ("mag", 512, 0), ("radio", 300, 0),
+                                           ("radio", 300, 3), ("mag", 1024, 0)])
 def test_kalman_update_dense(rbslam_lib, fam, m, variant):
     rb = rbslam_lib
     pr, om, gm = _problem(rb, fam, m=m)
