@@ -263,6 +263,9 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
     ctx->hs_p = (size_t)ctx->ld * 4; ctx->hs_a = 1; ctx->hs_c = 4;
     int ns = N >= 4096 ? 2 : std::max(1, std::min(8, (4 * 148 + N - 1) / N));
     if (const char *e = getenv("RBSLAM_NSPLIT")) ns = std::max(1, atoi(e));
+    if (const char *e = getenv("RBSLAM_STREAM_CFG")) { int kc = 4, st = 4; if (sscanf(e, "%d,%d", &kc, &st) == 2) ctx->stream_cfg = kc * 100 + st; }
+    if (const char *e = getenv("RBSLAM_CTAS_PER_SM")) ctx->stream_ctas_per_sm = atoi(e);
+    if (const char *e = getenv("RBSLAM_STREAM_HINTS")) ctx->stream_hints = atoi(e);
     int cw = ((M + ns - 1) / ns + 3) / 4 * 4;
     ctx->nsplit = (M + cw - 1) / cw; ctx->cw = cw;
   } else {
@@ -585,17 +588,17 @@ static int launch_large(rbslam_ctx *ctx, const KalmanArgs &a) {
 }
 
 // streaming path: one pass per slab with the deferred downdate (kalman_stream.cuh)
-#define RB_KC 4
-#define RB_STAGES 4
-template <int D, int R2>
-static int launch_stream_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+// (KC columns per stage, S stages) is a tuning knob: RBSLAM_STREAM_CFG="KC,S" (d=3 only)
+template <int D, int R2, int KC, int S>
+static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   const int N = ctx->N, ld = ctx->ld;
   StreamArgs sa;
+  sa.hints = ctx->stream_hints;
   sa.M = ctx->M; sa.ld = ld; sa.cw = ctx->cw; sa.nsplit = ctx->nsplit; sa.slab = ctx->slab;
   sa.P = ctx->d_P; sa.src_slot = a.src_slot; sa.dst_slot = a.dst_slot; sa.anc = a.ai;
   sa.G4prev = ctx->d_G4[ctx->cg]; sa.KS4prev = ctx->d_KS4[ctx->cg]; sa.H4 = a.H; sa.PHp = ctx->d_PHp;
-  const size_t smem = sizeof(double) * (size_t)RB_STAGES * ((size_t)RB_KC * ld + 8 * RB_KC);
-  auto kern = k_stream_pass<D, R2, RB_KC, RB_STAGES>;
+  const size_t smem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 8 * KC);
+  auto kern = k_stream_pass<D, R2, KC, S>;
   static bool attr_done = false;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
@@ -603,7 +606,7 @@ static int launch_stream_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled)
   }
   if (smem > ctx->smem_optin - 1024) return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin) / (smem + 2048)));
-  if (const char *e = getenv("RBSLAM_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+  if (ctx->stream_ctas_per_sm > 0) per_sm = ctx->stream_ctas_per_sm;
   const int grid = std::min(N * ctx->nsplit, per_sm * ctx->num_sms);
   for (int phase = 0; phase < 2; ++phase) {
     if (phase == 0 && !resampled) continue;
@@ -621,6 +624,22 @@ static int launch_stream_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled)
   ctx->cg ^= 1;
   ctx->pending = true;
   return RBSLAM_OK;
+}
+template <int D, int R2>
+static int launch_stream_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  // default (KC=8 columns per stage, S=2 stages) measured best on C4; see profiles/tuning_r1.md
+  if (D == 3) {
+    switch (ctx->stream_cfg) {
+      case 403: return launch_stream_cfg<D, R2, 4, 3>(ctx, a, resampled);
+      case 404: return launch_stream_cfg<D, R2, 4, 4>(ctx, a, resampled);
+      case 406: return launch_stream_cfg<D, R2, 4, 6>(ctx, a, resampled);
+      case 604: return launch_stream_cfg<D, R2, 6, 4>(ctx, a, resampled);
+      case 803: return launch_stream_cfg<D, R2, 8, 3>(ctx, a, resampled);
+      case 1202: return launch_stream_cfg<D, R2, 12, 2>(ctx, a, resampled);
+      default: break;
+    }
+  }
+  return launch_stream_cfg<D, R2, 8, 2>(ctx, a, resampled);
 }
 template <int D>
 static int launch_stream(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {

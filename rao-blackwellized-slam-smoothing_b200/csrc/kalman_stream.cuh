@@ -65,7 +65,22 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
       : "memory");
 }
 
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                                 uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 struct StreamArgs {
+  int hints;               // bit0: L2 evict_first on the slab loads, bit1: streaming (.cs) stores
   int M, ld, cw, nsplit;
   size_t slab;
   double *P;
@@ -101,6 +116,8 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
 
   // ---- producer (thread 0): next chunk to issue --------------------------------
   int p_it = blockIdx.x, p_c = 0, p_q = 0;   // item, column offset inside the item's chunk, seq no
+  const uint64_t pol = l2_policy_evict_first();
+  const bool hint_ld = a.hints & 1, hint_st = a.hints & 2;
   auto issue = [&]() {
     if (p_it >= n_items) return;
     const int i = list[p_it / a.nsplit], sp = p_it % a.nsplit;
@@ -112,7 +129,8 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
     uint64_t *bar = &full[p_q % S];
     const uint32_t bytes_p = (uint32_t)ncols * ld * 8u, bytes_v = (uint32_t)ncols * 32u;
     mbar_expect_tx(bar, bytes_p + 2 * bytes_v);
-    tma_load_1d(st, a.P + (size_t)a.src_slot[i] * a.slab + (size_t)c * ld, bytes_p, bar);
+    if (hint_ld) tma_load_1d_hint(st, a.P + (size_t)a.src_slot[i] * a.slab + (size_t)c * ld, bytes_p, bar, pol);
+    else tma_load_1d(st, a.P + (size_t)a.src_slot[i] * a.slab + (size_t)c * ld, bytes_p, bar);
     tma_load_1d(st + (size_t)KC * ld, a.G4prev + ((size_t)an * ld + c) * 4, bytes_v, bar);
     tma_load_1d(st + (size_t)KC * ld + 4 * KC, a.H4 + ((size_t)i * ld + c) * 4, bytes_v, bar);
     ++p_q;
@@ -175,7 +193,7 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
                 acc[k][b].x = fma(v.x, h[b], acc[k][b].x);
                 acc[k][b].y = fma(v.y, h[b], acc[k][b].y);
               }
-              dcol[rp] = v;
+              if (hint_st) __stcs(dcol + rp, v); else dcol[rp] = v;
             }
           }
         }
