@@ -26,7 +26,7 @@ def stacked_future_jacobian(dy_xnk, t, ny):
 
 
 def particleSmoother(model, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P, N_K, dt,
-                     streams, sparseFeatures=None, makePlots=None, forced=None, tap=None,
+                     streams, sparseFeatures=None, makePlots=None, forced=None, tap=None, record=None,
                      jitter=1e-2, verbose=False):
     """Rao-Blackwellized particle smoother (src/particleSmoother.m:1-2).
 
@@ -183,6 +183,9 @@ def particleSmoother(model, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P, N
                 xl[:, i] = xl[:, i] + K @ e
                 P[i] = P[i] - K @ SS @ K.T
 
+            if record is not None:
+                record.setdefault("ai", {})[(k, t)] = ai.copy()
+                record.setdefault("paNt", {})[(k, t)] = None if paNt is None else paNt.copy()
             if tap is not None:
                 tap(k, t, dict(xn=xn.copy(), xl=xl.copy(), P=P, logw=logw.copy(), w=w.copy(),
                                ai=ai.copy(), paNt=None if paNt is None else paNt.copy()))
@@ -191,6 +194,8 @@ def particleSmoother(model, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P, N
             ak = int(forced["ak"][k])
         else:
             ak = sample(w, streams.Uend[k])
+        if record is not None:
+            record.setdefault("ak", {})[k] = ak
         xnk = xn_traj[:, ak, :].copy()                                    # :347
         XNK[:, :, k] = xnk                                                # :352-354
         XLK[:, k] = xl[:, ak]

@@ -13,7 +13,7 @@ from .particle_smoother import default_dyn_res_norm
 
 def particleSmootherInformationForm(model, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P,
                                     N_K, dt, streams, sparseFeatures=None, makePlots=None,
-                                    forced=None, tap=None, jitter=1e-2, verbose=False):
+                                    forced=None, tap=None, record=None, jitter=1e-2, verbose=False):
     """Information-form RBPS (src/particleSmootherInformationForm.m:1-2).
 
     Dense models only (:77-80).  Quirk Q8: a per-particle x0_lin is ignored
@@ -188,6 +188,9 @@ def particleSmootherInformationForm(model, odometry, y, x0_nonLin, x0_lin, P0_li
                 ivec[:, i] = ivec[:, i] + dv                              # :333
                 Imat[i] = Imat[i] + dM                                    # :334
 
+            if record is not None:
+                record.setdefault("ai", {})[(k, t)] = ai.copy()
+                record.setdefault("paNt", {})[(k, t)] = None if paNt is None else paNt.copy()
             if tap is not None:
                 tap(k, t, dict(xn=xn.copy(), xl=xl.copy(), P=P, ivec=ivec.copy(), Imat=Imat,
                                halfLogDetP=halfLogDetP.copy(), logw=logw.copy(), w=w.copy(),
@@ -197,6 +200,8 @@ def particleSmootherInformationForm(model, odometry, y, x0_nonLin, x0_lin, P0_li
             ak = int(forced["ak"][k])
         else:
             ak = sample(w, streams.Uend[k])
+        if record is not None:
+            record.setdefault("ak", {})[k] = ak
         xnk = xn_traj[:, ak, :].copy()
         XNK[:, :, k] = xnk
         XLK[:, k] = xl[:, ak]

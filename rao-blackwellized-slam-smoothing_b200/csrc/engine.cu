@@ -254,7 +254,9 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   // 1 = streaming pass with deferred downdate (kalman_stream.cuh), 2 = legacy 3-kernel path
   const bool small = kalman_small_smem(M, d) + 1024 <= ctx->smem_optin;
   const bool can_stream = d <= 4 && ctx->ld <= 4 * 2 * RB_STREAM_THREADS;
-  if (small && cfg->kalman_variant != 2 && cfg->kalman_variant != 3) ctx->kpath = 0;
+  if (cfg->information_form && !can_stream)
+    return ctx->fail(RBSLAM_EARG, "information form needs d<=3 and M<=1536");
+  if (small && cfg->kalman_variant != 2 && cfg->kalman_variant != 3 && !cfg->information_form) ctx->kpath = 0;
   else if (can_stream && cfg->kalman_variant != 3) ctx->kpath = 1;
   else if (d <= 4 && ctx->ld <= 2048) ctx->kpath = 2;
   else return ctx->fail(RBSLAM_EARG, "unsupported size: d>4 needs M*M*8 B to fit shared memory; "
@@ -593,12 +595,12 @@ template <int D, int R2, int KC, int S>
 static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   const int N = ctx->N, ld = ctx->ld;
   StreamArgs sa;
-  sa.hints = ctx->stream_hints;
+  sa.hints = ctx->stream_hints; sa.gk_by_particle = 0;
   sa.M = ctx->M; sa.ld = ld; sa.cw = ctx->cw; sa.nsplit = ctx->nsplit; sa.slab = ctx->slab;
   sa.P = ctx->d_P; sa.src_slot = a.src_slot; sa.dst_slot = a.dst_slot; sa.anc = a.ai;
   sa.G4prev = ctx->d_G4[ctx->cg]; sa.KS4prev = ctx->d_KS4[ctx->cg]; sa.H4 = a.H; sa.PHp = ctx->d_PHp;
   const size_t smem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 8 * KC);
-  auto kern = k_stream_pass<D, R2, KC, S>;
+  auto kern = k_stream_pass<D, D, R2, KC, S>;
   static bool attr_done = false;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
@@ -737,7 +739,7 @@ int rb_resample_phase(rbslam_ctx *ctx, int n_draws) {
   const int *forced = ctx->have_forced ? ctx->d_forced + soff : nullptr;
   size_t smem = sizeof(double) * (size_t)N;
   if (smem > ctx->smem_resample_max) smem = 0;
-  k_resample<<<1, 1024, smem, ctx->stream>>>(N, n_draws, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
+  k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, n_draws, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
   ctx->launches += 1;
   CK(cudaGetLastError());
   return RBSLAM_OK;

@@ -84,6 +84,8 @@ struct rbslam_ctx {
   double phase_ms[RB_PH_COUNT] = {0};
   cudaEvent_t user_events[16] = {nullptr};
 
+  void *smoother_ws = nullptr;   // SmootherWs (smoother.cu)
+
   // collectives (multi-GPU)
   rbslam_allgather_fn ag_fn = nullptr;
   rbslam_barrier_fn bar_fn = nullptr;

@@ -81,6 +81,7 @@ __device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gme
 
 struct StreamArgs {
   int hints;               // bit0: L2 evict_first on the slab loads, bit1: streaming (.cs) stores
+  int gk_by_particle;      // 1: G4prev/KS4prev are indexed by the particle, not its ancestor
   int M, ld, cw, nsplit;
   size_t slab;
   double *P;
@@ -95,7 +96,9 @@ struct StreamArgs {
 
 #define RB_STREAM_THREADS 192
 
-template <int D, int R2, int KC, int S>
+// D: rank of the pending update; DA >= D: columns of H4 to multiply with (DA = D+1 carries
+// P*ivec for the information form)
+template <int D, int DA, int R2, int KC, int S>
 __global__ void __launch_bounds__(RB_STREAM_THREADS, 1)
 k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict__ count) {
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -124,7 +127,7 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
     const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);
     const int c = c0 + p_c;
     const int ncols = min(KC, c1 - c);
-    const int an = a.anc ? a.anc[i] : i;
+    const int an = a.gk_by_particle ? i : (a.anc ? a.anc[i] : i);
     double *st = stages + (size_t)(p_q % S) * stage_doubles;
     uint64_t *bar = &full[p_q % S];
     const uint32_t bytes_p = (uint32_t)ncols * ld * 8u, bytes_v = (uint32_t)ncols * 32u;
@@ -147,9 +150,9 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int i = list[it / a.nsplit], sp = it % a.nsplit;
     const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);
-    const int an = a.anc ? a.anc[i] : i;
+    const int an = a.gk_by_particle ? i : (a.anc ? a.anc[i] : i);
     double *Pd = a.P + (size_t)a.dst_slot[i] * a.slab;
-    double2 ks[R2][D], acc[R2][D];
+    double2 ks[R2][D], acc[R2][DA];
 #pragma unroll
     for (int k = 0; k < R2; ++k) {
       const int rp = tid + k * RB_STREAM_THREADS;
@@ -164,7 +167,7 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
         for (int b = 0; b < D; ++b) ks[k][b] = make_double2(0.0, 0.0);
       }
 #pragma unroll
-      for (int b = 0; b < D; ++b) acc[k][b] = make_double2(0.0, 0.0);
+      for (int b = 0; b < DA; ++b) acc[k][b] = make_double2(0.0, 0.0);
     }
     for (int c = c0; c < c1; c += KC, ++q) {
       const double *st = stages + (size_t)(q % S) * stage_doubles;
@@ -189,7 +192,7 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
                 v.y = fma(-ks[k][b].y, g[b], v.y);
               }
 #pragma unroll
-              for (int b = 0; b < D; ++b) {   // PH(r,b) += P(r,c) H(b,c)
+              for (int b = 0; b < DA; ++b) {  // PH(r,b) += P(r,c) H(b,c)
                 acc[k][b].x = fma(v.x, h[b], acc[k][b].x);
                 acc[k][b].y = fma(v.y, h[b], acc[k][b].y);
               }
@@ -208,7 +211,7 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
       if (rp < npairs) {
         double o0[4] = {0, 0, 0, 0}, o1[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int b = 0; b < D; ++b) { o0[b] = acc[k][b].x; o1[b] = acc[k][b].y; }
+        for (int b = 0; b < DA; ++b) { o0[b] = acc[k][b].x; o1[b] = acc[k][b].y; }
         double4 *op = reinterpret_cast<double4 *>(out + (size_t)2 * rp * 4);
         op[0] = make_double4(o0[0], o0[1], o0[2], o0[3]);
         op[1] = make_double4(o1[0], o1[1], o1[2], o1[3]);

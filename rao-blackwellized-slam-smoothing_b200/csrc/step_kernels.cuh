@@ -18,9 +18,10 @@ struct RngSrc {
 };
 
 __global__ void __launch_bounds__(1024)
-k_resample(int N, int n_draws, const double *__restrict__ w, double *__restrict__ wc,
+k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__restrict__ wc,
            RngSrc rng, const int *__restrict__ forced, int *__restrict__ ai,
            DevStatus *status) {
+  // draws for particles i0 .. i0+n_draws-1 (uniform U[i] / Philox counter i, result ai[i])
   extern __shared__ double s_wc[];   // N doubles if it fits, else unused (use_smem=false)
   __shared__ int use_smem;
   if (threadIdx.x == 0) {
@@ -49,7 +50,7 @@ k_resample(int N, int n_draws, const double *__restrict__ w, double *__restrict_
     for (; j < N; ++j) { acc += src[j]; buf[j] = acc; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_draws; i += blockDim.x) {
+  for (int i = i0 + threadIdx.x; i < i0 + n_draws; i += blockDim.x) {
     int idx;
     if (forced != nullptr) {
       idx = forced[i];

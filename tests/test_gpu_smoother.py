@@ -1,0 +1,142 @@
+"""Parity of the CUDA smoothers (rbslam_smoother_run, covariance and information form)
+against the oracle restatements of src/particleSmoother.m and
+src/particleSmootherInformationForm.m."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_close_norm
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(rb, fam, N, **kw):
+    s = rb.synth
+    if fam == "radio":
+        pr = s.dense_radio_problem(kw.get("traj", "line_3D"), m=kw.get("m", 128), seed=2, m_sim=400)
+        om = oracle.DenseRadio2D(pr["NN"], pr["L"])
+    elif fam == "mag":
+        pr = s.dense_mag_problem(N_T=kw.get("T", 12), m=kw.get("m", 64), seed=3, m_sim=300)
+        om = oracle.DenseMag3D(pr["NN"], pr["L"])
+    else:
+        pr = s.sparse_visual_problem(N_T=kw.get("T", 30), n_landmarks=kw.get("nl", 20), N_P=N, seed=4,
+                                     guess_map_var=0.01)
+        om = oracle.SparseVisual2D(pr["n_landmarks"], *pr["camera"])
+    return pr, om, rb.models.from_problem(pr)
+
+
+def _args(pr):
+    return (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
+
+
+def _oracle_run(form, om, pr, N, K, st):
+    rec = {}
+    fn = oracle.particleSmootherInformationForm if form else oracle.particleSmoother
+    out = fn(om, *_args(pr), N, K, pr["dt"], st, record=rec)
+    T = pr["y"].shape[0]
+    ai = np.zeros((K, T, N), dtype=np.int32)
+    for (k, t), v in rec["ai"].items():
+        ai[k, t] = v
+    ak = np.array([rec["ak"][k] for k in range(K)], dtype=np.int32)
+    return out, ai, ak, rec["paNt"]
+
+
+def _check(o, ref, paNt, K, T, tol=1e-8, ai_tol=1e-6):
+    XNK, XLK, PK = ref
+    assert_close_norm(o["XNK"], XNK, tol, "XNK")
+    assert_close_norm(o["XLK"], XLK, tol, "XLK")
+    assert_close_norm(o["PK"], PK, tol, "PK")
+    n = 0
+    for (k, t), p in paNt.items():
+        if p is not None:
+            assert_close_norm(o["AI"][:, t, k], p, ai_tol, "AI k=%d t=%d" % (k, t))
+            n += 1
+    assert n == (K - 1) * (T - 1)
+
+
+CASES = [
+    ("radio", 30, 3, {}),                         # C2 shape (M=128, T=32): shared-memory Kalman kernel
+    ("radio", 16, 2, {"traj": "square_3D", "m": 40}),
+    ("mag", 10, 2, {"m": 64, "T": 10}),           # d=3, future system up to 27 x 27
+    ("mag", 8, 2, {"m": 253, "T": 8}),            # streaming Kalman kernel + flush before K6
+    ("sparse", 8, 2, {"T": 30}),                  # re-linearised future Jacobians, NaN rows
+]
+
+
+@pytest.mark.parametrize("fam,N,K,kw", CASES)
+def test_smoother_cov_teacher_forced(rbslam_lib, fam, N, K, kw):
+    rb = rbslam_lib
+    pr, om, gm = _setup(rb, fam, N, **kw)
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(7), K, T, N, om.nz)
+    ref, ai, ak, paNt = _oracle_run(0, om, pr, N, K, st)
+    with rb.Context(gm, N, T, rng_mode=0) as ctx:
+        o = ctx.smoother_run(*_args(pr), pr["dt"], K, 0, streams=st, forced_ancestors=ai, forced_ak=ak,
+                             want_AI=True)
+    _check(o, ref, paNt, K, T)
+
+
+@pytest.mark.parametrize("fam,N,K,kw", [CASES[0], CASES[2], CASES[4]])
+def test_smoother_cov_free_running(rbslam_lib, fam, N, K, kw):
+    rb = rbslam_lib
+    pr, om, gm = _setup(rb, fam, N, **kw)
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(8), K, T, N, om.nz)
+    ref, ai, ak, paNt = _oracle_run(0, om, pr, N, K, st)
+    with rb.Context(gm, N, T, rng_mode=0) as ctx:
+        o = ctx.smoother_run(*_args(pr), pr["dt"], K, 0, streams=st, want_AI=True)
+    assert np.array_equal(o["ak"], ak)
+    _check(o, ref, paNt, K, T)
+
+
+@pytest.mark.parametrize("fam,N,K,kw", [("radio", 20, 3, {"m": 40}), ("radio", 12, 2, {}),
+                                        ("mag", 8, 2, {"m": 40, "T": 8}), ("mag", 6, 2, {"m": 253, "T": 6})])
+def test_smoother_information_form(rbslam_lib, fam, N, K, kw):
+    rb = rbslam_lib
+    pr, om, gm = _setup(rb, fam, N, **kw)
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(9), K, T, N, om.nz)
+    ref, ai, ak, paNt = _oracle_run(1, om, pr, N, K, st)
+    with rb.Context(gm, N, T, rng_mode=0, information_form=True) as ctx:
+        o = ctx.smoother_run(*_args(pr), pr["dt"], K, 1, streams=st, forced_ancestors=ai, forced_ak=ak,
+                             want_AI=True)
+    _check(o, ref, paNt, K, T, ai_tol=1e-5)
+    # the information-form state itself (Imat, ivec, halfLogDetP) after the last sweep
+    st2, lws = {}, {}
+
+    def tap(k, t, d):
+        st2.update(ivec=d["ivec"], Imat=np.array(d["Imat"]), hld=d["halfLogDetP"])
+        lws[(k, t)] = d["w"].copy()
+    oracle.particleSmootherInformationForm(om, *_args(pr), N, K, pr["dt"], st,
+                                           forced=dict(ai=ai, ak=ak), tap=tap)
+    with rb.Context(gm, N, T, rng_mode=0, information_form=True) as ctx:
+        def cb(k, t):
+            assert_close_norm(ctx.read_particles(P=False)["w"], lws[(k, t)], 1e-6, "w k=%d t=%d" % (k, t))
+        ctx.set_step_callback(cb)
+        ctx.smoother_run(*_args(pr), pr["dt"], K, 1, streams=st, forced_ancestors=ai, forced_ak=ak)
+        inf = ctx.read_information()
+    assert_close_norm(inf["ivec"], st2["ivec"], 1e-8, "ivec")
+    assert_close_norm(inf["Imat"], st2["Imat"].transpose(1, 2, 0), 1e-8, "Imat")
+    assert_close_norm(inf["halfLogDetP"], st2["hld"], 1e-8, "halfLogDetP")
+
+
+def test_smoother_dropin_signatures(rbslam_lib):
+    rb = rbslam_lib
+    N, K = 12, 2
+    pr, om, gm = _setup(rb, "radio", N, m=30)
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(1), K, T, N, om.nz)
+    ref, ai, ak, _ = _oracle_run(0, om, pr, N, K, st)
+    XNK, XLK, PK = rb.particleSmoother(gm.dynModel, gm.measModel, gm.dynResNorm, pr["odometry"], pr["y"],
+                                       pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"], N, K,
+                                       pr["dt"], False, None, rng=st)
+    assert XNK.shape == (3, T, K) and XLK.shape == (30, K) and PK.shape == (30, 30, K)
+    assert_close_norm(XNK, ref[0], 1e-7)
+    out = rb.particleSmootherInformationForm(gm.dynModel, gm.measModel, gm.dynResNorm, pr["odometry"],
+                                             pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"],
+                                             pr["R"], N, K, pr["dt"], False, None, rng=st)
+    assert_close_norm(out[0], ref[0], 1e-7)      # cross-form identity on the device
+    pr2, om2, gm2 = _setup(rb, "sparse", 6, T=10)
+    assert rb.particleSmootherInformationForm(gm2.dynModel, gm2.measModel, None, pr2["odometry"], pr2["y"],
+                                              pr2["x0_nonLin"], pr2["x0_lin"], pr2["P0_lin"], pr2["Q"],
+                                              pr2["R"], 6, 2, pr2["dt"], True) is None
