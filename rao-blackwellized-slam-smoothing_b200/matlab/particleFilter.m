@@ -1,0 +1,25 @@
+function [traj_max,traj_mean,xl_max,xl_mean,P_max,P_mean,traj_sample_iwmax,xn_traj] = ...
+    particleFilter(dynModel,measModel,odometry,y,...
+    x0_nonLin,x0_lin,P0_lin,Q,R,N_P,dt,sparseFeatures,makePlots)
+% PARTICLEFILTER - drop-in for src/particleFilter.m:1-3 running on the GPU (librbslam).
+%
+% Same positional arguments and outputs as the reference.  dynModel/measModel must be
+% handles made by rbslam_model (the descriptor of the reference's closure family).
+% Randomness: compat mode by default (rand/randn are pre-drawn from MATLAB's global
+% stream in the reference's order); setenv('RBSLAM_RNG','philox') uses the device RNG.
+  if nargin < 12 || isempty(sparseFeatures), sparseFeatures = false; end
+  if nargin < 13, makePlots = []; end
+  desc = rbslam_resolve(dynModel, measModel);
+  if logical(sparseFeatures) ~= strcmp(desc.family, 'sparseVisual2D')
+    error('rbslam:unsupportedModel', 'sparseFeatures does not match the model family');
+  end
+  if ~isempty(makePlots)
+    warning('rbslam:makePlots', 'per-step makePlots callbacks are not forwarded by the MEX gateway');
+  end
+  opts = rbslam_opts();
+  if strcmp(opts.rng, 'compat')
+    opts = rbslam_streams(opts, desc, N_P, size(y,1), 1, false);
+  end
+  [traj_max,traj_mean,xl_max,xl_mean,P_max,P_mean,traj_sample_iwmax,xn_traj] = ...
+      rbslam_mex('filter', desc, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P, dt, opts);
+end

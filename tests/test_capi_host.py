@@ -129,3 +129,19 @@ def test_synthetic_problem_shapes():
     pr = rbslam.synth.sparse_visual_problem(N_T=20, n_landmarks=5, N_P=6, seed=1)
     assert pr["y"].shape == (20, 5) and pr["x0_lin"].shape == (10, 6)
     assert np.isnan(pr["y"]).any()
+
+
+def test_mex_gateway_compiles_against_stub_header():
+    """No MATLAB in the image: the gateway is syntax/type-checked against mex/stub/mex.h."""
+    import subprocess
+    mexdir = os.path.join(PKG, "mex")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(mexdir, "stub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(mexdir, "rbslam_mex.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the MATLAB shims keep the reference's signatures
+    for name, args in [("particleFilter", "dynModel,measModel,odometry,y"),
+                       ("particleSmoother", "dynModel,measModel,dynResNorm,odometry,y"),
+                       ("particleSmootherInformationForm", "dynModel,measModel,dynResNorm,odometry,y")]:
+        src = open(os.path.join(PKG, "matlab", name + ".m")).read()
+        assert name + "(" + args in src.replace(" ", "").replace("...\n", "")
