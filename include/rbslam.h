@@ -222,11 +222,22 @@ RBSLAM_API int rbslam_op_dyn_logweight(rbslam_ctx *ctx, int32_t N, const double 
    n_migrate (total). */
 RBSLAM_API int rbslam_plan_migration(int32_t N, int32_t world, const int32_t *ai, const int32_t *old_owner,
                           int32_t *new_owner, int32_t *n_migrate);
-/* CUDA-IPC export of this rank's covariance slab allocation (64-byte handle) and
-   import of a peer's; after all peers are imported the resampling gather reads
-   ancestor slabs straight from peer HBM over NVLink. */
-RBSLAM_API int rbslam_ipc_export(rbslam_ctx *ctx, void *handle64);
-RBSLAM_API int rbslam_ipc_import(rbslam_ctx *ctx, int32_t peer_rank, const void *handle64);
+/* Full per-step plan of the sharded engine (host only, deterministic, identical on every
+   rank): owner and local slab slot of every new particle.  First offspring staying on the
+   ancestor's rank keep the ancestor's slab; migrants are placed in DEAD slabs (no offspring
+   anywhere) because they are fetched before the peer barrier. */
+RBSLAM_API int rbslam_plan_shard(int32_t N, int32_t world, const int32_t *ai, const int32_t *owner_old,
+                                 const int32_t *lslot_old, int32_t *owner_new, int32_t *lslot_new,
+                                 int32_t *n_migrate);
+/* A context created with world > 1 owns N/world slabs and shares rbslam_ipc_count() device
+   buffers with its peers through CUDA IPC (64-byte handles exchanged by the host): slabs,
+   pending (G,KS) ping-pong, xl ping-pong, the replicated log-weight array and the barrier
+   flags.  After every peer's handles are imported, rbslam_filter_begin/step/end run the
+   SHARDED filter: migrants' state is read straight from the exporter's HBM over NVLink,
+   log-weights are all-gathered by peer stores, barriers are flags in peer memory. */
+RBSLAM_API int rbslam_ipc_count(void);
+RBSLAM_API int rbslam_ipc_export(rbslam_ctx *ctx, int32_t which, void *handle64);
+RBSLAM_API int rbslam_ipc_import(rbslam_ctx *ctx, int32_t peer_rank, int32_t which, const void *handle64);
 /* collective hooks supplied by the host (torch.distributed/NCCL in Python, NCCL in
    the MEX gateway): all-gather of the per-rank log-weight blocks and a barrier.
    Both are called with DEVICE pointers on the context's stream. */

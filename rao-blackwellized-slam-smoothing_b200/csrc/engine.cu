@@ -229,8 +229,9 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   }
   if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world)
     return ctx->fail(RBSLAM_EARG, "bad rank/world");
-  if (cfg->world > 1) return ctx->fail(RBSLAM_EARG, "world>1: use the sharded entry points");
-  ctx->N = cfg->N; ctx->T = cfg->T; ctx->M = mc.M; ctx->d = mc.d; ctx->n = mc.n;
+  if (cfg->world > 1 && cfg->N % cfg->world) return ctx->fail(RBSLAM_EARG, "N must be divisible by world");
+  ctx->N = cfg->N / cfg->world;   // local particle count (== N on one GPU)
+  ctx->T = cfg->T; ctx->M = mc.M; ctx->d = mc.d; ctx->n = mc.n;
   ctx->nz = mc.nz; ctx->nw = mc.nw; ctx->n_odo = mc.n_odo;
   const int M = ctx->M, N = ctx->N, T = ctx->T, d = ctx->d, n = ctx->n;
   ctx->ld = cfg->ld > 0 ? cfg->ld : ((M + 7) / 8) * 8;
@@ -336,6 +337,10 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
     CK(cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_resample_max));
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  if (cfg->world > 1) {
+    int rcs = rb_shard_create(ctx, cfg->world, cfg->rank, cfg->N);
+    if (rcs) return rcs;
+  }
   return RBSLAM_OK;
 }
 
@@ -365,6 +370,7 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_run_inputs(ctx);
   rb_smoother_free(ctx);
+  rb_shard_free(ctx);
   void *ptrs[] = {ctx->d_NN, ctx->d_P, ctx->d_Imat, ctx->d_xl[0], ctx->d_xl[1], ctx->d_ivec[0],
                   ctx->d_ivec[1], ctx->d_hld[0], ctx->d_hld[1], ctx->d_slot[0], ctx->d_slot[1],
                   ctx->d_src_slot, ctx->d_first_child, ctx->d_free_list, ctx->d_listA, ctx->d_listB,
@@ -684,7 +690,8 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled) {
   a.src_slot = ctx->d_src_slot;
   a.dst_slot = ctx->d_slot[ctx->cs];
   a.xl_old = ctx->d_xl[ctx->cx];
-  a.ai = resampled ? ctx->d_Ahist + (size_t)(ctx->t % ctx->T_hist) * N : nullptr;
+  a.ai = ctx->anc_override ? ctx->anc_override
+                           : (resampled ? ctx->d_Ahist + (size_t)(ctx->t % ctx->T_hist) * N : nullptr);
   a.xl_new = ctx->d_xl[1 - ctx->cx];
   a.H = ctx->d_H;
   a.yhat = ctx->mc.family == FAM_SPARSE_VISUAL2D ? ctx->d_yhat : nullptr;
@@ -836,6 +843,7 @@ static int filter_step_impl(rbslam_ctx *ctx) {
 
 extern "C" int rbslam_filter_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
   if (!ctx) return RBSLAM_EARG;
+  if (ctx->shard_ws) return rb_shard_begin(ctx, in);
   int rc = rb_upload_inputs(ctx, in, 1);
   if (rc) return rc;
   ctx->jitter = 1e-3;   // src/particleFilter.m:89
@@ -848,6 +856,7 @@ extern "C" int rbslam_filter_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
 
 extern "C" int rbslam_filter_step(rbslam_ctx *ctx) {
   if (!ctx) return RBSLAM_EARG;
+  if (ctx->shard_ws) return rb_shard_step(ctx);
   return filter_step_impl(ctx);
 }
 
@@ -860,6 +869,7 @@ int rb_enable_taps(rbslam_ctx *ctx, bool logw, bool w) {
 
 extern "C" int rbslam_filter_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
   if (!ctx || !out) return RBSLAM_EARG;
+  if (ctx->shard_ws) return rb_shard_end(ctx, out);
   if (!ctx->running) return ctx->fail(RBSLAM_EARG, "filter_end without filter_begin");
   CK(cudaSetDevice(ctx->cfg.device));
   const int N = ctx->N, M = ctx->M, n = ctx->n, T = ctx->t;
@@ -929,9 +939,9 @@ extern "C" int rbslam_filter_run(rbslam_ctx *ctx, const rbslam_inputs *in, rbsla
   if (!ctx || !in || !out) return RBSLAM_EARG;
   int rc = rbslam_filter_begin(ctx, in);
   if (rc) return rc;
-  if ((rc = rb_enable_taps(ctx, out->logw_hist != nullptr, out->w_hist != nullptr))) return rc;
+  if (!ctx->shard_ws && (rc = rb_enable_taps(ctx, out->logw_hist != nullptr, out->w_hist != nullptr))) return rc;
   for (int t = 0; t < in->T; ++t)
-    if ((rc = filter_step_impl(ctx))) return rc;
+    if ((rc = rbslam_filter_step(ctx))) return rc;
   return rbslam_filter_end(ctx, out);
 }
 

@@ -85,6 +85,8 @@ struct rbslam_ctx {
   cudaEvent_t user_events[16] = {nullptr};
 
   void *smoother_ws = nullptr;   // SmootherWs (smoother.cu)
+  void *shard_ws = nullptr;      // ShardWs (sharded.cu); N is the LOCAL particle count when set
+  const int *anc_override = nullptr;   // sharded engine: thin arrays are slot-indexed
 
   // collectives (multi-GPU)
   rbslam_allgather_fn ag_fn = nullptr;

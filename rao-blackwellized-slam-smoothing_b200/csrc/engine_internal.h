@@ -47,6 +47,13 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled);
 int rb_normalize_phase(rbslam_ctx *ctx);
 int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host);
 int rb_flush_pending(rbslam_ctx *ctx);
+// sharded.cu
+int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN);
+void rb_shard_free(rbslam_ctx *ctx);
+int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in);
+int rb_shard_step(rbslam_ctx *ctx);
+int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out);
+int64_t rb_shard_migrated(rbslam_ctx *ctx);
 // smoother.cu
 int rb_info_init(rbslam_ctx *ctx);
 void rb_smoother_free(rbslam_ctx *ctx);

@@ -246,20 +246,6 @@ extern "C" int rbslam_plan_migration(int32_t N, int32_t world, const int32_t *ai
   return RBSLAM_OK;
 }
 
-extern "C" int rbslam_ipc_export(rbslam_ctx *ctx, void *handle64) {
-  if (!ctx || !handle64) return RBSLAM_EARG;
-  CK(cudaSetDevice(ctx->cfg.device));
-  cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, ctx->d_P));
-  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  memcpy(handle64, &h, 64);
-  return RBSLAM_OK;
-}
-
-extern "C" int rbslam_ipc_import(rbslam_ctx *ctx, int32_t, const void *) {
-  return ctx ? ctx->fail(RBSLAM_EARG, "peer import is part of the sharded engine (not built yet)") : RBSLAM_EARG;
-}
-
 extern "C" int rbslam_set_collectives(rbslam_ctx *ctx, rbslam_allgather_fn ag, rbslam_barrier_fn bar, void *user) {
   if (!ctx) return RBSLAM_EARG;
   ctx->ag_fn = ag; ctx->bar_fn = bar; ctx->coll_user = user;

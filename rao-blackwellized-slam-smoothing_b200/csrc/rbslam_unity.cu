@@ -3,3 +3,4 @@
 #include "engine.cu"
 #include "smoother.cu"
 #include "ops.cu"
+#include "sharded.cu"

@@ -1,0 +1,463 @@
+// librbslam: one particle filter sharded over the GPUs of a node (one process per GPU).
+//
+// Particles are exchangeable within a step; ranks are coupled only through the weight
+// normalisation and the resampling.  Every rank owns N/G covariance slabs (plus the thin
+// per-slab arrays) and REPLICATES everything that is O(N): poses, weights, ancestors,
+// the owner/slot maps.  Per step:
+//   1. every rank draws the same ancestors from the same weights (k_resample, bit-exact),
+//   2. every rank derives the same migration plan on the host (rbslam_plan_shard):
+//      offspring stay on their ancestor's rank up to the rank's capacity, only the surplus
+//      migrates; a rank either exports or imports, so migrants always land in DEAD slabs,
+//   3. importers pull the migrants' ancestor state (slab, pending (G,KS), xl) straight out
+//      of the exporter's HBM over NVLink with plain peer loads (k_peer_fetch; buffers are
+//      mapped with CUDA IPC), then a peer barrier (flags in peer memory, system-scope
+//      release/acquire) lets exporters reuse the slabs that were read,
+//   4. the local streaming Kalman pass runs exactly as on one GPU (slot-indexed),
+//   5. every rank stores its log-weights into every peer's replicated array (peer stores),
+//      a second peer barrier, and every rank normalises the identical N log-weights with
+//      the same fixed reduction tree -> identical weights on all ranks, independent of G.
+// No NCCL call sits in the step loop; NCCL/gloo are only used by the host to exchange the
+// 64-byte IPC handles once.
+#include <vector>
+#include <algorithm>
+#include <cstring>
+#include "engine_internal.h"
+#include "step_kernels.cuh"
+
+using namespace rb;
+
+#define RB_MAXW 8
+enum { SH_P = 0, SH_G4A, SH_G4B, SH_KS4A, SH_KS4B, SH_XLA, SH_XLB, SH_LOGW, SH_FLAGS, SH_COUNT };
+
+struct PeerTable {
+  void *p[SH_COUNT][RB_MAXW];
+};
+
+struct ShardWs {
+  int world = 1, rank = 0, gN = 0, Nloc = 0;
+  double *g_Xhist = nullptr, *g_w = nullptr, *g_wc = nullptr, *g_logw = nullptr;
+  double *traj_max = nullptr, *traj_mean = nullptr;
+  int *g_Ahist = nullptr, *iwmax = nullptr;
+  unsigned long long *flags = nullptr;
+  int *d_glob = nullptr, *d_fetch = nullptr, *d_owner = nullptr, *d_lslot = nullptr;
+  PeerTable peers{};
+  bool imported[SH_COUNT][RB_MAXW] = {};
+  std::vector<int> owner[2], lslot[2];
+  int cur = 0;
+  unsigned long long epoch = 0;
+  std::vector<int> h_ai, h_src, h_listA, h_listB, h_glob, h_fetch;
+  int64_t migrated = 0;
+};
+
+static ShardWs *sh_of(rbslam_ctx *ctx) { return static_cast<ShardWs *>(ctx->shard_ws); }
+
+void rb_shard_free(rbslam_ctx *ctx) {
+  ShardWs *s = sh_of(ctx);
+  if (!s) return;
+  for (int w = 0; w < SH_COUNT; ++w)
+    for (int r = 0; r < RB_MAXW; ++r)
+      if (s->imported[w][r]) cudaIpcCloseMemHandle(s->peers.p[w][r]);
+  void *ptrs[] = {s->g_Xhist, s->g_w, s->g_wc, s->g_logw, s->traj_max, s->traj_mean, s->g_Ahist, s->iwmax,
+                  s->flags, s->d_glob, s->d_fetch, s->d_owner, s->d_lslot};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  delete s;
+  ctx->shard_ws = nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// host planner (pure integer logic; exported for the CPU tests)
+// ---------------------------------------------------------------------------
+extern "C" int rbslam_plan_shard(int32_t N, int32_t world, const int32_t *ai, const int32_t *owner_old,
+                                 const int32_t *lslot_old, int32_t *owner_new, int32_t *lslot_new,
+                                 int32_t *n_migrate) {
+  if (N < 1 || world < 1 || N % world || !ai || !owner_old || !lslot_old || !owner_new || !lslot_new)
+    return RBSLAM_EARG;
+  int nm = 0;
+  int rc = rbslam_plan_migration(N, world, ai, owner_old, owner_new, &nm);
+  if (rc) return rc;
+  const int Nloc = N / world;
+  // children anywhere / children staying on the ancestor's rank
+  std::vector<int> n_child(N, 0), keeper(N, -1);
+  for (int i = 0; i < N; ++i) {
+    ++n_child[ai[i]];
+    if (owner_new[i] == owner_old[ai[i]] && keeper[ai[i]] < 0) keeper[ai[i]] = i;   // first local child
+  }
+  // free slots per rank: dead first (no children anywhere), then exported-only
+  std::vector<std::vector<int>> dead(world), expo(world);
+  for (int a = 0; a < N; ++a) {
+    if (keeper[a] >= 0) continue;
+    (n_child[a] == 0 ? dead : expo)[owner_old[a]].push_back(lslot_old[a]);
+  }
+  std::vector<size_t> nd(world, 0), ne(world, 0);
+  // migrants first: they are fetched before the barrier and must land in dead slots
+  for (int i = 0; i < N; ++i) {
+    const int r = owner_new[i];
+    if (owner_old[ai[i]] == r) continue;
+    if (nd[r] >= dead[r].size()) return RBSLAM_EARG;   // cannot happen with the locality planner
+    lslot_new[i] = dead[r][nd[r]++];
+  }
+  for (int i = 0; i < N; ++i) {
+    const int r = owner_new[i], a = ai[i];
+    if (owner_old[a] != r) continue;
+    if (keeper[a] == i) { lslot_new[i] = lslot_old[a]; continue; }
+    if (nd[r] < dead[r].size()) lslot_new[i] = dead[r][nd[r]++];
+    else if (ne[r] < expo[r].size()) lslot_new[i] = expo[r][ne[r]++];
+    else return RBSLAM_EARG;
+  }
+  for (int r = 0; r < world; ++r)
+    if (nd[r] + ne[r] != dead[r].size() + expo[r].size()) return RBSLAM_EARG;
+  (void)Nloc;
+  if (n_migrate) *n_migrate = nm;
+  return RBSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+// pull the ancestor state of every migrant out of the exporter's HBM (NVLink peer loads)
+__global__ void __launch_bounds__(256)
+k_peer_fetch(int n_fetch, const int *__restrict__ fetch, PeerTable pt, int cg, int cx, size_t slab,
+             int ld, int M, double *__restrict__ P, double *__restrict__ G4, double *__restrict__ KS4,
+             double *__restrict__ xl) {
+  const int f = blockIdx.y;
+  if (f >= n_fetch) return;
+  const int j = fetch[4 * f], sr = fetch[4 * f + 1], ss = fetch[4 * f + 2];
+  const double2 *srcP = reinterpret_cast<const double2 *>(static_cast<const double *>(pt.p[SH_P][sr]) + (size_t)ss * slab);
+  double2 *dstP = reinterpret_cast<double2 *>(P + (size_t)j * slab);
+  const size_t n2 = slab / 2;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n2; idx += (size_t)gridDim.x * blockDim.x)
+    dstP[idx] = srcP[idx];
+  if (blockIdx.x == 0) {
+    const double *sg = static_cast<const double *>(pt.p[cg ? SH_G4B : SH_G4A][sr]) + (size_t)ss * ld * 4;
+    const double *sk = static_cast<const double *>(pt.p[cg ? SH_KS4B : SH_KS4A][sr]) + (size_t)ss * ld * 4;
+    const double *sx = static_cast<const double *>(pt.p[cx ? SH_XLB : SH_XLA][sr]) + (size_t)ss * M;
+    for (int idx = threadIdx.x; idx < ld * 4; idx += blockDim.x) {
+      G4[(size_t)j * ld * 4 + idx] = sg[idx];
+      KS4[(size_t)j * ld * 4 + idx] = sk[idx];
+    }
+    for (int idx = threadIdx.x; idx < M; idx += blockDim.x) xl[(size_t)j * M + idx] = sx[idx];
+  }
+}
+
+// every rank stores its local log-weights into every peer's replicated array
+__global__ void k_logw_scatter(int Nloc, int world, const int *__restrict__ glob,
+                               const double *__restrict__ logw_loc, PeerTable pt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Nloc) return;
+  const double v = logw_loc[j];
+  const int g = glob[j];
+  for (int r = 0; r < world; ++r) static_cast<double *>(pt.p[SH_LOGW][r])[g] = v;
+}
+
+// barrier across the GPUs of the node: flags live in every rank's memory, mapped by all
+__global__ void k_peer_barrier(int world, int rank, unsigned long long epoch, PeerTable pt) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  unsigned long long *remote = static_cast<unsigned long long *>(pt.p[SH_FLAGS][r]) + rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
+  const unsigned long long *mine = static_cast<const unsigned long long *>(pt.p[SH_FLAGS][rank]) + r;
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+  } while (v < epoch);
+  __threadfence_system();
+}
+
+__global__ void k_final_means_sharded(int gN, int M, const int *__restrict__ owner,
+                                      const int *__restrict__ lslot, PeerTable pt, int cx,
+                                      const double *__restrict__ w, const int *__restrict__ iw_max,
+                                      double *__restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const int which = cx ? SH_XLB : SH_XLA;
+  const int im = *iw_max;
+  out[r] = static_cast<const double *>(pt.p[which][owner[im]])[(size_t)lslot[im] * M + r];
+  double acc = 0.0;
+  for (int i = 0; i < gN; ++i)
+    acc = fma(static_cast<const double *>(pt.p[which][owner[i]])[(size_t)lslot[i] * M + r], w[i], acc);
+  out[M + r] = acc;
+}
+
+__global__ void k_final_cov_sharded(int M, int ld, const double *__restrict__ Pm, const double *__restrict__ Pl,
+                                    const double *__restrict__ G4m, const double *__restrict__ KS4m,
+                                    const double *__restrict__ G4l, const double *__restrict__ KS4l,
+                                    const double *__restrict__ xll, double wl, const double *__restrict__ means,
+                                    double *__restrict__ Pmax, double *__restrict__ Pmean) {
+  const int c = blockIdx.x;
+  const double *xmean = means + M;
+  const double dc = xmean[c] - xll[c];
+  for (int r = threadIdx.x; r < M; r += blockDim.x) {
+    double pm = Pm[r + (size_t)c * ld], pl = Pl[r + (size_t)c * ld];
+    for (int b = 0; b < 4; ++b) {
+      pm = fma(-KS4m[(size_t)r * 4 + b], G4m[(size_t)c * 4 + b], pm);
+      pl = fma(-KS4l[(size_t)r * 4 + b], G4l[(size_t)c * 4 + b], pl);
+    }
+    Pmax[r + (size_t)c * M] = pm;
+    Pmean[r + (size_t)c * M] = wl * (pl + (xmean[r] - xll[r]) * dc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// setup
+// ---------------------------------------------------------------------------
+int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN) {
+  if (world > RB_MAXW) return ctx->fail(RBSLAM_EARG, "at most 8 ranks (one node)");
+  if (ctx->kpath != 1) return ctx->fail(RBSLAM_EARG, "sharding needs the streaming Kalman path (dense model, M > ~160 or kalman_variant=2)");
+  if (!ctx->cfg.keep_history) return ctx->fail(RBSLAM_EARG, "sharding needs keep_history=1");
+  ShardWs *s = new ShardWs();
+  ctx->shard_ws = s;
+  s->world = world; s->rank = rank; s->gN = gN; s->Nloc = gN / world;
+  const int T = ctx->T, n = ctx->n;
+  RB_ALLOC(s->g_Xhist, (size_t)T * gN * n);
+  RB_ALLOC(s->g_Ahist, (size_t)T * gN);
+  RB_ALLOC(s->g_w, gN); RB_ALLOC(s->g_wc, gN); RB_ALLOC(s->g_logw, gN);
+  RB_ALLOC(s->traj_max, (size_t)T * n); RB_ALLOC(s->traj_mean, (size_t)T * n); RB_ALLOC(s->iwmax, T);
+  RB_ALLOC(s->flags, 64);
+  RB_ALLOC(s->d_glob, s->Nloc); RB_ALLOC(s->d_fetch, (size_t)4 * s->Nloc);
+  RB_ALLOC(s->d_owner, gN); RB_ALLOC(s->d_lslot, gN);
+  CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned long long)));
+  void *own[SH_COUNT] = {ctx->d_P, ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_xl[0],
+                         ctx->d_xl[1], s->g_logw, s->flags};
+  for (int w = 0; w < SH_COUNT; ++w) s->peers.p[w][rank] = own[w];
+  return RBSLAM_OK;
+}
+
+extern "C" int rbslam_ipc_export(rbslam_ctx *ctx, int32_t which, void *handle64) {
+  if (!ctx || !handle64 || which < 0 || which >= SH_COUNT) return RBSLAM_EARG;
+  ShardWs *s = sh_of(ctx);
+  if (!s) return ctx->fail(RBSLAM_EARG, "context is not sharded (world == 1)");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, s->peers.p[which][s->rank]));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return RBSLAM_OK;
+}
+
+extern "C" int rbslam_ipc_import(rbslam_ctx *ctx, int32_t peer, int32_t which, const void *handle64) {
+  if (!ctx || !handle64 || which < 0 || which >= SH_COUNT) return RBSLAM_EARG;
+  ShardWs *s = sh_of(ctx);
+  if (!s || peer < 0 || peer >= s->world || peer == s->rank) return ctx->fail(RBSLAM_EARG, "bad peer");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  s->peers.p[which][peer] = p;
+  s->imported[which][peer] = true;
+  return RBSLAM_OK;
+}
+
+extern "C" int rbslam_ipc_count(void) { return SH_COUNT; }
+
+// ---------------------------------------------------------------------------
+// sharded filter
+// ---------------------------------------------------------------------------
+static int peer_barrier(rbslam_ctx *ctx) {
+  ShardWs *s = sh_of(ctx);
+  ++s->epoch;
+  k_peer_barrier<<<1, 32, 0, ctx->stream>>>(s->world, s->rank, s->epoch, s->peers);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return RBSLAM_OK;
+}
+
+int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
+  ShardWs *s = sh_of(ctx);
+  for (int w = 0; w < SH_COUNT; ++w)
+    for (int r = 0; r < s->world; ++r)
+      if (!s->peers.p[w][r]) return ctx->fail(RBSLAM_EARG, "peer buffers not imported (rbslam_ipc_import)");
+  if (in->x0_lin_cols != 1) return ctx->fail(RBSLAM_EARG, "sharded filter takes a single x0_lin column");
+  if (in->U || in->Z || in->forced_ancestors)
+    return ctx->fail(RBSLAM_EARG, "sharded filter uses the device Philox stream (rng_mode PHILOX)");
+  int rc = rb_upload_inputs(ctx, in, 1);
+  if (rc) return rc;
+  ctx->jitter = 1e-3;
+  ctx->sweep = 0;
+  CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(DevStatus), ctx->stream));
+  if ((rc = rb_init_state(ctx, false))) return rc;   // local slabs, xl, pending = 0, slot = identity
+  const int gN = s->gN, n = ctx->n, Nloc = s->Nloc;
+  double *x0d = ctx->d_scratch;
+  CK(cudaMemcpyAsync(x0d, ctx->h_x0n.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_init_xn<<<(n * gN + 255) / 256, 256, 0, ctx->stream>>>(s->g_Xhist, n, gN, x0d);
+  k_fill<<<(gN + 255) / 256, 256, 0, ctx->stream>>>(s->g_w, (size_t)gN, 1.0 / gN);
+  ctx->launches += 2;
+  // block distribution: particle i lives on rank i / Nloc at slot i % Nloc
+  for (int b = 0; b < 2; ++b) { s->owner[b].assign(gN, 0); s->lslot[b].assign(gN, 0); }
+  for (int i = 0; i < gN; ++i) { s->owner[0][i] = i / Nloc; s->lslot[0][i] = i % Nloc; }
+  s->cur = 0;
+  s->h_glob.assign(Nloc, 0);
+  for (int j = 0; j < Nloc; ++j) s->h_glob[j] = s->rank * Nloc + j;
+  CK(cudaMemcpyAsync(s->d_glob, s->h_glob.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
+  s->migrated = 0;
+  ctx->running = true;
+  ctx->t = 0;
+  if ((rc = peer_barrier(ctx))) return rc;   // nobody starts before everybody is initialised
+  return RBSLAM_OK;
+}
+
+int rb_shard_step(rbslam_ctx *ctx) {
+  ShardWs *s = sh_of(ctx);
+  if (!ctx->running) return ctx->fail(RBSLAM_EARG, "filter_step without filter_begin");
+  if (ctx->t >= ctx->run_T) return ctx->fail(RBSLAM_EARG, "all time steps already processed");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int gN = s->gN, Nloc = s->Nloc, t = ctx->t, n = ctx->n, d = ctx->d, M = ctx->M;
+  int rc;
+  double *xn_t = s->g_Xhist + (size_t)t * gN * n;
+  const bool resampled = t > 0;
+  if (resampled) {
+    rb_phase_begin(ctx, RB_PH_RESAMPLE);
+    int *ai = s->g_Ahist + (size_t)t * gN;
+    RngSrc rs;
+    rs.U = nullptr; rs.seed = ctx->cfg.seed; rs.sweep = 0; rs.t = t;
+    size_t smem = sizeof(double) * (size_t)gN;
+    if (smem > ctx->smem_resample_max) smem = 0;
+    k_resample<<<1, 1024, smem, ctx->stream>>>(gN, 0, gN, s->g_w, s->g_wc, rs, nullptr, ai, ctx->d_status);
+    ctx->launches += 1;
+    // identical plan on every rank (host, pure integer logic)
+    s->h_ai.resize(gN);
+    if ((rc = rb_d2h(ctx, s->h_ai.data(), ai, sizeof(int) * gN))) return rc;
+    const int o = s->cur, nw = 1 - s->cur;
+    int nmig = 0;
+    if (rbslam_plan_shard(gN, s->world, s->h_ai.data(), s->owner[o].data(), s->lslot[o].data(),
+                          s->owner[nw].data(), s->lslot[nw].data(), &nmig) != RBSLAM_OK)
+      return ctx->fail(RBSLAM_EARG, "internal: shard plan failed");
+    s->migrated += nmig;
+    s->h_src.assign(Nloc, 0); s->h_listA.clear(); s->h_listB.clear(); s->h_fetch.clear();
+    for (int i = 0; i < gN; ++i) {
+      if (s->owner[nw][i] != s->rank) continue;
+      const int j = s->lslot[nw][i], a = s->h_ai[i];
+      s->h_glob[j] = i;
+      if (s->owner[o][a] != s->rank) {          // migrant: fetched into slot j, then updated in place
+        s->h_fetch.push_back(j); s->h_fetch.push_back(s->owner[o][a]); s->h_fetch.push_back(s->lslot[o][a]);
+        s->h_fetch.push_back(0);
+        s->h_src[j] = j; s->h_listB.push_back(j);
+      } else {
+        s->h_src[j] = s->lslot[o][a];
+        (s->h_src[j] == j ? s->h_listB : s->h_listA).push_back(j);
+      }
+    }
+    s->cur = nw;
+    const int nA = (int)s->h_listA.size(), nB = (int)s->h_listB.size(), nF = (int)s->h_fetch.size() / 4;
+    const int counts[2] = {nA, nB};
+    CK(cudaMemcpyAsync(ctx->d_src_slot, s->h_src.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
+    if (nA) CK(cudaMemcpyAsync(ctx->d_listA, s->h_listA.data(), sizeof(int) * nA, cudaMemcpyHostToDevice, ctx->stream));
+    if (nB) CK(cudaMemcpyAsync(ctx->d_listB, s->h_listB.data(), sizeof(int) * nB, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(s->d_glob, s->h_glob.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
+    if (nF) CK(cudaMemcpyAsync(s->d_fetch, s->h_fetch.data(), sizeof(int) * 4 * nF, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // the host vectors are reused next step
+    ctx->h2d += (int64_t)sizeof(int) * (3 * Nloc + 4 * nF);
+    rb_phase_end(ctx);
+    rb_phase_begin(ctx, RB_PH_PROPAGATE);
+    NormalSrc ns;
+    ns.Z = nullptr; ns.seed = ctx->cfg.seed; ns.sweep = 0; ns.t = t;
+    const double *Qp = ctx->d_Q + (ctx->Q_pages > 1 ? (size_t)(t - 1) * ctx->nw * ctx->nw : 0);
+    k_propagate<<<(gN + 127) / 128, 128, 0, ctx->stream>>>(ctx->mc, gN, gN, s->g_Xhist + (size_t)(t - 1) * gN * n, ai,
+                                                           ctx->d_odo + (size_t)(t - 1) * ctx->n_odo, ctx->h_dt[t - 1],
+                                                           Qp, ns, xn_t);
+    ctx->launches += 1;
+    rb_phase_end(ctx);
+    rb_phase_begin(ctx, RB_PH_ANCESTOR);   // reported as the "migration" phase
+    if (nF) {
+      k_peer_fetch<<<dim3(16, nF), 256, 0, ctx->stream>>>(nF, s->d_fetch, s->peers, ctx->cg, ctx->cx, ctx->slab,
+                                                          ctx->ld, M, ctx->d_P, ctx->d_G4[ctx->cg], ctx->d_KS4[ctx->cg],
+                                                          ctx->d_xl[ctx->cx]);
+      ctx->launches += 1;
+    }
+    if ((rc = peer_barrier(ctx))) return rc;   // all remote reads of old slabs are done
+    rb_phase_end(ctx);
+  } else {
+    k_plan_identity<<<(Nloc + 255) / 256, 256, 0, ctx->stream>>>(Nloc, ctx->d_slot[ctx->cs], ctx->d_src_slot,
+                                                                ctx->d_listB, ctx->d_counts);
+    ctx->launches += 1;
+  }
+  rb_phase_begin(ctx, RB_PH_MEAS);
+  k_meas<<<Nloc, 128, 0, ctx->stream>>>(ctx->mc, Nloc, xn_t, nullptr, M, nullptr, ctx->d_H, ctx->hs_p, ctx->hs_a,
+                                        ctx->hs_c, ctx->ld, nullptr, s->d_glob);
+  ctx->launches += 1;
+  rb_phase_end(ctx);
+  rb_phase_begin(ctx, RB_PH_KALMAN);
+  ctx->anc_override = ctx->d_src_slot;     // thin arrays are slot-indexed: ancestor index = source slot
+  rc = rb_kalman_phase(ctx, ctx->d_y + (size_t)t * d, resampled);
+  ctx->anc_override = nullptr;
+  rb_phase_end(ctx);
+  if (rc) return rc;
+  rb_phase_begin(ctx, RB_PH_NORMALIZE);
+  k_logw_scatter<<<(Nloc + 127) / 128, 128, 0, ctx->stream>>>(Nloc, s->world, s->d_glob, ctx->d_logw, s->peers);
+  ctx->launches += 1;
+  if ((rc = peer_barrier(ctx))) return rc;
+  k_normalize<<<1, 1024, 0, ctx->stream>>>(gN, n, s->g_logw, s->g_w, xn_t, s->traj_max + (size_t)t * n,
+                                           s->traj_mean + (size_t)t * n, s->iwmax + t, nullptr, nullptr);
+  ctx->launches += 1;
+  rb_phase_end(ctx);
+  CK(cudaGetLastError());
+  ctx->t += 1;
+  return RBSLAM_OK;
+}
+
+int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
+  ShardWs *s = sh_of(ctx);
+  const int gN = s->gN, M = ctx->M, n = ctx->n, T = ctx->t, ld = ctx->ld;
+  if (T < 1) return ctx->fail(RBSLAM_EARG, "no step was run");
+  int rc = rb_check_status(ctx);
+  if (rc) return rc;
+  if (s->rank == 0) {
+    const int cur = s->cur;
+    CK(cudaMemcpyAsync(s->d_owner, s->owner[cur].data(), sizeof(int) * gN, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(s->d_lslot, s->lslot[cur].data(), sizeof(int) * gN, cudaMemcpyHostToDevice, ctx->stream));
+    const int *iw = s->iwmax + (T - 1);
+    double *means = ctx->d_scratch;
+    double *Pmax = ctx->d_scratch + 2 * (size_t)M + 64, *Pmean = Pmax + (size_t)M * M;
+    k_final_means_sharded<<<(M + 127) / 128, 128, 0, ctx->stream>>>(gN, M, s->d_owner, s->d_lslot, s->peers, ctx->cx,
+                                                                   s->g_w, iw, means);
+    ctx->launches += 1;
+    int im = 0;
+    double wl = 0.0;
+    if ((rc = rb_d2h(ctx, &im, iw, sizeof(int)))) return rc;
+    if ((rc = rb_d2h(ctx, &wl, s->g_w + (gN - 1), sizeof(double)))) return rc;
+    auto at = [&](int which, int i, size_t stride) {
+      return static_cast<const double *>(s->peers.p[which][s->owner[cur][i]]) + (size_t)s->lslot[cur][i] * stride;
+    };
+    const int gsel = ctx->cg ? SH_G4B : SH_G4A, ksel = ctx->cg ? SH_KS4B : SH_KS4A, xsel = ctx->cx ? SH_XLB : SH_XLA;
+    const size_t t4 = (size_t)ld * 4;
+    k_final_cov_sharded<<<M, 128, 0, ctx->stream>>>(M, ld, at(SH_P, im, ctx->slab), at(SH_P, gN - 1, ctx->slab),
+                                                    at(gsel, im, t4), at(ksel, im, t4), at(gsel, gN - 1, t4),
+                                                    at(ksel, gN - 1, t4), at(xsel, gN - 1, M), wl, means, Pmax, Pmean);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    if (out->traj_max && (rc = rb_d2h(ctx, out->traj_max, s->traj_max, sizeof(double) * n * T))) return rc;
+    if (out->traj_mean && (rc = rb_d2h(ctx, out->traj_mean, s->traj_mean, sizeof(double) * n * T))) return rc;
+    if (out->xl_max && (rc = rb_d2h(ctx, out->xl_max, means, sizeof(double) * M))) return rc;
+    if (out->xl_mean && (rc = rb_d2h(ctx, out->xl_mean, means + M, sizeof(double) * M))) return rc;
+    if (out->P_max && (rc = rb_d2h(ctx, out->P_max, Pmax, sizeof(double) * M * M))) return rc;
+    if (out->P_mean && (rc = rb_d2h(ctx, out->P_mean, Pmean, sizeof(double) * M * M))) return rc;
+    if (out->traj_sample_iwmax) {
+      double *tmp = nullptr;
+      RB_ALLOC(tmp, (size_t)n * T);
+      k_trace<<<1, 32, 0, ctx->stream>>>(gN, n, T, s->g_Xhist, s->g_Ahist, iw, tmp);
+      ctx->launches += 1;
+      rc = rb_d2h(ctx, out->traj_sample_iwmax, tmp, sizeof(double) * n * T);
+      cudaFree(tmp);
+      if (rc) return rc;
+    }
+    if (out->xn_traj) {
+      double *tmp = nullptr;
+      RB_ALLOC(tmp, (size_t)n * gN * T);
+      k_trace<<<(gN + 127) / 128, 128, 0, ctx->stream>>>(gN, n, T, s->g_Xhist, s->g_Ahist, nullptr, tmp);
+      ctx->launches += 1;
+      rc = rb_d2h(ctx, out->xn_traj, tmp, sizeof(double) * n * gN * T);
+      cudaFree(tmp);
+      if (rc) return rc;
+    }
+    if (out->ancestors && (rc = rb_d2h(ctx, out->ancestors, s->g_Ahist, sizeof(int) * (size_t)gN * T))) return rc;
+  }
+  // peers keep their slabs alive until rank 0 has read what it needs
+  if ((rc = peer_barrier(ctx))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->running = false;
+  return rb_check_status(ctx);
+}
+
+int64_t rb_shard_migrated(rbslam_ctx *ctx) { return sh_of(ctx) ? sh_of(ctx)->migrated : 0; }

@@ -215,12 +215,13 @@ __global__ void k_dyn_logweight(ModelConsts mc, int N, const double *__restrict_
 __global__ void __launch_bounds__(128)
 k_meas(ModelConsts mc, int N, const double *__restrict__ xn, const double *__restrict__ xl,
        int ldxl, const int *__restrict__ xl_index, double *__restrict__ H, size_t hs_p, int hs_a,
-       int hs_c, int ldpad, double *__restrict__ yhat) {
+       int hs_c, int ldpad, double *__restrict__ yhat, const int *__restrict__ pidx = nullptr) {
   const int i = blockIdx.x;
   if (i >= N) return;
   __shared__ double s_sin[3][RB_MAXTAB], s_cos[3][RB_MAXTAB];
   __shared__ double s_x[7];
-  if (threadIdx.x < mc.n) s_x[threadIdx.x] = xn[threadIdx.x + (size_t)i * mc.n];
+  // pidx: pose index of item i (sharded engine: item = local slab, pose = global particle)
+  if (threadIdx.x < mc.n) s_x[threadIdx.x] = xn[threadIdx.x + (size_t)(pidx ? pidx[i] : i) * mc.n];
   __syncthreads();
   // H_i(a, c) lives at Hi[a*hs_a + c*hs_c]; columns M..ldpad-1 are zero padding
   double *Hi = H + (size_t)i * hs_p;

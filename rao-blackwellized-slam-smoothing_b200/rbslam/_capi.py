@@ -101,8 +101,11 @@ SYMBOLS = {
                                           C.c_double, c_double_p, C.c_int32, c_double_p]),
     "rbslam_plan_migration": (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p,
                                         c_int32_p]),
-    "rbslam_ipc_export": (C.c_int, [_ctx, C.c_void_p]),
-    "rbslam_ipc_import": (C.c_int, [_ctx, C.c_int32, C.c_void_p]),
+    "rbslam_plan_shard": (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+                                    c_int32_p, c_int32_p]),
+    "rbslam_ipc_count": (C.c_int, []),
+    "rbslam_ipc_export": (C.c_int, [_ctx, C.c_int32, C.c_void_p]),
+    "rbslam_ipc_import": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p]),
     "rbslam_set_collectives": (C.c_int, [_ctx, ALLGATHER_FN, BARRIER_FN, C.c_void_p]),
 }
 

@@ -36,7 +36,7 @@ class Context:
     """Owns one rbslam_ctx (one GPU)."""
 
     def __init__(self, model, N, T, device=0, rng_mode=_capi.RNG_PHILOX, seed=0,
-                 information_form=False, keep_history=True, ld=0, kalman_variant=0):
+                 information_form=False, keep_history=True, ld=0, kalman_variant=0, rank=0, world=1):
         self._lib = _capi.lib()
         self.model = model
         self.N, self.T = int(N), int(T)
@@ -55,7 +55,8 @@ class Context:
         cfg.ld = ld
         cfg.information_form = int(information_form)
         cfg.keep_history = int(keep_history)
-        cfg.rank, cfg.world = 0, 1
+        cfg.rank, cfg.world = rank, world
+        self.rank, self.world = rank, world
         cfg.kalman_variant = kalman_variant
         self._h = C.c_void_p()
         rc = self._lib.rbslam_create(C.byref(self._h), C.byref(cfg))
@@ -261,6 +262,26 @@ class Context:
         out.AI = _capi.dptr(o.get("AI"))
         self._ck(self._lib.rbslam_smoother_run(self._h, C.byref(inp), N_K, form, C.byref(out)))
         return o
+
+    # -- sharding (one process per GPU) --------------------------------------
+    def ipc_export(self, which):
+        buf = C.create_string_buffer(64)
+        self._ck(self._lib.rbslam_ipc_export(self._h, which, buf))
+        return buf.raw
+
+    def ipc_import(self, peer, which, handle):
+        self._ck(self._lib.rbslam_ipc_import(self._h, peer, which, C.create_string_buffer(handle, 64)))
+
+    def connect_peers(self, all_gather_object):
+        """Exchange the CUDA-IPC handles of the shared buffers with every peer.
+        ``all_gather_object(obj) -> list`` is any host collective (torch.distributed)."""
+        n = self._lib.rbslam_ipc_count()
+        mine = [self.ipc_export(w) for w in range(n)]
+        everyone = all_gather_object(mine)
+        for r, hs in enumerate(everyone):
+            if r != self.rank:
+                for w, h in enumerate(hs):
+                    self.ipc_import(r, w, h)
 
     # -- timing / counters ---------------------------------------------------
     def event_record(self, slot):

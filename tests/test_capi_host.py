@@ -145,3 +145,40 @@ def test_mex_gateway_compiles_against_stub_header():
                        ("particleSmootherInformationForm", "dynModel,measModel,dynResNorm,odometry,y")]:
         src = open(os.path.join(PKG, "matlab", name + ".m")).read()
         assert name + "(" + args in src.replace(" ", "").replace("...\n", "")
+
+
+def test_plan_shard_invariants():
+    """Slot-level plan of the sharded engine: permutation per rank, in-place keepers,
+    migrants only into dead slots."""
+    _build()
+    from rbslam import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(5)
+    for world in (2, 4, 8):
+        N = 64 * world
+        Nloc = N // world
+        owner = (np.arange(N) // Nloc).astype(np.int32)
+        lslot = (np.arange(N) % Nloc).astype(np.int32)
+        for step in range(6):
+            w = rng.random(N) ** (1 + 4 * (step % 3))
+            ai = rng.choice(N, size=N, p=w / w.sum()).astype(np.int32)
+            no, nl = np.zeros(N, np.int32), np.zeros(N, np.int32)
+            nm = C.c_int32()
+            rc = L.rbslam_plan_shard(N, world, _capi.iptr(ai), _capi.iptr(owner), _capi.iptr(lslot),
+                                     _capi.iptr(no), _capi.iptr(nl), C.byref(nm))
+            assert rc == 0
+            n_child = np.bincount(ai, minlength=N)
+            for r in range(world):
+                mine = np.flatnonzero(no == r)
+                assert len(mine) == Nloc and sorted(nl[mine]) == list(range(Nloc))   # permutation
+            for i in range(N):
+                a = ai[i]
+                if owner[a] != no[i]:                       # migrant -> slot of a DEAD old particle
+                    old = np.flatnonzero((owner == no[i]) & (lslot == nl[i]))[0]
+                    assert n_child[old] == 0
+            for a in np.flatnonzero(n_child):
+                kids = np.flatnonzero((ai == a) & (no == owner[a]))
+                if len(kids):                               # first local child keeps the slab
+                    assert nl[kids[0]] == lslot[a]
+                    assert np.count_nonzero(nl[kids] == lslot[a]) == 1
+            owner, lslot = no.copy(), nl.copy()
