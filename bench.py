@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=10000, help="N_P per GPU (C4: 10^4)")
     ap.add_argument("--basis", type=int, default=1024, help="m eigenfunctions (C4: 1024)")
     ap.add_argument("--variant", type=int, default=0, help="kalman kernel variant (0=auto)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = --particles per GPU (default), strong = --particles in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-particles", type=int, default=64)
     ap.add_argument("--cpu-sample-steps", type=int, default=4)
@@ -203,7 +205,7 @@ def run_cuda(args):
     pr, T = make_problem(m, T)
     gm = rbslam.models.from_problem(pr)
     fargs = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
-    seed = 1 + rank
+    seed = 1          # sharded ranks replicate every O(N) decision: same stream everywhere
 
     def barrier():
         if dist is not None:
@@ -211,8 +213,19 @@ def run_cuda(args):
             torch.cuda.synchronize()
             dist.barrier()
 
-    ctx = rbslam.Context(gm, N, T, device=local_rank, rng_mode=_capi.RNG_PHILOX, seed=seed,
-                         keep_history=True, kalman_variant=args.variant)
+    if world > 1:
+        # ONE filter sharded over the GPUs (peer-memory data path, csrc/sharded.cu)
+        from rbslam.dist import ShardedFilter
+        gN = N * world if args.scaling == "weak" else N
+        if gN % world:
+            raise SystemExit("--particles must be divisible by the number of GPUs")
+        ctx = ShardedFilter(gm, gN, T, rank=rank, world=world, device=local_rank, seed=seed,
+                            kalman_variant=args.variant)
+    else:
+        gN = N
+        ctx = rbslam.Context(gm, N, T, device=local_rank, rng_mode=_capi.RNG_PHILOX, seed=seed,
+                             keep_history=True, kalman_variant=args.variant)
+    n_loc = gN // world
     M, d = ctx.M, ctx.d
     # ---- device-resident measurement ------------------------------------------------
     ctx.filter_begin(*fargs, pr["dt"])
@@ -257,29 +270,33 @@ def run_cuda(args):
         dist.all_reduce(lt)
         launches = int(lt.item())
     if rank == 0:
-        total_particles = N * world
+        total_particles = gN
         value = total_particles * K / (ms / 1e3)
-        bytes_alg_step = N * (16.0 * M * M + 8.0 * M * (2 * d + 2))
+        bytes_alg_step = n_loc * (16.0 * M * M + 8.0 * M * (2 * d + 2))   # per GPU
         kal_ms = phases["kalman"] / K
         peak, peak_src = measured_peak()
         achieved = bytes_alg_step / (kal_ms / 1e3) / 1e9 if kal_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C4 synthetic 3D dense-mag scale-up (BASELINE.json configs[3])",
-                       "N_particles_per_gpu": N, "m_basis": m, "M_linear_states": M, "d_meas": d,
-                       "state_bytes_per_gpu": N * ctx.ld * M * 8,
-                       "parallelism": "replicas" if world > 1 else "single",
-                       "l2": "inputs (%.1f GB of covariance slabs per step) far larger than L2"
-                             % (N * ctx.ld * M * 8 / 1e9),
+                       "N_particles_total": gN, "N_particles_per_gpu": n_loc, "m_basis": m,
+                       "M_linear_states": M, "d_meas": d,
+                       "state_bytes_per_gpu": n_loc * ctx.ld * M * 8,
+                       "parallelism": ("one filter, particles sharded %d per GPU; peer-memory "
+                                       "all-gather of log-weights + migration of surplus slabs" % n_loc)
+                       if world > 1 else "single",
+                       "l2": "inputs (%.1f GB of covariance slabs per GPU per step) far larger than L2"
+                             % (n_loc * ctx.ld * M * 8 / 1e9),
                        "rng": "device Philox4x32-10"},
             "clocks": clocks,
             "e2e": {"value": total_particles * T / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": (cB["h2d_bytes"] - cA["h2d_bytes"]) / T,
                     "d2h_bytes_per_step": (cB["d2h_bytes"] - cA["d2h_bytes"]) / T,
                     "what": "rbslam_filter_run from host buffers: upload, init of %d slabs, %d steps, "
-                            "final extraction, download" % (N, T)},
+                            "final extraction, download" % (n_loc, T)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(M),

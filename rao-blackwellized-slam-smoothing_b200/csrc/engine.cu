@@ -745,7 +745,7 @@ int rb_resample_phase(rbslam_ctx *ctx, int n_draws) {
   rs.seed = ctx->cfg.seed; rs.sweep = ctx->sweep; rs.t = t;
   const int *forced = ctx->have_forced ? ctx->d_forced + soff : nullptr;
   size_t smem = sizeof(double) * (size_t)N;
-  if (smem > ctx->smem_resample_max) smem = 0;
+  smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
   k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, n_draws, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
   ctx->launches += 1;
   CK(cudaGetLastError());

@@ -38,7 +38,7 @@ extern "C" int rbslam_op_resample(rbslam_ctx *ctx, int32_t N, const double *w, i
   RngSrc rs;
   rs.U = d_u; rs.seed = 0; rs.sweep = 0; rs.t = 0;
   size_t smem = sizeof(double) * (size_t)N;
-  if (smem > ctx->smem_resample_max) smem = 0;
+  smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
   k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, n_draws, d_w, d_wc, rs, nullptr, d_ai, ctx->d_status);
   ctx->launches += 1;
   CK(cudaGetLastError());

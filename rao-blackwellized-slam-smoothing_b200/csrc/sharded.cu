@@ -312,7 +312,7 @@ int rb_shard_step(rbslam_ctx *ctx) {
     RngSrc rs;
     rs.U = nullptr; rs.seed = ctx->cfg.seed; rs.sweep = 0; rs.t = t;
     size_t smem = sizeof(double) * (size_t)gN;
-    if (smem > ctx->smem_resample_max) smem = 0;
+    smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
     k_resample<<<1, 1024, smem, ctx->stream>>>(gN, 0, gN, s->g_w, s->g_wc, rs, nullptr, ai, ctx->d_status);
     ctx->launches += 1;
     // identical plan on every rank (host, pure integer logic)

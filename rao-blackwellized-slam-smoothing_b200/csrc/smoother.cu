@@ -747,7 +747,7 @@ extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int
           rs.seed = ctx->cfg.seed; rs.sweep = k; rs.t = t;
           const int *forced = ctx->have_forced ? ctx->d_forced + soff : nullptr;
           size_t smem = sizeof(double) * (size_t)N;
-          if (smem > ctx->smem_resample_max) smem = 0;
+          smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
           k_resample<<<1, 1024, smem, ctx->stream>>>(N, N - 1, 1, w->paNt, ctx->d_wc, rs, forced, ai, ctx->d_status);
           ctx->launches += 2;
           rb_phase_end(ctx);
@@ -794,7 +794,7 @@ extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int
       rs.U = ctx->have_U ? w->Uend + k : nullptr;
       rs.seed = ctx->cfg.seed; rs.sweep = k; rs.t = T;
       size_t smem = sizeof(double) * (size_t)N;
-      if (smem > ctx->smem_resample_max) smem = 0;
+      smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
       k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, 1, ctx->d_w, ctx->d_wc, rs, nullptr, w->ak + k, ctx->d_status);
       ctx->launches += 1;
       if ((rc = rb_d2h(ctx, &h_ak[k], w->ak + k, sizeof(int)))) return rc;

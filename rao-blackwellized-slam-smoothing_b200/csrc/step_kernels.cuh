@@ -21,35 +21,37 @@ __global__ void __launch_bounds__(1024)
 k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__restrict__ wc,
            RngSrc rng, const int *__restrict__ forced, int *__restrict__ ai,
            DevStatus *status) {
-  // draws for particles i0 .. i0+n_draws-1 (uniform U[i] / Philox counter i, result ai[i])
-  extern __shared__ double s_wc[];   // N doubles if it fits, else unused (use_smem=false)
-  __shared__ int use_smem;
-  if (threadIdx.x == 0) {
-    unsigned dyn;
-    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    use_smem = dyn >= (unsigned)N * sizeof(double);
-  }
-  __syncthreads();
-  double *buf = use_smem ? s_wc : wc;
-  if (use_smem) {
-    for (int j = threadIdx.x; j < N; j += blockDim.x) buf[j] = w[j];
+  // draws for particles i0 .. i0+n_draws-1 (uniform U[i] / Philox counter i, result ai[i]).
+  // The scan runs chunk by chunk through shared memory: all threads stage a chunk, ONE thread
+  // adds it up left to right (the rounding order is the contract), all threads write it back.
+  extern __shared__ double s_buf[];
+  __shared__ double s_carry;
+  unsigned dyn;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+  const int chunk = (int)(dyn / sizeof(double));
+  if (threadIdx.x == 0) s_carry = 0.0;
+  for (int c0 = 0; c0 < N; c0 += chunk) {
+    const int cn = min(chunk, N - c0);
+    for (int j = threadIdx.x; j < cn; j += blockDim.x) s_buf[j] = w[c0 + j];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double acc = s_carry;
+      int j = 0;
+      for (; j + 4 <= cn; j += 4) {
+        const double a0 = s_buf[j], a1 = s_buf[j + 1], a2 = s_buf[j + 2], a3 = s_buf[j + 3];
+        acc += a0; s_buf[j] = acc;
+        acc += a1; s_buf[j + 1] = acc;
+        acc += a2; s_buf[j + 2] = acc;
+        acc += a3; s_buf[j + 3] = acc;
+      }
+      for (; j < cn; ++j) { acc += s_buf[j]; s_buf[j] = acc; }
+      s_carry = acc;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cn; j += blockDim.x) wc[c0 + j] = s_buf[j];
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    // serial fp64 chain; loads are independent of the chain so they pipeline
-    double acc = 0.0;
-    const double *src = use_smem ? buf : w;
-    int j = 0;
-    for (; j + 4 <= N; j += 4) {
-      const double a0 = src[j], a1 = src[j + 1], a2 = src[j + 2], a3 = src[j + 3];
-      acc += a0; buf[j] = acc;
-      acc += a1; buf[j + 1] = acc;
-      acc += a2; buf[j + 2] = acc;
-      acc += a3; buf[j + 3] = acc;
-    }
-    for (; j < N; ++j) { acc += src[j]; buf[j] = acc; }
-  }
-  __syncthreads();
+  const double *buf = (N <= chunk) ? s_buf : wc;   // single chunk: search in shared memory
   for (int i = i0 + threadIdx.x; i < i0 + n_draws; i += blockDim.x) {
     int idx;
     if (forced != nullptr) {
@@ -69,9 +71,6 @@ k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__r
       }
     }
     ai[i] = idx;
-  }
-  if (use_smem && wc != nullptr) {
-    for (int j = threadIdx.x; j < N; j += blockDim.x) wc[j] = buf[j];
   }
 }
 
