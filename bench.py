@@ -125,13 +125,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(M):
-    """DRAM bytes per Kalman-update launch set from the committed ncu capture, if any."""
+def ncu_traffic(M, n_particles):
+    """DRAM bytes of one step's Kalman-update launches, scaled from the committed ncu capture
+    (profiles/traffic.json: measured bytes per particle-step at this M), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            d = json.load(open(p))
-            return d.get(str(M))
+            per = json.load(open(p)).get("per_particle_step_bytes", {}).get(str(M))
+            return per * n_particles if per else None
         except Exception:
             pass
     return None
@@ -299,7 +300,7 @@ def run_cuda(args):
                             "final extraction, download" % (n_loc, T)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(M),
+                         "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(M, n_loc),
                          "kernel": "Kalman update phase (gather + log-weight + rank-%d downdate)" % d,
                          "algorithmic_bytes_per_launch": bytes_alg_step,
                          "kernel_ms_per_step": kal_ms, "peak_source": peak_src,
