@@ -238,15 +238,6 @@ RBSLAM_API int rbslam_plan_shard(int32_t N, int32_t world, const int32_t *ai, co
 RBSLAM_API int rbslam_ipc_count(void);
 RBSLAM_API int rbslam_ipc_export(rbslam_ctx *ctx, int32_t which, void *handle64);
 RBSLAM_API int rbslam_ipc_import(rbslam_ctx *ctx, int32_t peer_rank, int32_t which, const void *handle64);
-/* collective hooks supplied by the host (torch.distributed/NCCL in Python, NCCL in
-   the MEX gateway): all-gather of the per-rank log-weight blocks and a barrier.
-   Both are called with DEVICE pointers on the context's stream. */
-typedef int (*rbslam_allgather_fn)(void *user, const void *send_dev, void *recv_dev,
-                                   int64_t bytes_per_rank, void *cuda_stream);
-typedef int (*rbslam_barrier_fn)(void *user, void *cuda_stream);
-RBSLAM_API int rbslam_set_collectives(rbslam_ctx *ctx, rbslam_allgather_fn ag, rbslam_barrier_fn bar,
-                           void *user);
-
 #ifdef __cplusplus
 }
 #endif

@@ -88,10 +88,6 @@ struct rbslam_ctx {
   void *shard_ws = nullptr;      // ShardWs (sharded.cu); N is the LOCAL particle count when set
   const int *anc_override = nullptr;   // sharded engine: thin arrays are slot-indexed
 
-  // collectives (multi-GPU)
-  rbslam_allgather_fn ag_fn = nullptr;
-  rbslam_barrier_fn bar_fn = nullptr;
-  void *coll_user = nullptr;
 
   void fail_cuda(cudaError_t e, const char *what, const char *file, int line);
   int fail(int code, const std::string &msg) { err = msg; return code; }

@@ -245,9 +245,3 @@ extern "C" int rbslam_plan_migration(int32_t N, int32_t world, const int32_t *ai
   if (n_migrate) *n_migrate = (int)surplus.size();
   return RBSLAM_OK;
 }
-
-extern "C" int rbslam_set_collectives(rbslam_ctx *ctx, rbslam_allgather_fn ag, rbslam_barrier_fn bar, void *user) {
-  if (!ctx) return RBSLAM_EARG;
-  ctx->ag_fn = ag; ctx->bar_fn = bar; ctx->coll_user = user;
-  return RBSLAM_OK;
-}

@@ -59,8 +59,6 @@ class SmootherOutputs(C.Structure):
 
 
 STEP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32)
-ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
-BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 
 # every symbol include/rbslam.h declares: name -> (restype, argtypes)
 _ctx = C.c_void_p
@@ -106,7 +104,6 @@ SYMBOLS = {
     "rbslam_ipc_count": (C.c_int, []),
     "rbslam_ipc_export": (C.c_int, [_ctx, C.c_int32, C.c_void_p]),
     "rbslam_ipc_import": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p]),
-    "rbslam_set_collectives": (C.c_int, [_ctx, ALLGATHER_FN, BARRIER_FN, C.c_void_p]),
 }
 
 _lib = None
