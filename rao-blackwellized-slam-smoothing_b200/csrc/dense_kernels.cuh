@@ -8,6 +8,64 @@
 
 namespace rb {
 
+// ---- fp64 tensor-core tile: 128x64 outputs, K=32, 8 warps (4 x 2), warp tile 32 x 32 -------
+// mma.sync.aligned.m8n8k4.f64 (DMMA; SASS DMMA).  Measured on B200 (profiles/fp64_peaks_r1.json):
+// DMMA 37.1 TFLOP/s = DFMA 36.6 TFLOP/s, but a DMMA needs 2 operand doubles per 256 MACs
+// where a 4x4 SIMT tile needs 8 per 16, so shared-memory bandwidth stops being the limiter.
+// Operand tiles in shared memory, row index contiguous: As[32][RB_LDA] (A[i][k] at k*RB_LDA+i),
+// Bs[32][RB_LDB] (C = A * B' with B given by rows: B[j][k] at k*RB_LDB+j).  The leading
+// dimensions are = 8 (mod 16) doubles so that a fragment read (8 rows x 4 k) costs the
+// minimal two shared-memory wavefronts.
+#define RB_LDA 136
+#define RB_LDB 72
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+// acc[mi][nj][e]: C(row = wr + 8 mi + g, col = wc + 8 nj + 2 tg + e), g = lane>>2, tg = lane&3
+template <int LDA_ = RB_LDA>
+__device__ __forceinline__ void mma_tile_k32(const double *__restrict__ As, const double *__restrict__ Bs,
+                                             int wr, int wc, int lane, double (&acc)[4][4][2]) {
+  const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < 32; kk += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = As[(kk + tg) * LDA_ + wr + 8 * mi + g];
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj) b[nj] = Bs[(kk + tg) * RB_LDB + wc + 8 * nj + g];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
+  }
+}
+// asynchronous 16-byte global->shared copy; bytes beyond src_bytes are zero-filled
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+// stage rows [row0, row0+ROWS) x 32 columns of a column-major matrix (16-byte aligned columns,
+// row0 even) into a [32][LD] tile; rows >= nrows are zero
+template <int ROWS, int LD, int NT = 256>
+__device__ __forceinline__ void stage_rows_k32(double *tile, const double *__restrict__ src, int ld_src,
+                                               int row0, int nrows, int tid) {
+#pragma unroll
+  for (int q = 0; q < (ROWS / 2) * 32 / NT; ++q) {
+    const int idx = tid + q * NT;
+    const int i2 = idx % (ROWS / 2), k = idx / (ROWS / 2);
+    const int r = row0 + 2 * i2;
+    const int valid = max(0, min(2, nrows - r));
+    const double *gp = src + (size_t)k * ld_src + (valid ? r : 0);
+    cp_async16(tile + k * LD + 2 * i2, gp, 8 * valid);
+  }
+}
+
 struct GemmArgs {
   int m, n, k;
   const double *A; int lda; size_t strideA;   // op(A) is m x k; TA: A stored k x m
@@ -18,72 +76,59 @@ struct GemmArgs {
 };
 
 template <bool TA>
-__global__ void __launch_bounds__(256) k_dgemm(GemmArgs g) {
-  __shared__ double As[16][64 + 4];
-  __shared__ double Bs[16][64 + 4];
+__global__ void __launch_bounds__(256, 2) k_dgemm(GemmArgs g) {
+  extern __shared__ double sm_gemm[];
+  double *As = sm_gemm;                  // [32][RB_LDA]
+  double *Bs = sm_gemm + 32 * RB_LDA;    // [32][RB_LDB]
   const int b = blockIdx.z;
   const double *A = g.A + (size_t)(g.slotA ? g.slotA[b] : b) * g.strideA;
   const double *B = g.B + (size_t)b * g.strideB;
   double *C = g.C + (size_t)b * g.strideC;
-  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  double acc[4][4];
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+  double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = 0; k0 < g.k; k0 += 16) {
-    if (TA) {
-      // A stored [k x m]: element (kk, i) at kk + i*lda
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int kk = tid & 15, i = (tid >> 4) + 16 * q;
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int k0 = 0; k0 < g.k; k0 += 32) {
+    if (TA) {   // A stored [k x m]: (kk, i) at kk + i*lda, contiguous along kk
+      for (int idx = tid; idx < 128 * 32; idx += 256) {
+        const int kk = idx & 31, i = idx >> 5;
         const int gk = k0 + kk, gi = m0 + i;
-        As[kk][i] = (gk < g.k && gi < g.m) ? A[gk + (size_t)gi * g.lda] : 0.0;
+        As[kk * RB_LDA + i] = (gk < g.k && gi < g.m) ? A[gk + (size_t)gi * g.lda] : 0.0;
       }
-    } else {
-      // A stored [m x k]: element (i, kk) at i + kk*lda
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i = tid & 63, kk = (tid >> 6) + 4 * q;
+    } else {    // A stored [m x k]: (i, kk) at i + kk*lda, contiguous along i
+      for (int idx = tid; idx < 128 * 32; idx += 256) {
+        const int i = idx & 127, kk = idx >> 7;
         const int gk = k0 + kk, gi = m0 + i;
-        As[kk][i] = (gk < g.k && gi < g.m) ? A[gi + (size_t)gk * g.lda] : 0.0;
+        As[kk * RB_LDA + i] = (gk < g.k && gi < g.m) ? A[gi + (size_t)gk * g.lda] : 0.0;
       }
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int kk = tid & 15, j = (tid >> 4) + 16 * q;
+    for (int idx = tid; idx < 64 * 32; idx += 256) {   // B [k x n]: contiguous along kk
+      const int kk = idx & 31, j = idx >> 5;
       const int gk = k0 + kk, gj = n0 + j;
-      Bs[kk][j] = (gk < g.k && gj < g.n) ? B[gk + (size_t)gj * g.ldb] : 0.0;
+      Bs[kk * RB_LDB + j] = (gk < g.k && gj < g.n) ? B[gk + (size_t)gj * g.ldb] : 0.0;
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      double a[4], bv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][ty * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bv[j], acc[i][j]);
-    }
+    mma_tile_k32(As, Bs, wr, wc, lane, acc);
     __syncthreads();
   }
+  const int gq = lane >> 2, tg = lane & 3;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int gj = n0 + ty * 4 + j;
-    if (gj >= g.n) continue;
+  for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gi = m0 + tx * 4 + i;
-      if (gi >= g.m) continue;
-      double v = acc[i][j];
-      if (g.Rblk && (gi / g.d) == (gj / g.d)) v += g.Rblk[(gi % g.d) + (gj % g.d) * g.d];
-      C[gi + (size_t)gj * g.ldc] = v;
-    }
-  }
+    for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gi = m0 + wr + 8 * mi + gq, gj = n0 + wc + 8 * nj + 2 * tg + e;
+        if (gi < g.m && gj < g.n) {
+          double v = acc[mi][nj][e];
+          if (g.Rblk && (gi / g.d) == (gj / g.d)) v += g.Rblk[(gi % g.d) + (gj % g.d) * g.d];
+          C[gi + (size_t)gj * g.ldc] = v;
+        }
+      }
 }
 
 // ---------------------------------------------------------------------------
@@ -104,51 +149,75 @@ struct CholArgs {
 };
 
 #define RB_CH_NB 32
-__global__ void __launch_bounds__(256) k_chol_solve(CholArgs a) {
+// Right-looking blocked Cholesky, NB = 32.  The right-hand side rides along as row n of the
+// workspace (ldl >= n+1): the panel solve and the trailing update applied to that row ARE the
+// forward substitution, so after the last panel L(n, 0:n-1) = (L \ rhs)'.
+//   per panel: (1) 32x32 diagonal block in shared memory, left-looking by one warp;
+//              (2) L21 = A21 L11^-T, one row per thread, registers;
+//              (3) A22 -= L21 L21' with fp64 tensor-core tiles (mma_tile_k32), lower tiles only.
+// NT threads per matrix: 256 (row tiles of 128, 2 CTAs/SM) or 128 (row tiles of 64, 4 CTAs/SM --
+// more CTAs per SM overlap one matrix's serial panel phases with another's tensor-core phase)
+template <int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
+  constexpr int TR = NT / 2, LDA_T = TR + 8, NWARP = NT / 32;
   extern __shared__ double sm[];
-  double *sD = sm;                      // [32][33] diagonal block
-  double *sR = sD + 32 * 33;            // [64][33] L21 rows of the row tile
-  double *sC = sR + 64 * 33;            // [64][33] L21 rows of the column tile
-  double *sv = sC + 64 * 33;            // [n] right-hand side / solution
+  double *sD = sm;                           // [32][33]
+  double *As = sD + 32 * 34;                 // [32][LDA_T] L21 rows of the row tile (16-B aligned)
+  double *Bs = As + 32 * LDA_T;              // [32][RB_LDB] L21 rows of the column tile
   __shared__ int s_fail;
-  const int b = blockIdx.x, n = a.n, tid = threadIdx.x;
+  __shared__ double s_red[2][8];
+  const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double *A1 = a.A1 + (size_t)(a.slot1 ? a.slot1[b] : b) * a.strideA1;
   double *L = a.L + (size_t)b * a.strideL;
   const int ldl = a.ldl;
+  const int nr = n + 1;                      // rows incl. the right-hand-side row
   bool ok = false;
   for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
     const double jit = attempt ? a.jitter : 0.0;
-    for (int c = 0; c < n; ++c)
-      for (int r = c + tid; r < n; r += blockDim.x) {   // lower triangle only
-        double v = A1[r + (size_t)c * a.lda1];
-        if (a.A2) v += a.A2[r + (size_t)c * a.lda2];
-        if (r == c) v += jit;
-        L[r + (size_t)c * ldl] = v;
+    // lower triangle, one warp per column, four independent loads in flight per lane
+    for (int c = warp; c < n; c += NWARP) {
+      const double *a1 = A1 + (size_t)c * a.lda1;
+      const double *a2 = a.A2 ? a.A2 + (size_t)c * a.lda2 : nullptr;
+      double *lc = L + (size_t)c * ldl;
+      for (int r = c + lane; r < n; r += 128) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = r + 32 * u;
+          v[u] = rr < n ? a1[rr] + (a2 ? a2[rr] : 0.0) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = r + 32 * u;
+          if (rr < n) lc[rr] = v[u] + (rr == c ? jit : 0.0);
+        }
       }
+    }
+    for (int c = tid; c < n; c += blockDim.x)
+      L[n + (size_t)c * ldl] = a.rhs[(size_t)b * a.stride_rhs + c] + (a.rhs2 ? a.rhs2[c] : 0.0);
     if (tid == 0) s_fail = 0;
     __syncthreads();
     for (int jb = 0; jb < n; jb += RB_CH_NB) {
       const int nb = min(RB_CH_NB, n - jb);
-      // (1) diagonal block -> smem, unblocked factorisation by warp 0
+      // (1) diagonal block
       for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
         const int r = idx % nb, c = idx / nb;
         sD[r * 33 + c] = (r >= c) ? L[(jb + r) + (size_t)(jb + c) * ldl] : 0.0;
       }
       __syncthreads();
-      if (tid < 32) {
-        const int r = tid;
-        for (int j = 0; j < nb; ++j) {
-          const double dj = sD[j * 33 + j];
+      if (warp == 0) {
+        const int r = lane;
+        for (int j = 0; j < nb; ++j) {        // left-looking: column j from columns 0..j-1
+          double s = 0.0;
+          if (r >= j && r < nb) {
+            s = sD[r * 33 + j];
+            for (int k = 0; k < j; ++k) s = fma(-sD[r * 33 + k], sD[j * 33 + k], s);
+          }
+          const double dj = __shfl_sync(0xffffffffu, s, j);
           if (!(dj > 0.0)) { if (r == 0) s_fail = 1; break; }
           const double ljj = sqrt(dj);
-          __syncwarp();
           if (r == j) sD[j * 33 + j] = ljj;
-          if (r > j && r < nb) sD[r * 33 + j] /= ljj;
-          __syncwarp();
-          if (r > j && r < nb) {
-            const double lrj = sD[r * 33 + j];
-            for (int c = j + 1; c <= r; ++c) sD[r * 33 + c] -= lrj * sD[c * 33 + j];
-          }
+          else if (r > j && r < nb) sD[r * 33 + j] = s / ljj;
           __syncwarp();
         }
       }
@@ -159,69 +228,69 @@ __global__ void __launch_bounds__(256) k_chol_solve(CholArgs a) {
         if (r >= c) L[(jb + r) + (size_t)(jb + c) * ldl] = sD[r * 33 + c];
       }
       const int r0 = jb + nb;
-      if (r0 >= n) break;
-      // (2) panel solve: L21 = A21 * L11^-T, one row per thread
-      for (int r = r0 + tid; r < n; r += blockDim.x) {
-        double x[RB_CH_NB];
+      // (2) panel solve for rows r0..n (row n = right-hand side)
+      if (nb == RB_CH_NB) {
+#pragma unroll 1
+        for (int r = r0 + tid; r < nr; r += blockDim.x) {
+          asm volatile("" ::: "memory");   // keep the 496 L11 loads inside the iteration (no LICM spills)
+          double x[RB_CH_NB];
 #pragma unroll
-        for (int k = 0; k < RB_CH_NB; ++k) x[k] = L[r + (size_t)(jb + k) * ldl];
+          for (int k = 0; k < RB_CH_NB; ++k) x[k] = L[r + (size_t)(jb + k) * ldl];
 #pragma unroll
-        for (int k = 0; k < RB_CH_NB; ++k) {
-          double s = x[k];
+          for (int k = 0; k < RB_CH_NB; ++k) {
+            double sx = x[k];
 #pragma unroll
-          for (int q = 0; q < RB_CH_NB; ++q)
-            if (q < k) s -= x[q] * sD[k * 33 + q];
-          x[k] = s / sD[k * 33 + k];
+            for (int q = 0; q < RB_CH_NB; ++q)
+              if (q < k) sx = fma(-x[q], sD[k * 33 + q], sx);
+            x[k] = sx / sD[k * 33 + k];
+          }
+#pragma unroll
+          for (int k = 0; k < RB_CH_NB; ++k) L[r + (size_t)(jb + k) * ldl] = x[k];
         }
-#pragma unroll
-        for (int k = 0; k < RB_CH_NB; ++k) L[r + (size_t)(jb + k) * ldl] = x[k];
+      } else {   // last, narrower panel: only the right-hand-side row is left below it
+        if (tid == 0) {
+          for (int k = 0; k < nb; ++k) {
+            double sx = L[n + (size_t)(jb + k) * ldl];
+            for (int q = 0; q < k; ++q) sx = fma(-L[n + (size_t)(jb + q) * ldl], sD[k * 33 + q], sx);
+            L[n + (size_t)(jb + k) * ldl] = sx / sD[k * 33 + k];
+          }
+        }
       }
       __syncthreads();
-      // (3) trailing update A22 -= L21 L21' on lower 64x64 tiles
-      const int tx = tid & 15, ty = tid >> 4;
+      if (r0 >= n) break;
+      // (3) trailing update on lower tiles: rows r0..n, columns r0..n-1
+      const int wr = (warp % (TR / 32)) * 32, wc = (warp / (TR / 32)) * 32;
+      const int gq = lane >> 2, tg = lane & 3;
+      const double *Lp = L + (size_t)jb * ldl;   // the factored panel: columns jb..jb+31
       for (int tj = r0; tj < n; tj += 64) {
-        for (int idx = tid; idx < 64 * 32; idx += blockDim.x) {
-          const int i = idx & 63, k = idx >> 6;
-          sC[i * 33 + k] = (tj + i < n) ? L[(tj + i) + (size_t)(jb + k) * ldl] : 0.0;
-        }
-        for (int ti = tj; ti < n; ti += 64) {
+        stage_rows_k32<64, RB_LDB, NT>(Bs, Lp, ldl, tj, n, tid);
+        for (int ti = tj; ti < nr; ti += TR) {
+          // C tile first: its loads fly while the operand tile is staged.  acc = -C, then
+          // acc += A B' on the tensor cores, store C = -acc  (C -= A B').
+          double acc[4][4][2];
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int gr = ti + wr + 8 * mi + gq, gc = tj + wc + 8 * nj + 2 * tg + e;
+                acc[mi][nj][e] = (gr < nr && gc < n && gr >= gc) ? -L[gr + (size_t)gc * ldl] : 0.0;
+              }
+          __syncthreads();                       // previous tile fully consumed
+          stage_rows_k32<TR, LDA_T, NT>(As, Lp, ldl, ti, nr, tid);
+          cp_async_wait_all();
           __syncthreads();
-          if (ti == tj) {
-            for (int idx = tid; idx < 64 * 32; idx += blockDim.x) sR[(idx & 63) * 33 + (idx >> 6)] = sC[(idx & 63) * 33 + (idx >> 6)];
-          } else {
-            for (int idx = tid; idx < 64 * 32; idx += blockDim.x) {
-              const int i = idx & 63, k = idx >> 6;
-              sR[i * 33 + k] = (ti + i < n) ? L[(ti + i) + (size_t)(jb + k) * ldl] : 0.0;
-            }
-          }
-          __syncthreads();
-          double acc[4][4];
+          mma_tile_k32<LDA_T>(As, Bs, wr, wc, lane, acc);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 8
-          for (int k = 0; k < 32; ++k) {
-            double ar[4], bc[4];
+            for (int nj = 0; nj < 4; ++nj)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) ar[i] = sR[(tx + 16 * i) * 33 + k];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bc[j] = sC[(ty + 16 * j) * 33 + k];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc[i][j] = fma(ar[i], bc[j], acc[i][j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int gc = tj + ty + 16 * j;
-            if (gc >= n) continue;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int gr = ti + tx + 16 * i;
-              if (gr < n && gr >= gc) L[gr + (size_t)gc * ldl] -= acc[i][j];
-            }
-          }
+              for (int e = 0; e < 2; ++e) {
+                const int gr = ti + wr + 8 * mi + gq, gc = tj + wc + 8 * nj + 2 * tg + e;
+                if (gr < nr && gc < n && gr >= gc) L[gr + (size_t)gc * ldl] = -acc[mi][nj][e];
+              }
         }
         __syncthreads();
       }
@@ -242,36 +311,14 @@ __global__ void __launch_bounds__(256) k_chol_solve(CholArgs a) {
     if (tid == 0) { a.sum_log_diag[b] = nan(""); a.vtv[b] = nan(""); }
     return;
   }
-  // ---- sum log diag, forward solve v = L \ rhs, v'v ---------------------------
-  for (int r = tid; r < n; r += blockDim.x)
-    sv[r] = a.rhs[(size_t)b * a.stride_rhs + r] + (a.rhs2 ? a.rhs2[r] : 0.0);
-  __syncthreads();
-  for (int jb = 0; jb < n; jb += RB_CH_NB) {
-    const int nb = min(RB_CH_NB, n - jb);
-    if (tid < 32) {   // diagonal block: serial over rows, lanes share the dot product
-      for (int j = 0; j < nb; ++j) {
-        double part = (tid < j) ? L[(jb + j) + (size_t)(jb + tid) * ldl] * sv[jb + tid] : 0.0;
-        part = warp_sum(part);
-        if (tid == 0) sv[jb + j] = (sv[jb + j] - part) / L[(jb + j) + (size_t)(jb + j) * ldl];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int r = jb + nb + tid; r < n; r += blockDim.x) {
-      double s = 0.0;
-      for (int k = 0; k < nb; ++k) s = fma(L[r + (size_t)(jb + k) * ldl], sv[jb + k], s);
-      sv[r] -= s;
-    }
-    __syncthreads();
-  }
   double ld = 0.0, vv = 0.0;
   for (int r = tid; r < n; r += blockDim.x) {
     ld += log(L[r + (size_t)r * ldl]);
-    vv = fma(sv[r], sv[r], vv);
+    const double v = L[n + (size_t)r * ldl];    // v = L \ rhs
+    vv = fma(v, v, vv);
   }
-  __shared__ double s_red[2][8];
   ld = warp_sum(ld); vv = warp_sum(vv);
-  if ((tid & 31) == 0) { s_red[0][tid >> 5] = ld; s_red[1][tid >> 5] = vv; }
+  if (lane == 0) { s_red[0][warp] = ld; s_red[1][warp] = vv; }
   __syncthreads();
   if (tid == 0) {
     double l2 = 0.0, v2 = 0.0;
@@ -281,8 +328,10 @@ __global__ void __launch_bounds__(256) k_chol_solve(CholArgs a) {
   }
 }
 
-static inline size_t chol_solve_smem(int n) {
-  return sizeof(double) * (32 * 33 + 2 * 64 * 33 + (size_t)n);
+static inline size_t chol_solve_smem(int nt) {
+  return sizeof(double) * (32 * 34 + 32 * (nt / 2 + 8) + 32 * RB_LDB);
 }
+// workspace leading dimension: n rows + the right-hand-side row, 64-byte aligned columns
+static inline int chol_ldl(int n) { return ((n + 1 + 7) / 8) * 8; }
 
 }  // namespace rb

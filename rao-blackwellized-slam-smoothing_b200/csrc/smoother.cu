@@ -483,23 +483,31 @@ int rb_info_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, const double *y
 // ancestor weights of the reference particle
 // ---------------------------------------------------------------------------
 static int launch_gemm(rbslam_ctx *ctx, bool ta, const GemmArgs &g, int batch) {
-  dim3 grid((g.m + 63) / 64, (g.n + 63) / 64, batch);
-  if (ta) k_dgemm<true><<<grid, 256, 0, ctx->stream>>>(g);
-  else k_dgemm<false><<<grid, 256, 0, ctx->stream>>>(g);
+  dim3 grid((g.m + 127) / 128, (g.n + 63) / 64, batch);
+  const size_t smem = sizeof(double) * 32 * (RB_LDA + RB_LDB);
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(k_dgemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_dgemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  if (ta) k_dgemm<true><<<grid, 256, smem, ctx->stream>>>(g);
+  else k_dgemm<false><<<grid, 256, smem, ctx->stream>>>(g);
   ctx->launches += 1;
   CK(cudaGetLastError());
   return RBSLAM_OK;
 }
 
 static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
-  const size_t smem = chol_solve_smem(c.n);
-  static bool attr = false;
-  if (!attr) {
-    CK(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+  static int nt = 0;
+  if (!nt) {
+    nt = 128;
+    if (const char *e = getenv("RBSLAM_CHOL_THREADS")) nt = atoi(e) == 256 ? 256 : 128;
+    CK(cudaFuncSetAttribute(k_chol_solve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_solve_smem(128)));
+    CK(cudaFuncSetAttribute(k_chol_solve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_solve_smem(256)));
   }
-  if (smem > 200 * 1024) return ctx->fail(RBSLAM_EARG, "ancestor-weight system too large");
-  k_chol_solve<<<batch, 256, smem, ctx->stream>>>(c);
+  if (nt == 256) k_chol_solve<256><<<batch, 256, chol_solve_smem(256), ctx->stream>>>(c);
+  else k_chol_solve<128><<<batch, 128, chol_solve_smem(128), ctx->stream>>>(c);
   ctx->launches += 1;
   CK(cudaGetLastError());
   return RBSLAM_OK;
@@ -522,6 +530,7 @@ static int ancestor_weights_cov(rbslam_ctx *ctx, int t, bool use_default_dyn) {
   const double *xl_old = ctx->d_xl[ctx->cx];
   const int *slot_old = ctx->d_slot[ctx->cs];
   const size_t sW = (size_t)M * w->ntau_max, sS = w->ntau_max * w->ntau_max;
+  const size_t sLw = (size_t)chol_ldl((int)w->ntau_max) * w->ntau_max;
   for (int b0 = 0; b0 < N; b0 += (int)w->batch) {
     const int cnt = std::min<int>((int)w->batch, N - b0);
     if (ne > 0) {
@@ -558,7 +567,7 @@ static int ancestor_weights_cov(rbslam_ctx *ctx, int t, bool use_default_dyn) {
       }
       CholArgs c{};
       c.n = ne; c.A1 = w->SS; c.lda1 = ne; c.strideA1 = sS; c.slot1 = nullptr; c.A2 = nullptr; c.lda2 = 0;
-      c.L = w->Lw; c.ldl = ne; c.strideL = sS; c.rhs = w->e; c.stride_rhs = w->ntau_max; c.rhs2 = nullptr;
+      c.L = w->Lw; c.ldl = chol_ldl(ne); c.strideL = sLw; c.rhs = w->e; c.stride_rhs = w->ntau_max; c.rhs2 = nullptr;
       c.jitter = ctx->jitter; c.sum_log_diag = w->sumlog; c.vtv = w->vtv; c.status = ctx->d_status; c.t = t;
       if ((rc = launch_chol(ctx, c, cnt))) return rc;
     } else {
@@ -588,12 +597,12 @@ static int ancestor_weights_info(rbslam_ctx *ctx, int t, bool use_default_dyn) {
                                                             ctx->d_odo + (size_t)(t - 1) * ctx->n_odo,
                                                             ctx->h_dt[t - 1], Qp, use_default_dyn ? 1 : 0, w->lwdyn);
   ctx->launches += 1;
-  const size_t sL = (size_t)M * M;
+  const size_t sL = (size_t)chol_ldl(M) * M;
   for (int b0 = 0; b0 < N; b0 += (int)w->batch) {
     const int cnt = std::min<int>((int)w->batch, N - b0);
     CholArgs c{};
     c.n = M; c.A1 = ctx->d_Imat; c.lda1 = ctx->ld; c.strideA1 = ctx->slab; c.slot1 = ctx->d_slot[ctx->cs] + b0;
-    c.A2 = w->ImatAddt; c.lda2 = M; c.L = w->Lw; c.ldl = M; c.strideL = sL;
+    c.A2 = w->ImatAddt; c.lda2 = M; c.L = w->Lw; c.ldl = chol_ldl(M); c.strideL = sL;
     c.rhs = ctx->d_ivec[ctx->cx] + (size_t)b0 * M; c.stride_rhs = M; c.rhs2 = w->ivecAddt;
     c.jitter = -1.0;   // quirk Q7: the reference's retry branch is broken and would raise
     c.sum_log_diag = w->sumlog; c.vtv = w->vtv; c.status = ctx->d_status; c.t = t;
@@ -665,12 +674,12 @@ extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int
       RB_ALLOC(w->W, w->batch * M * w->ntau_max);
       if (sparse) RB_ALLOC(w->Dti, w->batch * M * w->ntau_max);
       RB_ALLOC(w->SS, w->batch * w->ntau_max * w->ntau_max);
-      RB_ALLOC(w->Lw, w->batch * w->ntau_max * w->ntau_max);
+      RB_ALLOC(w->Lw, w->batch * (size_t)chol_ldl((int)w->ntau_max) * w->ntau_max);
       RB_ALLOC(w->e, w->batch * w->ntau_max);
     } else {
       const size_t per = (size_t)M * M * 8;
       w->batch = std::max<size_t>(1, std::min<size_t>(N, ((size_t)12 << 30) / per));
-      RB_ALLOC(w->Lw, w->batch * M * M);
+      RB_ALLOC(w->Lw, w->batch * (size_t)chol_ldl(M) * M);
     }
     RB_ALLOC(w->sumlog, w->batch); RB_ALLOC(w->vtv, w->batch);
   }

@@ -26,13 +26,18 @@ def main():
     ap.add_argument("--m", type=int, default=512)
     ap.add_argument("--T", type=int, default=192)
     ap.add_argument("--cpu", action="store_true", help="also time the oracle on a bounded sample")
+    ap.add_argument("--forms", default="0,1", help="comma list: 0 covariance form, 1 information form")
+    ap.add_argument("--laps", type=int, default=3)
     a = ap.parse_args()
     import rbslam
-    pr = rbslam.synth.dense_mag_problem(N_T=a.T, m=a.m, seed=1, n_laps=3, m_sim=2000)
+    pr = rbslam.synth.dense_mag_problem(N_T=a.T, m=a.m, seed=1, n_laps=a.laps, m_sim=2000)
     gm = rbslam.models.from_problem(pr)
     args = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
     out = {"config": {"workload": "C1 dense-mag smoother", "N_P": a.N, "M": gm.M, "T": a.T, "N_K": a.NK}}
+    forms = [int(f) for f in a.forms.split(",")]
     for form, name in ((0, "covariance_form"), (1, "information_form")):
+        if form not in forms:
+            continue
         with rbslam.Context(gm, a.N, a.T, rng_mode=1, seed=1, information_form=(form == 1)) as ctx:
             ctx.smoother_run(*args, pr["dt"], 1, form)          # warm-up (one plain-filter sweep)
             ctx.phase_timing(True)
