@@ -381,6 +381,8 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
   for (void *p : ptrs) if (p) cudaFree(p);
   for (auto e : ctx->ph_events) cudaEventDestroy(e);
   for (auto &e : ctx->user_events) if (e) cudaEventDestroy(e);
+  if (ctx->ev_fetch) cudaEventDestroy(ctx->ev_fetch);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -616,11 +618,18 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin) / (smem + 2048)));
   if (ctx->stream_ctas_per_sm > 0) per_sm = ctx->stream_ctas_per_sm;
   const int grid = std::min(N * ctx->nsplit, per_sm * ctx->num_sms);
-  for (int phase = 0; phase < 2; ++phase) {
-    if (phase == 0 && !resampled) continue;
-    kern<<<grid, RB_STREAM_THREADS, smem, ctx->stream>>>(sa, phase == 0 ? ctx->d_listA : ctx->d_listB,
-                                                         ctx->d_counts + phase);
-    ctx->launches += 1;
+  for (int grp = 0; grp < ctx->stream_groups; ++grp) {
+    if (grp > 0 && ctx->group_hook) {
+      int rch = ctx->group_hook(ctx, grp);
+      if (rch) return rch;
+    }
+    for (int phase = 0; phase < 2; ++phase) {
+      if (phase == 0 && !resampled) continue;
+      kern<<<grid, RB_STREAM_THREADS, smem, ctx->stream>>>(
+          sa, (phase == 0 ? ctx->d_listA : ctx->d_listB) + ctx->group_off[grp][phase],
+          ctx->d_counts + 2 * grp + phase);
+      ctx->launches += 1;
+    }
   }
   Innov4Args ia;
   ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = ctx->nsplit; ia.PHp = ctx->d_PHp; ia.H4 = a.H;

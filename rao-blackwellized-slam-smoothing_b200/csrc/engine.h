@@ -87,6 +87,13 @@ struct rbslam_ctx {
   void *smoother_ws = nullptr;   // SmootherWs (smoother.cu)
   void *shard_ws = nullptr;      // ShardWs (sharded.cu); N is the LOCAL particle count when set
   const int *anc_override = nullptr;   // sharded engine: thin arrays are slot-indexed
+  // streaming pass in groups: group g uses listA/listB + group_off[g][phase], counts d_counts[2g+phase];
+  // group_hook(ctx, g) runs before group g>0 (sharded engine: wait for migrants + peer barrier)
+  int stream_groups = 1;
+  int group_off[2][2] = {{0, 0}, {0, 0}};
+  int (*group_hook)(rbslam_ctx *, int) = nullptr;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fetch = nullptr;
 
 
   void fail_cuda(cudaError_t e, const char *what, const char *file, int line);

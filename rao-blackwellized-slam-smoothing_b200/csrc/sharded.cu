@@ -45,7 +45,8 @@ struct ShardWs {
   std::vector<int> owner[2], lslot[2];
   int cur = 0;
   unsigned long long epoch = 0;
-  std::vector<int> h_ai, h_src, h_listA, h_listB, h_glob, h_fetch;
+  std::vector<int> h_ai, h_src, h_listA, h_listB, h_glob, h_fetch, h_nchild, h_inv, h_lists[4];
+  std::vector<unsigned char> h_unsafe;
   int64_t migrated = 0;
 };
 
@@ -82,30 +83,41 @@ extern "C" int rbslam_plan_shard(int32_t N, int32_t world, const int32_t *ai, co
     ++n_child[ai[i]];
     if (owner_new[i] == owner_old[ai[i]] && keeper[ai[i]] < 0) keeper[ai[i]] = i;   // first local child
   }
-  // free slots per rank: dead first (no children anywhere), then exported-only
-  std::vector<std::vector<int>> dead(world), expo(world);
+  // free slots per rank as flat, rank-major lists: dead (no children anywhere) and
+  // exported-only (children only on other ranks)
+  std::vector<int> dcnt(world + 1, 0), ecnt(world + 1, 0);
   for (int a = 0; a < N; ++a) {
     if (keeper[a] >= 0) continue;
-    (n_child[a] == 0 ? dead : expo)[owner_old[a]].push_back(lslot_old[a]);
+    ++(n_child[a] == 0 ? dcnt : ecnt)[owner_old[a] + 1];
   }
-  std::vector<size_t> nd(world, 0), ne(world, 0);
+  for (int r = 0; r < world; ++r) { dcnt[r + 1] += dcnt[r]; ecnt[r + 1] += ecnt[r]; }
+  std::vector<int> dead(dcnt[world]), expo(ecnt[world]), dfill(dcnt.begin(), dcnt.end() - 1),
+      efill(ecnt.begin(), ecnt.end() - 1);
+  for (int a = 0; a < N; ++a) {
+    if (keeper[a] >= 0) continue;
+    if (n_child[a] == 0) dead[dfill[owner_old[a]]++] = lslot_old[a];
+    else expo[efill[owner_old[a]]++] = lslot_old[a];
+  }
+  std::vector<int> nd(dcnt.begin(), dcnt.end() - 1), ne(ecnt.begin(), ecnt.end() - 1);   // cursors
   // migrants first: they are fetched before the barrier and must land in dead slots
-  for (int i = 0; i < N; ++i) {
-    const int r = owner_new[i];
-    if (owner_old[ai[i]] == r) continue;
-    if (nd[r] >= dead[r].size()) return RBSLAM_EARG;   // cannot happen with the locality planner
-    lslot_new[i] = dead[r][nd[r]++];
+  if (nm > 0) {
+    for (int i = 0; i < N; ++i) {
+      const int r = owner_new[i];
+      if (owner_old[ai[i]] == r) continue;
+      if (nd[r] >= dcnt[r + 1]) return RBSLAM_EARG;   // cannot happen with the locality planner
+      lslot_new[i] = dead[nd[r]++];
+    }
   }
   for (int i = 0; i < N; ++i) {
     const int r = owner_new[i], a = ai[i];
     if (owner_old[a] != r) continue;
     if (keeper[a] == i) { lslot_new[i] = lslot_old[a]; continue; }
-    if (nd[r] < dead[r].size()) lslot_new[i] = dead[r][nd[r]++];
-    else if (ne[r] < expo[r].size()) lslot_new[i] = expo[r][ne[r]++];
+    if (nd[r] < dcnt[r + 1]) lslot_new[i] = dead[nd[r]++];
+    else if (ne[r] < ecnt[r + 1]) lslot_new[i] = expo[ne[r]++];
     else return RBSLAM_EARG;
   }
   for (int r = 0; r < world; ++r)
-    if (nd[r] + ne[r] != dead[r].size() + expo[r].size()) return RBSLAM_EARG;
+    if (nd[r] != dcnt[r + 1] || ne[r] != ecnt[r + 1]) return RBSLAM_EARG;
   (void)Nloc;
   if (n_migrate) *n_migrate = nm;
   return RBSLAM_OK;
@@ -217,6 +229,8 @@ int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN) {
   RB_ALLOC(s->d_glob, s->Nloc); RB_ALLOC(s->d_fetch, (size_t)4 * s->Nloc);
   RB_ALLOC(s->d_owner, gN); RB_ALLOC(s->d_lslot, gN);
   CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned long long)));
+  CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_fetch, cudaEventDisableTiming));
   void *own[SH_COUNT] = {ctx->d_P, ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_xl[0],
                          ctx->d_xl[1], s->g_logw, s->flags};
   for (int w = 0; w < SH_COUNT; ++w) s->peers.p[w][rank] = own[w];
@@ -261,6 +275,12 @@ static int peer_barrier(rbslam_ctx *ctx) {
   ctx->launches += 1;
   CK(cudaGetLastError());
   return RBSLAM_OK;
+}
+
+// between the safe and the deferred group: migrants have landed, every peer is done reading
+static int shard_group_hook(rbslam_ctx *ctx, int) {
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fetch, 0));
+  return peer_barrier(ctx);
 }
 
 int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
@@ -324,7 +344,27 @@ int rb_shard_step(rbslam_ctx *ctx) {
                           s->owner[nw].data(), s->lslot[nw].data(), &nmig) != RBSLAM_OK)
       return ctx->fail(RBSLAM_EARG, "internal: shard plan failed");
     s->migrated += nmig;
-    s->h_src.assign(Nloc, 0); s->h_listA.clear(); s->h_listB.clear(); s->h_fetch.clear();
+    // Work lists in two groups.  Group 0 ("safe") touches no slab that a peer may still be
+    // reading and runs WHILE migrants are in flight; group 1 (everything that involves an
+    // exported slab, plus the migrants themselves) runs after the peer barrier.  All local
+    // offspring of one ancestor are kept in the same group so that copies still precede the
+    // in-place update of their source slab.
+    s->h_src.assign(Nloc, 0); s->h_fetch.clear();
+    for (int q = 0; q < 4; ++q) s->h_lists[q].clear();   // A0, B0, A1, B1
+    s->h_nchild.assign(gN, 0); s->h_unsafe.assign(gN, 0); s->h_inv.assign(Nloc, -1);
+    for (int i = 0; i < gN; ++i) {
+      const int a = s->h_ai[i];
+      ++s->h_nchild[a];
+      if (s->owner[nw][i] != s->owner[o][a]) s->h_unsafe[a] = 1;        // ancestor's slab is exported
+      if (s->owner[o][i] == s->rank) s->h_inv[s->lslot[o][i]] = i;      // old particle living in each slot
+    }
+    for (int i = 0; i < gN; ++i) {   // a copy landing in an exported-only slot must wait as well
+      if (s->owner[nw][i] != s->rank) continue;
+      const int a = s->h_ai[i];
+      if (s->owner[o][a] != s->rank) continue;
+      const int old = s->h_inv[s->lslot[nw][i]];
+      if (old != a && old >= 0 && s->h_nchild[old] > 0) s->h_unsafe[a] = 1;
+    }
     for (int i = 0; i < gN; ++i) {
       if (s->owner[nw][i] != s->rank) continue;
       const int j = s->lslot[nw][i], a = s->h_ai[i];
@@ -332,18 +372,26 @@ int rb_shard_step(rbslam_ctx *ctx) {
       if (s->owner[o][a] != s->rank) {          // migrant: fetched into slot j, then updated in place
         s->h_fetch.push_back(j); s->h_fetch.push_back(s->owner[o][a]); s->h_fetch.push_back(s->lslot[o][a]);
         s->h_fetch.push_back(0);
-        s->h_src[j] = j; s->h_listB.push_back(j);
+        s->h_src[j] = j; s->h_lists[3].push_back(j);
       } else {
         s->h_src[j] = s->lslot[o][a];
-        (s->h_src[j] == j ? s->h_listB : s->h_listA).push_back(j);
+        const int grp = s->h_unsafe[a] ? 1 : 0;
+        s->h_lists[2 * grp + (s->h_src[j] == j ? 1 : 0)].push_back(j);
       }
     }
     s->cur = nw;
-    const int nA = (int)s->h_listA.size(), nB = (int)s->h_listB.size(), nF = (int)s->h_fetch.size() / 4;
-    const int counts[2] = {nA, nB};
+    const int nF = (int)s->h_fetch.size() / 4;
+    const int counts[4] = {(int)s->h_lists[0].size(), (int)s->h_lists[1].size(), (int)s->h_lists[2].size(),
+                           (int)s->h_lists[3].size()};
+    ctx->stream_groups = 2;
+    ctx->group_off[0][0] = 0; ctx->group_off[0][1] = 0;
+    ctx->group_off[1][0] = counts[0]; ctx->group_off[1][1] = counts[1];
     CK(cudaMemcpyAsync(ctx->d_src_slot, s->h_src.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
-    if (nA) CK(cudaMemcpyAsync(ctx->d_listA, s->h_listA.data(), sizeof(int) * nA, cudaMemcpyHostToDevice, ctx->stream));
-    if (nB) CK(cudaMemcpyAsync(ctx->d_listB, s->h_listB.data(), sizeof(int) * nB, cudaMemcpyHostToDevice, ctx->stream));
+    for (int q = 0; q < 4; ++q) {
+      if (!counts[q]) continue;
+      int *dst = (q & 1 ? ctx->d_listB : ctx->d_listA) + (q >= 2 ? counts[q - 2] : 0);
+      CK(cudaMemcpyAsync(dst, s->h_lists[q].data(), sizeof(int) * counts[q], cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaMemcpyAsync(ctx->d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(s->d_glob, s->h_glob.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
     if (nF) CK(cudaMemcpyAsync(s->d_fetch, s->h_fetch.data(), sizeof(int) * 4 * nF, cudaMemcpyHostToDevice, ctx->stream));
@@ -359,19 +407,20 @@ int rb_shard_step(rbslam_ctx *ctx) {
                                                            Qp, ns, xn_t);
     ctx->launches += 1;
     rb_phase_end(ctx);
-    rb_phase_begin(ctx, RB_PH_ANCESTOR);   // reported as the "migration" phase
+    // migrants travel on a second stream, concurrently with the "safe" group of the Kalman pass
     if (nF) {
-      k_peer_fetch<<<dim3(16, nF), 256, 0, ctx->stream>>>(nF, s->d_fetch, s->peers, ctx->cg, ctx->cx, ctx->slab,
-                                                          ctx->ld, M, ctx->d_P, ctx->d_G4[ctx->cg], ctx->d_KS4[ctx->cg],
-                                                          ctx->d_xl[ctx->cx]);
+      k_peer_fetch<<<dim3(16, nF), 256, 0, ctx->stream2>>>(nF, s->d_fetch, s->peers, ctx->cg, ctx->cx, ctx->slab,
+                                                           ctx->ld, M, ctx->d_P, ctx->d_G4[ctx->cg], ctx->d_KS4[ctx->cg],
+                                                           ctx->d_xl[ctx->cx]);
       ctx->launches += 1;
     }
-    if ((rc = peer_barrier(ctx))) return rc;   // all remote reads of old slabs are done
-    rb_phase_end(ctx);
+    CK(cudaEventRecord(ctx->ev_fetch, ctx->stream2));
   } else {
     k_plan_identity<<<(Nloc + 255) / 256, 256, 0, ctx->stream>>>(Nloc, ctx->d_slot[ctx->cs], ctx->d_src_slot,
                                                                 ctx->d_listB, ctx->d_counts);
     ctx->launches += 1;
+    ctx->stream_groups = 1;
+    ctx->group_off[0][0] = ctx->group_off[0][1] = 0;
   }
   rb_phase_begin(ctx, RB_PH_MEAS);
   k_meas<<<Nloc, 128, 0, ctx->stream>>>(ctx->mc, Nloc, xn_t, nullptr, M, nullptr, ctx->d_H, ctx->hs_p, ctx->hs_a,
@@ -380,8 +429,12 @@ int rb_shard_step(rbslam_ctx *ctx) {
   rb_phase_end(ctx);
   rb_phase_begin(ctx, RB_PH_KALMAN);
   ctx->anc_override = ctx->d_src_slot;     // thin arrays are slot-indexed: ancestor index = source slot
+  ctx->group_hook = shard_group_hook;
   rc = rb_kalman_phase(ctx, ctx->d_y + (size_t)t * d, resampled);
   ctx->anc_override = nullptr;
+  ctx->group_hook = nullptr;
+  ctx->stream_groups = 1;
+  ctx->group_off[0][0] = ctx->group_off[0][1] = 0;
   rb_phase_end(ctx);
   if (rc) return rc;
   rb_phase_begin(ctx, RB_PH_NORMALIZE);

@@ -321,7 +321,16 @@ k_normalize(int N, int n, const double *__restrict__ logw, double *__restrict__ 
   __shared__ double s_bcast;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   double m = -INFINITY;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmax(m, logw[i]);
+  {
+    double m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int i = threadIdx.x;
+    for (; i + 3 * (int)blockDim.x < N; i += 4 * blockDim.x) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m4[u] = fmax(m4[u], logw[i + u * blockDim.x]);
+    }
+    for (; i < N; i += blockDim.x) m4[0] = fmax(m4[0], logw[i]);
+    m = fmax(fmax(m4[0], m4[1]), fmax(m4[2], m4[3]));
+  }
   m = warp_max(m);
   if (lane == 0) s_red[wid] = m;
   __syncthreads();
@@ -333,7 +342,17 @@ k_normalize(int N, int n, const double *__restrict__ logw, double *__restrict__ 
   __syncthreads();
   const double c = s_bcast;
   double s = 0.0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) s += exp(logw[i] - c);
+  {   // four independent exp chains per thread (the single CTA is latency-bound, not throughput-bound);
+      // the summation order is fixed by (blockDim, N) only, so it is the same on every GPU
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    int i = threadIdx.x;
+    for (; i + 3 * (int)blockDim.x < N; i += 4 * blockDim.x) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] += exp(logw[i + u * blockDim.x] - c);
+    }
+    for (; i < N; i += blockDim.x) s4[0] += exp(logw[i] - c);
+    s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  }
   s = warp_sum(s);
   __syncthreads();
   if (lane == 0) s_red[wid] = s;
@@ -347,12 +366,28 @@ k_normalize(int N, int n, const double *__restrict__ logw, double *__restrict__ 
   const double lse = s_bcast;
   double best = -1.0;
   int bidx = 0x7fffffff;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const double wi = exp(logw[i] - lse);
-    w[i] = wi;
-    if (logw_hist_t) logw_hist_t[i] = logw[i];
-    if (w_hist_t) w_hist_t[i] = wi;
-    if (wi > best) { best = wi; bidx = i; }   // strided ascending i: first index kept on ties
+  {
+    int i = threadIdx.x;
+    for (; i + 3 * (int)blockDim.x < N; i += 4 * blockDim.x) {
+      double wi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wi[u] = exp(logw[i + u * blockDim.x] - lse);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ii = i + u * blockDim.x;
+        w[ii] = wi[u];
+        if (logw_hist_t) logw_hist_t[ii] = logw[ii];
+        if (w_hist_t) w_hist_t[ii] = wi[u];
+        if (wi[u] > best) { best = wi[u]; bidx = ii; }   // ascending ii: first index kept on ties
+      }
+    }
+    for (; i < N; i += blockDim.x) {
+      const double wi = exp(logw[i] - lse);
+      w[i] = wi;
+      if (logw_hist_t) logw_hist_t[i] = logw[i];
+      if (w_hist_t) w_hist_t[i] = wi;
+      if (wi > best) { best = wi; bidx = i; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
