@@ -229,6 +229,14 @@ RBSLAM_API int rbslam_plan_migration(int32_t N, int32_t world, const int32_t *ai
 RBSLAM_API int rbslam_plan_shard(int32_t N, int32_t world, const int32_t *ai, const int32_t *owner_old,
                                  const int32_t *lslot_old, int32_t *owner_new, int32_t *lslot_new,
                                  int32_t *n_migrate);
+/* The same plan computed ON THE DEVICE (what the sharded step uses; no host round trip),
+   plus rank `rank`'s work: src_slot/glob [N/world], listA/listB [N/world] (safe group first,
+   then the group deferred behind the peer barrier), fetch [N/world][4] and counts8 =
+   {nA0, nB0, nA1, nB1, nFetch, nMigrantsTotal, -, -}.  Kernel-level entry point for tests. */
+RBSLAM_API int rbslam_op_plan_shard(int32_t device, int32_t N, int32_t world, int32_t rank, const int32_t *ai,
+                                    const int32_t *owner_old, const int32_t *lslot_old, int32_t *owner_new,
+                                    int32_t *lslot_new, int32_t *src_slot, int32_t *glob, int32_t *listA,
+                                    int32_t *listB, int32_t *fetch, int32_t *counts8);
 /* A context created with world > 1 owns N/world slabs and shares rbslam_ipc_count() device
    buffers with its peers through CUDA IPC (64-byte handles exchanged by the host): slabs,
    pending (G,KS) ping-pong, xl ping-pong, the replicated log-weight array and the barrier

@@ -382,6 +382,7 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
   for (auto e : ctx->ph_events) cudaEventDestroy(e);
   for (auto &e : ctx->user_events) if (e) cudaEventDestroy(e);
   if (ctx->ev_fetch) cudaEventDestroy(ctx->ev_fetch);
+  if (ctx->ev_plan) cudaEventDestroy(ctx->ev_plan);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -627,7 +628,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
       if (phase == 0 && !resampled) continue;
       kern<<<grid, RB_STREAM_THREADS, smem, ctx->stream>>>(
           sa, (phase == 0 ? ctx->d_listA : ctx->d_listB) + ctx->group_off[grp][phase],
-          ctx->d_counts + 2 * grp + phase);
+          ctx->d_counts + 2 * grp + phase, ctx->group_off_dev[grp][phase]);
       ctx->launches += 1;
     }
   }

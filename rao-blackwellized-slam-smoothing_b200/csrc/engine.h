@@ -91,9 +91,10 @@ struct rbslam_ctx {
   // group_hook(ctx, g) runs before group g>0 (sharded engine: wait for migrants + peer barrier)
   int stream_groups = 1;
   int group_off[2][2] = {{0, 0}, {0, 0}};
+  const int *group_off_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // device-side offsets (planner on GPU)
   int (*group_hook)(rbslam_ctx *, int) = nullptr;
   cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fetch = nullptr;
+  cudaEvent_t ev_fetch = nullptr, ev_plan = nullptr;
 
 
   void fail_cuda(cudaError_t e, const char *what, const char *file, int line);

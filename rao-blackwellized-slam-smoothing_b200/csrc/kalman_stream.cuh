@@ -100,7 +100,9 @@ struct StreamArgs {
 // P*ivec for the information form)
 template <int D, int DA, int R2, int KC, int S>
 __global__ void __launch_bounds__(RB_STREAM_THREADS, 1)
-k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict__ count) {
+k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict__ count,
+              const int *__restrict__ list_off = nullptr) {
+  if (list_off) list += *list_off;   // lists of later work groups start where the previous group ends
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ __align__(8) uint64_t full[S];
   const int ld = a.ld, M = a.M;

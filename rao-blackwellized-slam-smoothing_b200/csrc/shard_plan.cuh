@@ -1,0 +1,220 @@
+// Device-side plan of one sharded resampling step (single CTA, deterministic).  Same policy
+// and same results as the host reference rbslam_plan_shard (sharded.cu): offspring stay on the
+// ancestor's rank up to the capacity N/world (in particle order), the surplus fills the
+// deficits of the other ranks in rank order; the first staying offspring keeps the ancestor's
+// slab; migrants take dead slabs, remaining local copies take dead then exported-only slabs.
+// On top it emits this rank's work lists in two groups (safe / deferred) and the fetch list.
+// Running it on the device removes the only host round trip of the sharded step.
+#pragma once
+#include "common.cuh"
+
+namespace rb {
+
+#define RB_PW 8   // max ranks
+
+struct PlanArgs {
+  int N, world, rank;
+  const int *ai;                          // [N] ancestors of the new particles
+  const int *owner_old, *lslot_old;       // [N]
+  int *owner_new, *lslot_new;             // [N]
+  int *n_child, *keeper, *unsafe, *inv;   // [N] scratch ([Nloc] for inv)
+  int *dead_list, *expo_list;             // [world][Nloc] scratch
+  // this rank's work
+  int *src_slot, *glob;                   // [Nloc]
+  int *listA, *listB;                     // [Nloc] each: group 0 first, then group 1
+  int *fetch;                             // [Nloc][4]: dst slot, source rank, source slot, 0
+  int *counts;                            // [8]: nA0, nB0, nA1, nB1, nFetch, nMigTotal
+};
+
+// exclusive scan across the block of W ints per thread; totals (all threads get them)
+template <int W>
+__device__ __forceinline__ void block_scan_vec(int (&v)[W], int (&tot)[W], int *s_w /*[32][W]*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int incl[W];
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    int x = v[c];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    incl[c] = x;
+  }
+  __syncthreads();
+  if (lane == 31) {
+#pragma unroll
+    for (int c = 0; c < W; ++c) s_w[wid * W + c] = incl[c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    int base = 0, t = 0;
+    for (int q = 0; q < nw; ++q) {
+      const int x = s_w[q * W + c];
+      if (q < wid) base += x;
+      t += x;
+    }
+    tot[c] = t;
+    v[c] = base + incl[c] - v[c];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_plan_shard(PlanArgs p) {
+  __shared__ int s_w[32 * 16];
+  __shared__ int s_defp[RB_PW + 1], s_nmig[RB_PW], s_ndead[RB_PW];
+  const int N = p.N, W = p.world, me = p.rank, cap = N / W, Nloc = cap;
+  const int tid = threadIdx.x;
+  const int per = (N + blockDim.x - 1) / blockDim.x;
+  const int b = min(N, tid * per), e = min(N, b + per);
+  const int NONE = 0x7fffffff;
+  for (int a = tid; a < N; a += blockDim.x) { p.n_child[a] = 0; p.keeper[a] = NONE; p.unsafe[a] = 0; }
+  for (int j = tid; j < Nloc; j += blockDim.x) p.inv[j] = -1;
+  __syncthreads();
+  // ---- 1. who stays: position of each child among the children of its ancestor's rank
+  int cnt[RB_PW], tot[RB_PW];
+#pragma unroll
+  for (int r = 0; r < RB_PW; ++r) cnt[r] = 0;
+  for (int i = b; i < e; ++i) {
+    const int a = p.ai[i];
+    atomicAdd(&p.n_child[a], 1);
+    const int r = p.owner_old[a];
+#pragma unroll
+    for (int q = 0; q < RB_PW; ++q) cnt[q] += (q == r);
+  }
+  block_scan_vec<RB_PW>(cnt, tot, s_w);
+  if (tid == 0) {
+    int acc = 0;
+    for (int r = 0; r < W; ++r) { s_defp[r] = acc; acc += cap - min(cap, tot[r]); }
+    s_defp[W] = acc;
+  }
+  int n_sur = 0;
+  for (int i = b; i < e; ++i) {
+    const int a = p.ai[i], r = p.owner_old[a];
+    int pos = 0;
+#pragma unroll
+    for (int q = 0; q < RB_PW; ++q) if (q == r) pos = cnt[q]++;
+    if (pos < cap) { p.owner_new[i] = r; atomicMin(&p.keeper[a], i); }
+    else { p.owner_new[i] = -1; ++n_sur; }
+  }
+  {
+    int v1[1] = {n_sur}, t1[1];
+    block_scan_vec<1>(v1, t1, s_w);
+    int k = v1[0];
+    for (int i = b; i < e; ++i) {
+      if (p.owner_new[i] >= 0) continue;
+      int r2 = 0;
+      while (r2 + 1 < W && k >= s_defp[r2 + 1]) ++r2;
+      p.owner_new[i] = r2;
+      p.unsafe[p.ai[i]] = 1;          // the ancestor's slab is exported
+      ++k;
+    }
+    if (tid == 0) p.counts[5] = t1[0];
+  }
+  __syncthreads();
+  // ---- 2. free slabs per rank: dead (no offspring anywhere) and exported-only, ordered by a
+  int cf[16], tf[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) cf[q] = 0;
+  for (int a = b; a < e; ++a) {
+    if (p.keeper[a] != NONE) continue;
+    const int r = p.owner_old[a], kind = p.n_child[a] == 0 ? 0 : 8;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) cf[q] += (q == r + kind);
+  }
+  block_scan_vec<16>(cf, tf, s_w);
+  if (tid < W) s_ndead[tid] = tf[tid];
+  for (int a = b; a < e; ++a) {
+    if (p.keeper[a] != NONE) continue;
+    const int r = p.owner_old[a];
+    const bool dead = p.n_child[a] == 0;
+    int pos = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) if (q == r + (dead ? 0 : 8)) pos = cf[q]++;
+    (dead ? p.dead_list : p.expo_list)[(size_t)r * Nloc + pos] = p.lslot_old[a];
+    if (r == me) { /* slot becomes free on this rank */ }
+  }
+  for (int a = b; a < e; ++a)
+    if (p.owner_old[a] == me) p.inv[p.lslot_old[a]] = a;
+  __syncthreads();
+  // ---- 3. slab of every new particle
+  int cm[16], tm[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) cm[q] = 0;
+  for (int i = b; i < e; ++i) {
+    const int a = p.ai[i], r = p.owner_new[i];
+    const bool mig = p.owner_old[a] != r;
+    const bool copy = !mig && p.keeper[a] != i;
+    if (!mig && !copy) continue;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) cm[q] += (q == r + (mig ? 0 : 8));
+  }
+  block_scan_vec<16>(cm, tm, s_w);
+  if (tid < W) s_nmig[tid] = tm[tid];
+  __syncthreads();
+  for (int i = b; i < e; ++i) {
+    const int a = p.ai[i], r = p.owner_new[i];
+    const bool mig = p.owner_old[a] != r;
+    if (!mig && p.keeper[a] == i) { p.lslot_new[i] = p.lslot_old[a]; continue; }
+    int pos = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) if (q == r + (mig ? 0 : 8)) pos = cm[q]++;
+    if (mig) {
+      p.lslot_new[i] = p.dead_list[(size_t)r * Nloc + pos];
+    } else {
+      const int qd = s_nmig[r] + pos;
+      p.lslot_new[i] = qd < s_ndead[r] ? p.dead_list[(size_t)r * Nloc + qd]
+                                       : p.expo_list[(size_t)r * Nloc + qd - s_ndead[r]];
+    }
+  }
+  __syncthreads();
+  // ---- 4. deferred group: ancestors with an exported slab, or with a copy that lands in a
+  //         slab a peer may still be reading
+  for (int i = b; i < e; ++i) {
+    if (p.owner_new[i] != me) continue;
+    const int a = p.ai[i];
+    if (p.owner_old[a] != me || p.keeper[a] == i) continue;
+    const int old = p.inv[p.lslot_new[i]];
+    if (old != a && old >= 0 && p.n_child[old] > 0) p.unsafe[a] = 1;
+  }
+  __syncthreads();
+  // ---- 5. this rank's lists, in particle order
+  int cl[5], tl[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) cl[q] = 0;
+  for (int i = b; i < e; ++i) {
+    if (p.owner_new[i] != me) continue;
+    const int a = p.ai[i];
+    if (p.owner_old[a] != me) { ++cl[3]; ++cl[4]; continue; }
+    const int grp = p.unsafe[a] ? 1 : 0, inplace = p.keeper[a] == i ? 1 : 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cl[q] += (q == 2 * grp + inplace);
+  }
+  block_scan_vec<5>(cl, tl, s_w);
+  for (int i = b; i < e; ++i) {
+    if (p.owner_new[i] != me) continue;
+    const int a = p.ai[i], j = p.lslot_new[i];
+    p.glob[j] = i;
+    if (p.owner_old[a] != me) {
+      const int f = cl[4]++;
+      p.fetch[4 * f] = j; p.fetch[4 * f + 1] = p.owner_old[a]; p.fetch[4 * f + 2] = p.lslot_old[a];
+      p.fetch[4 * f + 3] = 0;
+      p.src_slot[j] = j;
+      p.listB[tl[1] + cl[3]++] = j;
+    } else {
+      const int grp = p.unsafe[a] ? 1 : 0, inplace = p.keeper[a] == i ? 1 : 0;
+      p.src_slot[j] = p.lslot_old[a];
+      const int q = 2 * grp + inplace;
+      int pos = 0;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) if (qq == q) pos = cl[qq]++;
+      (inplace ? p.listB : p.listA)[(grp ? tl[inplace] : 0) + pos] = j;
+    }
+  }
+  if (tid == 0) {
+    p.counts[0] = tl[0]; p.counts[1] = tl[1]; p.counts[2] = tl[2]; p.counts[3] = tl[3]; p.counts[4] = tl[4];
+  }
+}
+
+}  // namespace rb

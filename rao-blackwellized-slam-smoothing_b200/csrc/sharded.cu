@@ -23,6 +23,7 @@
 #include <cstring>
 #include "engine_internal.h"
 #include "step_kernels.cuh"
+#include "shard_plan.cuh"
 
 using namespace rb;
 
@@ -39,7 +40,10 @@ struct ShardWs {
   double *traj_max = nullptr, *traj_mean = nullptr;
   int *g_Ahist = nullptr, *iwmax = nullptr;
   unsigned long long *flags = nullptr;
-  int *d_glob = nullptr, *d_fetch = nullptr, *d_owner = nullptr, *d_lslot = nullptr;
+  int *d_glob = nullptr, *d_fetch = nullptr;
+  int *d_own[2] = {nullptr, nullptr}, *d_lsl[2] = {nullptr, nullptr};   // replicated owner / slot maps (device)
+  int *d_nchild = nullptr, *d_keeper = nullptr, *d_unsafe = nullptr, *d_inv = nullptr, *d_dead = nullptr, *d_expo = nullptr;
+  bool host_plan = false;
   PeerTable peers{};
   bool imported[SH_COUNT][RB_MAXW] = {};
   std::vector<int> owner[2], lslot[2];
@@ -59,7 +63,8 @@ void rb_shard_free(rbslam_ctx *ctx) {
     for (int r = 0; r < RB_MAXW; ++r)
       if (s->imported[w][r]) cudaIpcCloseMemHandle(s->peers.p[w][r]);
   void *ptrs[] = {s->g_Xhist, s->g_w, s->g_wc, s->g_logw, s->traj_max, s->traj_mean, s->g_Ahist, s->iwmax,
-                  s->flags, s->d_glob, s->d_fetch, s->d_owner, s->d_lslot};
+                  s->flags, s->d_glob, s->d_fetch, s->d_own[0], s->d_own[1], s->d_lsl[0], s->d_lsl[1], s->d_nchild,
+                  s->d_keeper, s->d_unsafe, s->d_inv, s->d_dead, s->d_expo};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete s;
   ctx->shard_ws = nullptr;
@@ -128,11 +133,11 @@ extern "C" int rbslam_plan_shard(int32_t N, int32_t world, const int32_t *ai, co
 // ---------------------------------------------------------------------------
 // pull the ancestor state of every migrant out of the exporter's HBM (NVLink peer loads)
 __global__ void __launch_bounds__(256)
-k_peer_fetch(int n_fetch, const int *__restrict__ fetch, PeerTable pt, int cg, int cx, size_t slab,
-             int ld, int M, double *__restrict__ P, double *__restrict__ G4, double *__restrict__ KS4,
-             double *__restrict__ xl) {
-  const int f = blockIdx.y;
-  if (f >= n_fetch) return;
+k_peer_fetch(const int *__restrict__ n_fetch_p, const int *__restrict__ fetch, PeerTable pt, int cg, int cx,
+             size_t slab, int ld, int M, double *__restrict__ P, double *__restrict__ G4,
+             double *__restrict__ KS4, double *__restrict__ xl) {
+  const int n_fetch = *n_fetch_p;
+  for (int f = blockIdx.y; f < n_fetch; f += gridDim.y) {
   const int j = fetch[4 * f], sr = fetch[4 * f + 1], ss = fetch[4 * f + 2];
   const double2 *srcP = reinterpret_cast<const double2 *>(static_cast<const double *>(pt.p[SH_P][sr]) + (size_t)ss * slab);
   double2 *dstP = reinterpret_cast<double2 *>(P + (size_t)j * slab);
@@ -148,6 +153,7 @@ k_peer_fetch(int n_fetch, const int *__restrict__ fetch, PeerTable pt, int cg, i
       KS4[(size_t)j * ld * 4 + idx] = sk[idx];
     }
     for (int idx = threadIdx.x; idx < M; idx += blockDim.x) xl[(size_t)j * M + idx] = sx[idx];
+  }
   }
 }
 
@@ -227,10 +233,14 @@ int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN) {
   RB_ALLOC(s->traj_max, (size_t)T * n); RB_ALLOC(s->traj_mean, (size_t)T * n); RB_ALLOC(s->iwmax, T);
   RB_ALLOC(s->flags, 64);
   RB_ALLOC(s->d_glob, s->Nloc); RB_ALLOC(s->d_fetch, (size_t)4 * s->Nloc);
-  RB_ALLOC(s->d_owner, gN); RB_ALLOC(s->d_lslot, gN);
+  for (int b = 0; b < 2; ++b) { RB_ALLOC(s->d_own[b], gN); RB_ALLOC(s->d_lsl[b], gN); }
+  RB_ALLOC(s->d_nchild, gN); RB_ALLOC(s->d_keeper, gN); RB_ALLOC(s->d_unsafe, gN); RB_ALLOC(s->d_inv, s->Nloc);
+  RB_ALLOC(s->d_dead, gN); RB_ALLOC(s->d_expo, gN);
+  s->host_plan = getenv("RBSLAM_HOST_PLAN") != nullptr;
   CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned long long)));
   CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_fetch, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_plan, cudaEventDisableTiming));
   void *own[SH_COUNT] = {ctx->d_P, ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_xl[0],
                          ctx->d_xl[1], s->g_logw, s->flags};
   for (int w = 0; w < SH_COUNT; ++w) s->peers.p[w][rank] = own[w];
@@ -307,6 +317,8 @@ int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
   for (int b = 0; b < 2; ++b) { s->owner[b].assign(gN, 0); s->lslot[b].assign(gN, 0); }
   for (int i = 0; i < gN; ++i) { s->owner[0][i] = i / Nloc; s->lslot[0][i] = i % Nloc; }
   s->cur = 0;
+  CK(cudaMemcpyAsync(s->d_own[0], s->owner[0].data(), sizeof(int) * gN, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(s->d_lsl[0], s->lslot[0].data(), sizeof(int) * gN, cudaMemcpyHostToDevice, ctx->stream));
   s->h_glob.assign(Nloc, 0);
   for (int j = 0; j < Nloc; ++j) s->h_glob[j] = s->rank * Nloc + j;
   CK(cudaMemcpyAsync(s->d_glob, s->h_glob.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
@@ -335,68 +347,92 @@ int rb_shard_step(rbslam_ctx *ctx) {
     smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
     k_resample<<<1, 1024, smem, ctx->stream>>>(gN, 0, gN, s->g_w, s->g_wc, rs, nullptr, ai, ctx->d_status);
     ctx->launches += 1;
-    // identical plan on every rank (host, pure integer logic)
-    s->h_ai.resize(gN);
-    if ((rc = rb_d2h(ctx, s->h_ai.data(), ai, sizeof(int) * gN))) return rc;
     const int o = s->cur, nw = 1 - s->cur;
-    int nmig = 0;
-    if (rbslam_plan_shard(gN, s->world, s->h_ai.data(), s->owner[o].data(), s->lslot[o].data(),
-                          s->owner[nw].data(), s->lslot[nw].data(), &nmig) != RBSLAM_OK)
-      return ctx->fail(RBSLAM_EARG, "internal: shard plan failed");
-    s->migrated += nmig;
-    // Work lists in two groups.  Group 0 ("safe") touches no slab that a peer may still be
-    // reading and runs WHILE migrants are in flight; group 1 (everything that involves an
-    // exported slab, plus the migrants themselves) runs after the peer barrier.  All local
-    // offspring of one ancestor are kept in the same group so that copies still precede the
-    // in-place update of their source slab.
-    s->h_src.assign(Nloc, 0); s->h_fetch.clear();
-    for (int q = 0; q < 4; ++q) s->h_lists[q].clear();   // A0, B0, A1, B1
-    s->h_nchild.assign(gN, 0); s->h_unsafe.assign(gN, 0); s->h_inv.assign(Nloc, -1);
-    for (int i = 0; i < gN; ++i) {
-      const int a = s->h_ai[i];
-      ++s->h_nchild[a];
-      if (s->owner[nw][i] != s->owner[o][a]) s->h_unsafe[a] = 1;        // ancestor's slab is exported
-      if (s->owner[o][i] == s->rank) s->h_inv[s->lslot[o][i]] = i;      // old particle living in each slot
-    }
-    for (int i = 0; i < gN; ++i) {   // a copy landing in an exported-only slot must wait as well
-      if (s->owner[nw][i] != s->rank) continue;
-      const int a = s->h_ai[i];
-      if (s->owner[o][a] != s->rank) continue;
-      const int old = s->h_inv[s->lslot[nw][i]];
-      if (old != a && old >= 0 && s->h_nchild[old] > 0) s->h_unsafe[a] = 1;
-    }
-    for (int i = 0; i < gN; ++i) {
-      if (s->owner[nw][i] != s->rank) continue;
-      const int j = s->lslot[nw][i], a = s->h_ai[i];
-      s->h_glob[j] = i;
-      if (s->owner[o][a] != s->rank) {          // migrant: fetched into slot j, then updated in place
-        s->h_fetch.push_back(j); s->h_fetch.push_back(s->owner[o][a]); s->h_fetch.push_back(s->lslot[o][a]);
-        s->h_fetch.push_back(0);
-        s->h_src[j] = j; s->h_lists[3].push_back(j);
-      } else {
-        s->h_src[j] = s->lslot[o][a];
-        const int grp = s->h_unsafe[a] ? 1 : 0;
-        s->h_lists[2 * grp + (s->h_src[j] == j ? 1 : 0)].push_back(j);
+    if (!s->host_plan) {
+      // plan on the device: no host round trip in the step (shard_plan.cuh)
+      PlanArgs pa;
+      pa.N = gN; pa.world = s->world; pa.rank = s->rank; pa.ai = ai;
+      pa.owner_old = s->d_own[o]; pa.lslot_old = s->d_lsl[o]; pa.owner_new = s->d_own[nw]; pa.lslot_new = s->d_lsl[nw];
+      pa.n_child = s->d_nchild; pa.keeper = s->d_keeper; pa.unsafe = s->d_unsafe; pa.inv = s->d_inv;
+      pa.dead_list = s->d_dead; pa.expo_list = s->d_expo;
+      pa.src_slot = ctx->d_src_slot; pa.glob = s->d_glob; pa.listA = ctx->d_listA; pa.listB = ctx->d_listB;
+      pa.fetch = s->d_fetch; pa.counts = ctx->d_counts;
+      k_plan_shard<<<1, 1024, 0, ctx->stream>>>(pa);
+      ctx->launches += 1;
+      s->cur = nw;
+      ctx->stream_groups = 2;
+      ctx->group_off[0][0] = ctx->group_off[0][1] = ctx->group_off[1][0] = ctx->group_off[1][1] = 0;
+      ctx->group_off_dev[0][0] = ctx->group_off_dev[0][1] = nullptr;
+      ctx->group_off_dev[1][0] = ctx->d_counts + 0;   // group 1 lists start after group 0's
+      ctx->group_off_dev[1][1] = ctx->d_counts + 1;
+    } else {
+      // identical plan on every rank (host, pure integer logic)
+      s->h_ai.resize(gN);
+      if ((rc = rb_d2h(ctx, s->h_ai.data(), ai, sizeof(int) * gN))) return rc;
+      int nmig = 0;
+      if (rbslam_plan_shard(gN, s->world, s->h_ai.data(), s->owner[o].data(), s->lslot[o].data(),
+                            s->owner[nw].data(), s->lslot[nw].data(), &nmig) != RBSLAM_OK)
+        return ctx->fail(RBSLAM_EARG, "internal: shard plan failed");
+      s->migrated += nmig;
+      // Work lists in two groups.  Group 0 ("safe") touches no slab that a peer may still be
+      // reading and runs WHILE migrants are in flight; group 1 (everything that involves an
+      // exported slab, plus the migrants themselves) runs after the peer barrier.  All local
+      // offspring of one ancestor are kept in the same group so that copies still precede the
+      // in-place update of their source slab.
+      s->h_src.assign(Nloc, 0); s->h_fetch.clear();
+      for (int q = 0; q < 4; ++q) s->h_lists[q].clear();   // A0, B0, A1, B1
+      s->h_nchild.assign(gN, 0); s->h_unsafe.assign(gN, 0); s->h_inv.assign(Nloc, -1);
+      for (int i = 0; i < gN; ++i) {
+        const int a = s->h_ai[i];
+        ++s->h_nchild[a];
+        if (s->owner[nw][i] != s->owner[o][a]) s->h_unsafe[a] = 1;        // ancestor's slab is exported
+        if (s->owner[o][i] == s->rank) s->h_inv[s->lslot[o][i]] = i;      // old particle living in each slot
       }
+      for (int i = 0; i < gN; ++i) {   // a copy landing in an exported-only slot must wait as well
+        if (s->owner[nw][i] != s->rank) continue;
+        const int a = s->h_ai[i];
+        if (s->owner[o][a] != s->rank) continue;
+        const int old = s->h_inv[s->lslot[nw][i]];
+        if (old != a && old >= 0 && s->h_nchild[old] > 0) s->h_unsafe[a] = 1;
+      }
+      for (int i = 0; i < gN; ++i) {
+        if (s->owner[nw][i] != s->rank) continue;
+        const int j = s->lslot[nw][i], a = s->h_ai[i];
+        s->h_glob[j] = i;
+        if (s->owner[o][a] != s->rank) {          // migrant: fetched into slot j, then updated in place
+          s->h_fetch.push_back(j); s->h_fetch.push_back(s->owner[o][a]); s->h_fetch.push_back(s->lslot[o][a]);
+          s->h_fetch.push_back(0);
+          s->h_src[j] = j; s->h_lists[3].push_back(j);
+        } else {
+          s->h_src[j] = s->lslot[o][a];
+          const int grp = s->h_unsafe[a] ? 1 : 0;
+          s->h_lists[2 * grp + (s->h_src[j] == j ? 1 : 0)].push_back(j);
+        }
+      }
+      s->cur = nw;
+      const int nF = (int)s->h_fetch.size() / 4;
+      const int counts[4] = {(int)s->h_lists[0].size(), (int)s->h_lists[1].size(), (int)s->h_lists[2].size(),
+                             (int)s->h_lists[3].size()};
+      ctx->stream_groups = 2;
+      ctx->group_off[0][0] = 0; ctx->group_off[0][1] = 0;
+      ctx->group_off[1][0] = counts[0]; ctx->group_off[1][1] = counts[1];
+      CK(cudaMemcpyAsync(ctx->d_src_slot, s->h_src.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
+      for (int q = 0; q < 4; ++q) {
+        if (!counts[q]) continue;
+        int *dst = (q & 1 ? ctx->d_listB : ctx->d_listA) + (q >= 2 ? counts[q - 2] : 0);
+        CK(cudaMemcpyAsync(dst, s->h_lists[q].data(), sizeof(int) * counts[q], cudaMemcpyHostToDevice, ctx->stream));
+      }
+      CK(cudaMemcpyAsync(ctx->d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(s->d_glob, s->h_glob.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
+      if (nF) CK(cudaMemcpyAsync(s->d_fetch, s->h_fetch.data(), sizeof(int) * 4 * nF, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));   // the host vectors are reused next step
+      ctx->h2d += (int64_t)sizeof(int) * (3 * Nloc + 4 * nF);
+      CK(cudaMemcpyAsync(s->d_own[nw], s->owner[nw].data(), sizeof(int) * gN, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(s->d_lsl[nw], s->lslot[nw].data(), sizeof(int) * gN, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->d_counts + 4, &nF, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      ctx->group_off_dev[1][0] = ctx->group_off_dev[1][1] = nullptr;
     }
-    s->cur = nw;
-    const int nF = (int)s->h_fetch.size() / 4;
-    const int counts[4] = {(int)s->h_lists[0].size(), (int)s->h_lists[1].size(), (int)s->h_lists[2].size(),
-                           (int)s->h_lists[3].size()};
-    ctx->stream_groups = 2;
-    ctx->group_off[0][0] = 0; ctx->group_off[0][1] = 0;
-    ctx->group_off[1][0] = counts[0]; ctx->group_off[1][1] = counts[1];
-    CK(cudaMemcpyAsync(ctx->d_src_slot, s->h_src.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
-    for (int q = 0; q < 4; ++q) {
-      if (!counts[q]) continue;
-      int *dst = (q & 1 ? ctx->d_listB : ctx->d_listA) + (q >= 2 ? counts[q - 2] : 0);
-      CK(cudaMemcpyAsync(dst, s->h_lists[q].data(), sizeof(int) * counts[q], cudaMemcpyHostToDevice, ctx->stream));
-    }
-    CK(cudaMemcpyAsync(ctx->d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(s->d_glob, s->h_glob.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
-    if (nF) CK(cudaMemcpyAsync(s->d_fetch, s->h_fetch.data(), sizeof(int) * 4 * nF, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));   // the host vectors are reused next step
-    ctx->h2d += (int64_t)sizeof(int) * (3 * Nloc + 4 * nF);
     rb_phase_end(ctx);
     rb_phase_begin(ctx, RB_PH_PROPAGATE);
     NormalSrc ns;
@@ -408,12 +444,12 @@ int rb_shard_step(rbslam_ctx *ctx) {
     ctx->launches += 1;
     rb_phase_end(ctx);
     // migrants travel on a second stream, concurrently with the "safe" group of the Kalman pass
-    if (nF) {
-      k_peer_fetch<<<dim3(16, nF), 256, 0, ctx->stream2>>>(nF, s->d_fetch, s->peers, ctx->cg, ctx->cx, ctx->slab,
-                                                           ctx->ld, M, ctx->d_P, ctx->d_G4[ctx->cg], ctx->d_KS4[ctx->cg],
-                                                           ctx->d_xl[ctx->cx]);
-      ctx->launches += 1;
-    }
+    CK(cudaEventRecord(ctx->ev_plan, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_plan, 0));   // plan written, previous step complete
+    k_peer_fetch<<<dim3(16, std::min(Nloc, 256)), 256, 0, ctx->stream2>>>(
+        ctx->d_counts + 4, s->d_fetch, s->peers, ctx->cg, ctx->cx, ctx->slab, ctx->ld, M, ctx->d_P,
+        ctx->d_G4[ctx->cg], ctx->d_KS4[ctx->cg], ctx->d_xl[ctx->cx]);
+    ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev_fetch, ctx->stream2));
   } else {
     k_plan_identity<<<(Nloc + 255) / 256, 256, 0, ctx->stream>>>(Nloc, ctx->d_slot[ctx->cs], ctx->d_src_slot,
@@ -458,20 +494,25 @@ int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
   if (rc) return rc;
   if (s->rank == 0) {
     const int cur = s->cur;
-    CK(cudaMemcpyAsync(s->d_owner, s->owner[cur].data(), sizeof(int) * gN, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(s->d_lslot, s->lslot[cur].data(), sizeof(int) * gN, cudaMemcpyHostToDevice, ctx->stream));
     const int *iw = s->iwmax + (T - 1);
     double *means = ctx->d_scratch;
     double *Pmax = ctx->d_scratch + 2 * (size_t)M + 64, *Pmean = Pmax + (size_t)M * M;
-    k_final_means_sharded<<<(M + 127) / 128, 128, 0, ctx->stream>>>(gN, M, s->d_owner, s->d_lslot, s->peers, ctx->cx,
+    k_final_means_sharded<<<(M + 127) / 128, 128, 0, ctx->stream>>>(gN, M, s->d_own[cur], s->d_lsl[cur], s->peers, ctx->cx,
                                                                    s->g_w, iw, means);
     ctx->launches += 1;
     int im = 0;
     double wl = 0.0;
     if ((rc = rb_d2h(ctx, &im, iw, sizeof(int)))) return rc;
     if ((rc = rb_d2h(ctx, &wl, s->g_w + (gN - 1), sizeof(double)))) return rc;
+    int own2[2], lsl2[2];   // owner / slot of the two particles whose slabs are read out
+    const int sel[2] = {im, gN - 1};
+    for (int q = 0; q < 2; ++q) {
+      if ((rc = rb_d2h(ctx, &own2[q], s->d_own[cur] + sel[q], sizeof(int)))) return rc;
+      if ((rc = rb_d2h(ctx, &lsl2[q], s->d_lsl[cur] + sel[q], sizeof(int)))) return rc;
+    }
     auto at = [&](int which, int i, size_t stride) {
-      return static_cast<const double *>(s->peers.p[which][s->owner[cur][i]]) + (size_t)s->lslot[cur][i] * stride;
+      const int q = (i == im) ? 0 : 1;
+      return static_cast<const double *>(s->peers.p[which][own2[q]]) + (size_t)lsl2[q] * stride;
     };
     const int gsel = ctx->cg ? SH_G4B : SH_G4A, ksel = ctx->cg ? SH_KS4B : SH_KS4A, xsel = ctx->cx ? SH_XLB : SH_XLA;
     const size_t t4 = (size_t)ld * 4;
@@ -514,3 +555,49 @@ int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
 }
 
 int64_t rb_shard_migrated(rbslam_ctx *ctx) { return sh_of(ctx) ? sh_of(ctx)->migrated : 0; }
+
+// kernel-level entry point (parity test): run the DEVICE planner on host arrays
+extern "C" int rbslam_op_plan_shard(int32_t device, int32_t N, int32_t world, int32_t rank, const int32_t *ai,
+                                    const int32_t *owner_old, const int32_t *lslot_old, int32_t *owner_new,
+                                    int32_t *lslot_new, int32_t *src_slot, int32_t *glob, int32_t *listA,
+                                    int32_t *listB, int32_t *fetch, int32_t *counts8) {
+  if (N < 1 || world < 1 || world > RB_PW || N % world || rank < 0 || rank >= world || !ai || !owner_old ||
+      !lslot_old || !owner_new || !lslot_new || !src_slot || !glob || !listA || !listB || !fetch || !counts8)
+    return RBSLAM_EARG;
+  if (cudaSetDevice(device) != cudaSuccess) return RBSLAM_ECUDA;
+  const int Nloc = N / world;
+  int *buf = nullptr;
+  const size_t total = (size_t)10 * N + (size_t)8 * Nloc + 8;
+  if (cudaMalloc(&buf, total * sizeof(int)) != cudaSuccess) return RBSLAM_ECUDA;
+  int *p = buf;
+  auto take = [&](size_t n) { int *q = p; p += n; return q; };
+  PlanArgs pa;
+  pa.N = N; pa.world = world; pa.rank = rank;
+  int *d_ai = take(N), *d_oo = take(N), *d_lo = take(N);
+  pa.ai = d_ai; pa.owner_old = d_oo; pa.lslot_old = d_lo;
+  pa.owner_new = take(N); pa.lslot_new = take(N); pa.n_child = take(N); pa.keeper = take(N); pa.unsafe = take(N);
+  pa.dead_list = take(N); pa.expo_list = take(N);
+  pa.inv = take(Nloc); pa.src_slot = take(Nloc); pa.glob = take(Nloc); pa.listA = take(Nloc); pa.listB = take(Nloc);
+  pa.fetch = take((size_t)3 * Nloc); pa.counts = take(8);
+  // fetch needs 4*Nloc ints: it shares the tail with counts only if 3*Nloc+8 >= 4*Nloc; allocate separately
+  int *d_fetch = nullptr;
+  if (cudaMalloc(&d_fetch, (size_t)4 * Nloc * sizeof(int)) != cudaSuccess) { cudaFree(buf); return RBSLAM_ECUDA; }
+  pa.fetch = d_fetch;
+  cudaMemcpy(d_ai, ai, sizeof(int) * N, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_oo, owner_old, sizeof(int) * N, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_lo, lslot_old, sizeof(int) * N, cudaMemcpyHostToDevice);
+  cudaMemset(pa.counts, 0, 8 * sizeof(int));
+  k_plan_shard<<<1, 1024>>>(pa);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(owner_new, pa.owner_new, sizeof(int) * N, cudaMemcpyDeviceToHost);
+  cudaMemcpy(lslot_new, pa.lslot_new, sizeof(int) * N, cudaMemcpyDeviceToHost);
+  cudaMemcpy(src_slot, pa.src_slot, sizeof(int) * Nloc, cudaMemcpyDeviceToHost);
+  cudaMemcpy(glob, pa.glob, sizeof(int) * Nloc, cudaMemcpyDeviceToHost);
+  cudaMemcpy(listA, pa.listA, sizeof(int) * Nloc, cudaMemcpyDeviceToHost);
+  cudaMemcpy(listB, pa.listB, sizeof(int) * Nloc, cudaMemcpyDeviceToHost);
+  cudaMemcpy(fetch, pa.fetch, sizeof(int) * 4 * Nloc, cudaMemcpyDeviceToHost);
+  cudaMemcpy(counts8, pa.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d_fetch);
+  cudaFree(buf);
+  return e == cudaSuccess ? RBSLAM_OK : RBSLAM_ECUDA;
+}

@@ -425,7 +425,7 @@ static int info_kalman_phase_d(rbslam_ctx *ctx, const double *y_t_dev, const dou
       {                                                                                                \
         auto kern = k_stream_pass<D, DA, R2V, 8, 2>;                                                   \
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024))); \
-        kern<<<grid, RB_STREAM_THREADS, smem, ctx->stream>>>(sa, list, cnt);                           \
+        kern<<<grid, RB_STREAM_THREADS, smem, ctx->stream>>>(sa, list, cnt, nullptr);                       \
       }
       switch (R2) { case 1: RB_INFO_LAUNCH(1, D) break; case 2: RB_INFO_LAUNCH(2, D) break;
                     case 3: RB_INFO_LAUNCH(3, D) break; default: RB_INFO_LAUNCH(4, D) break; }

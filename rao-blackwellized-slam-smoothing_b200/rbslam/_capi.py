@@ -101,6 +101,7 @@ SYMBOLS = {
                                         c_int32_p]),
     "rbslam_plan_shard": (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                     c_int32_p, c_int32_p]),
+    "rbslam_op_plan_shard": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [c_int32_p] * 11),
     "rbslam_ipc_count": (C.c_int, []),
     "rbslam_ipc_export": (C.c_int, [_ctx, C.c_int32, C.c_void_p]),
     "rbslam_ipc_import": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p]),

@@ -86,3 +86,65 @@ def test_sharded_filter_matches_single_gpu_and_oracle(rbslam_lib, world, N, m, T
     ref = oracle.particleFilter(om, *args, N, pr["dt"], st)
     for k, r in zip(["traj_max", "traj_mean", "xl_max", "xl_mean", "P_max", "P_mean"], ref):
         assert_close_norm(sh[k], r, 1e-7, "sharded vs oracle: " + k)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_device_planner_equals_host_planner(rbslam_lib, world):
+    """k_plan_shard (device) must reproduce rbslam_plan_shard (host reference) exactly, and its
+    work lists must cover every local slab once with the in-place / copy / fetch roles right."""
+    import ctypes as C
+    from rbslam import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(world)
+    for N in (64 * world, 1000 * world):
+        Nloc = N // world
+        owner = (np.arange(N) // Nloc).astype(np.int32)
+        lslot = (np.arange(N) % Nloc).astype(np.int32)
+        for step in range(5):
+            w = rng.random(N) ** (1 + 5 * (step % 3))
+            ai = rng.choice(N, size=N, p=w / w.sum()).astype(np.int32)
+            ho, hl = np.zeros(N, np.int32), np.zeros(N, np.int32)
+            nm = C.c_int32()
+            assert L.rbslam_plan_shard(N, world, _capi.iptr(ai), _capi.iptr(owner), _capi.iptr(lslot),
+                                       _capi.iptr(ho), _capi.iptr(hl), C.byref(nm)) == 0
+            n_child = np.bincount(ai, minlength=N)
+            for rank in range(world):
+                do, dl = np.zeros(N, np.int32), np.zeros(N, np.int32)
+                src, glob = np.zeros(Nloc, np.int32), np.zeros(Nloc, np.int32)
+                lA, lB = np.zeros(Nloc, np.int32), np.zeros(Nloc, np.int32)
+                fetch, cnt = np.zeros(4 * Nloc, np.int32), np.zeros(8, np.int32)
+                rc = L.rbslam_op_plan_shard(0, N, world, rank, *[_capi.iptr(x) for x in
+                                            (ai, owner, lslot, do, dl, src, glob, lA, lB, fetch, cnt)])
+                assert rc == 0
+                assert np.array_equal(do, ho) and np.array_equal(dl, hl)
+                nA0, nB0, nA1, nB1, nF, nmig = cnt[:6]
+                assert nmig == nm.value
+                assert nA0 + nA1 + nB0 + nB1 == Nloc
+                items = np.concatenate([lA[:nA0 + nA1], lB[:nB0 + nB1]])
+                assert sorted(items) == list(range(Nloc))                    # every local slab once
+                mine = np.flatnonzero(do == rank)
+                assert np.array_equal(np.sort(glob), np.sort(mine))
+                assert np.array_equal(dl[glob], np.arange(Nloc))             # glob[j] lives in slot j
+                migr = {int(f) for f in fetch[:4 * nF:4]}
+                assert nF == np.count_nonzero(owner[ai[mine]] != rank)
+                exported = np.zeros(N, bool)
+                exported[ai[do != owner[ai]]] = True
+                for grp, (la, lb) in enumerate([(lA[:nA0], lB[:nB0]), (lA[nA0:nA0 + nA1], lB[nB0:nB0 + nB1])]):
+                    for j in la:                                             # copies: src != dst, local source
+                        a = ai[glob[j]]
+                        assert owner[a] == rank and src[j] == lslot[a] and src[j] != j
+                        assert grp == 1 or not exported[a]
+                    for j in lb:
+                        a = ai[glob[j]]
+                        if j in migr:
+                            assert grp == 1 and owner[a] != rank and src[j] == j
+                        else:
+                            assert owner[a] == rank and src[j] == lslot[a] == j
+                            assert grp == 1 or not exported[a]
+                for f in range(nF):                                          # migrants land in dead slabs
+                    j, sr, ss = fetch[4 * f:4 * f + 3]
+                    a = ai[glob[j]]
+                    assert owner[a] == sr and lslot[a] == ss
+                    old = np.flatnonzero((owner == rank) & (lslot == j))[0]
+                    assert n_child[old] == 0
+            owner, lslot = ho.copy(), hl.copy()
