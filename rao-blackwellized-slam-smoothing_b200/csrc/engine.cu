@@ -8,6 +8,7 @@
 #include "step_kernels.cuh"
 #include "kalman_kernels.cuh"
 #include "kalman_stream.cuh"
+#include "family_kernels.cuh"
 #include "engine_internal.h"
 
 using namespace rb;
@@ -316,6 +317,8 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
       RB_ALLOC(ctx->d_KS4[b], (size_t)N * ctx->ld * 4);
     }
     RB_ALLOC(ctx->d_PHp, (size_t)N * ctx->nsplit * ctx->ld * 4);
+    RB_ALLOC(ctx->d_fam, (size_t)17 * N + 8);
+    ctx->use_fam = getenv("RBSLAM_NO_FAM") == nullptr;
   }
   RB_ALLOC(ctx->d_logw, N); RB_ALLOC(ctx->d_w, N); RB_ALLOC(ctx->d_wc, N);
   ctx->T_hist = cfg->keep_history ? T : 2;
@@ -375,7 +378,7 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
                   ctx->d_ivec[1], ctx->d_hld[0], ctx->d_hld[1], ctx->d_slot[0], ctx->d_slot[1],
                   ctx->d_src_slot, ctx->d_first_child, ctx->d_free_list, ctx->d_listA, ctx->d_listB,
                   ctx->d_counts, ctx->d_H, ctx->d_yhat, ctx->d_PHpart, ctx->d_G, ctx->d_KS,
-                  ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_PHp,
+                  ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_PHp, ctx->d_fam,
                   ctx->d_logw, ctx->d_w, ctx->d_wc, ctx->d_Xhist, ctx->d_Ahist, ctx->d_traj_max,
                   ctx->d_traj_mean, ctx->d_iwmax, ctx->d_status, ctx->d_scratch};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -619,6 +622,41 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin) / (smem + 2048)));
   if (ctx->stream_ctas_per_sm > 0) per_sm = ctx->stream_ctas_per_sm;
   const int grid = std::min(N * ctx->nsplit, per_sm * ctx->num_sms);
+  if (ctx->use_fam) {
+    // sibling fusion: families of offspring share one read of the ancestor slab
+    int *fm = ctx->d_fam;
+    FamBuildArgs fb;
+    fb.n_items = N; fb.n_slabs = N; fb.n_items_dev = nullptr;
+    fb.src_slot = a.src_slot; fb.dst_slot = a.dst_slot; fb.anc = a.ai;
+    fb.s_cnt = fm; fb.s_keeper = fm + N; fb.s_cursor = fm + 2 * (size_t)N; fb.s_first = fm + 3 * (size_t)N;
+    fb.s_fid = fm + 4 * (size_t)N; fb.s_xoff = fm + 5 * (size_t)N; fb.s_xfam = fm + 6 * (size_t)N;
+    int *lb = fm + 7 * (size_t)N, *la = fm + 12 * (size_t)N, *cnts = fm + 17 * (size_t)N;
+    fb.fb_src = lb; fb.fb_anc = lb + N; fb.fb_first = lb + 2 * (size_t)N; fb.fb_cnt = lb + 3 * (size_t)N;
+    fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
+    fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
+    fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
+    k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
+    ctx->launches += 1;
+    auto fkern = k_stream_fam<D, R2, KC, S, RB_CB>;
+    const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 4 * KC * (1 + RB_CB));
+    static bool fattr_done = false;
+    if (!fattr_done) {
+      CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
+      fattr_done = true;
+    }
+    if (fsmem > ctx->smem_optin - 1024) return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
+    const int fgrid = std::min(N * ctx->nsplit, ctx->num_sms);
+    for (int phase = 0; phase < 2; ++phase) {
+      if (phase == 0 && !resampled) continue;   // surplus families exist only after resampling
+      FamLists fl;
+      const int *base = phase == 0 ? la : lb;
+      fl.n_fam = cnts + (phase == 0 ? 1 : 0);
+      fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
+      fl.child = base + 4 * (size_t)N;
+      fkern<<<fgrid, RB_STREAM_THREADS, fsmem, ctx->stream>>>(sa, fl);
+      ctx->launches += 1;
+    }
+  } else {
   for (int grp = 0; grp < ctx->stream_groups; ++grp) {
     if (grp > 0 && ctx->group_hook) {
       int rch = ctx->group_hook(ctx, grp);
@@ -631,6 +669,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
           ctx->d_counts + 2 * grp + phase, ctx->group_off_dev[grp][phase]);
       ctx->launches += 1;
     }
+  }
   }
   Innov4Args ia;
   ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = ctx->nsplit; ia.PHp = ctx->d_PHp; ia.H4 = a.H;

@@ -444,13 +444,13 @@ int rb_shard_step(rbslam_ctx *ctx) {
     ctx->launches += 1;
     rb_phase_end(ctx);
     // migrants travel on a second stream, concurrently with the "safe" group of the Kalman pass
-    CK(cudaEventRecord(ctx->ev_plan, ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_plan, 0));   // plan written, previous step complete
-    k_peer_fetch<<<dim3(16, std::min(Nloc, 256)), 256, 0, ctx->stream2>>>(
+    rb_phase_begin(ctx, RB_PH_ANCESTOR);   // reported as the "migration" phase
+    k_peer_fetch<<<dim3(16, std::min(Nloc, 256)), 256, 0, ctx->stream>>>(
         ctx->d_counts + 4, s->d_fetch, s->peers, ctx->cg, ctx->cx, ctx->slab, ctx->ld, M, ctx->d_P,
         ctx->d_G4[ctx->cg], ctx->d_KS4[ctx->cg], ctx->d_xl[ctx->cx]);
     ctx->launches += 1;
-    CK(cudaEventRecord(ctx->ev_fetch, ctx->stream2));
+    if ((rc = peer_barrier(ctx))) return rc;   // all remote reads of old slabs are done
+    rb_phase_end(ctx);
   } else {
     k_plan_identity<<<(Nloc + 255) / 256, 256, 0, ctx->stream>>>(Nloc, ctx->d_slot[ctx->cs], ctx->d_src_slot,
                                                                 ctx->d_listB, ctx->d_counts);
@@ -465,10 +465,9 @@ int rb_shard_step(rbslam_ctx *ctx) {
   rb_phase_end(ctx);
   rb_phase_begin(ctx, RB_PH_KALMAN);
   ctx->anc_override = ctx->d_src_slot;     // thin arrays are slot-indexed: ancestor index = source slot
-  ctx->group_hook = shard_group_hook;
+  ctx->stream_groups = 1;
   rc = rb_kalman_phase(ctx, ctx->d_y + (size_t)t * d, resampled);
   ctx->anc_override = nullptr;
-  ctx->group_hook = nullptr;
   ctx->stream_groups = 1;
   ctx->group_off[0][0] = ctx->group_off[0][1] = 0;
   rb_phase_end(ctx);
