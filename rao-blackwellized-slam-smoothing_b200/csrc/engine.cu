@@ -317,7 +317,7 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
       RB_ALLOC(ctx->d_KS4[b], (size_t)N * ctx->ld * 4);
     }
     RB_ALLOC(ctx->d_PHp, (size_t)N * ctx->nsplit * ctx->ld * 4);
-    RB_ALLOC(ctx->d_fam, (size_t)17 * N + 8);
+    RB_ALLOC(ctx->d_fam, (size_t)17 * N + 8);   // + counters: n_fb, n_fa, work counters [2]
     ctx->use_fam = getenv("RBSLAM_NO_FAM") == nullptr;
   }
   RB_ALLOC(ctx->d_logw, N); RB_ALLOC(ctx->d_w, N); RB_ALLOC(ctx->d_wc, N);
@@ -635,6 +635,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
     fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
     fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
     fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
+    CK(cudaMemsetAsync(cnts + 2, 0, 2 * sizeof(int), ctx->stream));   // dynamic work counters
     k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
     ctx->launches += 1;
     auto fkern = k_stream_fam<D, R2, KC, S, RB_CB>;
@@ -651,6 +652,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
       FamLists fl;
       const int *base = phase == 0 ? la : lb;
       fl.n_fam = cnts + (phase == 0 ? 1 : 0);
+      fl.work_counter = cnts + 2 + phase;
       fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
       fl.child = base + 4 * (size_t)N;
       fkern<<<fgrid, RB_STREAM_THREADS, fsmem, ctx->stream>>>(sa, fl);

@@ -21,6 +21,7 @@ namespace rb {
 #define RB_KF (2 * RB_CB)      // siblings handled by the main family item (incl. the keeper)
 
 struct FamLists {
+  int *work_counter;   // [1] dynamic work distribution (zeroed before the launch)
   const int *n_fam;    // [1] number of families
   const int *src;      // [n_fam] source slab
   const int *anc;      // [n_fam] ancestor index for the pending (G,KS) arrays
@@ -122,8 +123,19 @@ k_stream_fam(StreamArgs a, FamLists f) {
   }
   __syncthreads();
 
-  // ---- producer (thread 0): walks items -> batches -> column chunks, S stages ahead
-  int p_it = blockIdx.x, p_b = 0, p_c = 0, p_q = 0;
+  // ---- producer (thread 0): walks items -> batches -> column chunks, S stages ahead.
+  // Items are claimed dynamically (atomic counter): families cost 1..KF/CB passes, a static
+  // round-robin leaves CTAs idle at the end of the launch.  Claimed ids go through a small
+  // shared ring so that the consumers process exactly the sequence the producer issued.
+  __shared__ int s_ring[8];
+  int p_claim = 0;                 // number of items claimed so far (producer)
+  int p_it = 0, p_b = 0, p_c = 0, p_q = 0;
+  auto claim = [&]() {
+    p_it = atomicAdd(f.work_counter, 1);
+    s_ring[p_claim & 7] = p_it;
+    ++p_claim;
+  };
+  if (tid == 0) claim();
   auto issue = [&]() {
     if (p_it >= n_items) return;
     const int fam = p_it / a.nsplit, sp = p_it % a.nsplit;
@@ -146,7 +158,7 @@ k_stream_fam(StreamArgs a, FamLists f) {
     p_c += KC;
     if (c0 + p_c >= c1) {
       p_c = 0;
-      if (++p_b >= nbat) { p_b = 0; p_it += gridDim.x; }
+      if (++p_b >= nbat) { p_b = 0; claim(); }
     }
   };
   if (tid == 0) {
@@ -156,7 +168,10 @@ k_stream_fam(StreamArgs a, FamLists f) {
 
   // ---- consumers
   int q = 0;
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+  __syncthreads();                 // first claim and the first S issues are visible
+  for (int c_claim = 0;; ++c_claim) {
+    const int it = s_ring[c_claim & 7];   // written by the producer at least one barrier ago
+    if (it >= n_items) break;
     const int fam = it / a.nsplit, sp = it % a.nsplit;
     const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);
     const int an = f.anc[fam], cnt = f.cnt[fam], first = f.first[fam];
