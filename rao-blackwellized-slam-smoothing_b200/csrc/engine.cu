@@ -635,9 +635,6 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
     fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
     fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
     fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
-    CK(cudaMemsetAsync(cnts + 2, 0, 2 * sizeof(int), ctx->stream));   // dynamic work counters
-    k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
-    ctx->launches += 1;
     auto fkern = k_stream_fam<D, R2, KC, S, RB_CB>;
     const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 4 * KC * (1 + RB_CB));
     static bool fattr_done = false;
@@ -647,16 +644,28 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
     }
     if (fsmem > ctx->smem_optin - 1024) return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
     const int fgrid = std::min(N * ctx->nsplit, ctx->num_sms);
-    for (int phase = 0; phase < 2; ++phase) {
-      if (phase == 0 && !resampled) continue;   // surplus families exist only after resampling
-      FamLists fl;
-      const int *base = phase == 0 ? la : lb;
-      fl.n_fam = cnts + (phase == 0 ? 1 : 0);
-      fl.work_counter = cnts + 2 + phase;
-      fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
-      fl.child = base + 4 * (size_t)N;
-      fkern<<<fgrid, RB_STREAM_THREADS, fsmem, ctx->stream>>>(sa, fl);
+    const int ngrp = ctx->item_group ? ctx->stream_groups : 1;   // no group tags: one pass over all families
+    for (int grp = 0; grp < ngrp; ++grp) {
+      if (grp > 0 && ctx->group_hook) {   // sharded engine: migrants landed, peers done reading
+        int rch = ctx->group_hook(ctx, grp);
+        if (rch) return rch;
+      }
+      fb.item_group = ngrp > 1 ? ctx->item_group : nullptr;
+      fb.group = grp;
+      CK(cudaMemsetAsync(cnts + 2, 0, 2 * sizeof(int), ctx->stream));   // dynamic work counters
+      k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
       ctx->launches += 1;
+      for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 0 && !resampled) continue;   // surplus families exist only after resampling
+        FamLists fl;
+        const int *base = phase == 0 ? la : lb;
+        fl.n_fam = cnts + (phase == 0 ? 1 : 0);
+        fl.work_counter = cnts + 2 + phase;
+        fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
+        fl.child = base + 4 * (size_t)N;
+        fkern<<<fgrid, RB_STREAM_THREADS, fsmem, ctx->stream>>>(sa, fl);
+        ctx->launches += 1;
+      }
     }
   } else {
   for (int grp = 0; grp < ctx->stream_groups; ++grp) {
@@ -797,8 +806,14 @@ int rb_resample_phase(rbslam_ctx *ctx, int n_draws) {
   const int *forced = ctx->have_forced ? ctx->d_forced + soff : nullptr;
   size_t smem = sizeof(double) * (size_t)N;
   smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
-  k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, n_draws, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
-  ctx->launches += 1;
+  if (N > 16384 && n_draws > 1024) {   // large populations: scan in one CTA, draws over the grid
+    k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, -1, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
+    k_resample_search<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(N, 0, n_draws, ctx->d_wc, rs, forced, ai, ctx->d_status);
+    ctx->launches += 2;
+  } else {
+    k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, n_draws, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
+    ctx->launches += 1;
+  }
   CK(cudaGetLastError());
   return RBSLAM_OK;
 }

@@ -39,6 +39,8 @@ struct FamBuildArgs {
   const int *src_slot;      // [n_items] source slab of each item
   const int *dst_slot;      // [n_items] or nullptr (= item index)
   const int *anc;           // [n_items] or nullptr (= source slab)
+  const int *item_group;    // [n_items] or nullptr: only items with item_group[j] == group take part
+  int group;
   int *s_cnt, *s_keeper, *s_cursor, *s_first, *s_fid, *s_xoff, *s_xfam;   // [n_slabs] scratch
   // main families (launch 2) and surplus families (launch 1)
   int *fb_src, *fb_anc, *fb_first, *fb_cnt, *fb_child, *n_fb;
@@ -51,6 +53,7 @@ __global__ void __launch_bounds__(1024) k_build_families(FamBuildArgs p) {
   for (int s = tid; s < ns; s += blockDim.x) { p.s_cnt[s] = 0; p.s_keeper[s] = -1; p.s_cursor[s] = 0; }
   __syncthreads();
   for (int j = tid; j < n; j += blockDim.x) {
+    if (p.item_group && p.item_group[j] != p.group) continue;
     const int s = p.src_slot[j];
     atomicAdd(&p.s_cnt[s], 1);
     if ((p.dst_slot ? p.dst_slot[j] : j) == s) p.s_keeper[s] = j;
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(1024) k_build_families(FamBuildArgs p) {
   if (tid == 0) { *p.n_fb = tot[0]; *p.n_fa = tot[2]; }
   __syncthreads();
   for (int j = tid; j < n; j += blockDim.x) {
+    if (p.item_group && p.item_group[j] != p.group) continue;
     const int s = p.src_slot[j];
     const int c = p.s_cnt[s], nm = min(c, RB_KF), kp = p.s_keeper[s];
     const int an = p.anc ? p.anc[j] : s;

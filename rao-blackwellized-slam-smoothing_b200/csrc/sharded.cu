@@ -42,8 +42,10 @@ struct ShardWs {
   unsigned long long *flags = nullptr;
   int *d_glob = nullptr, *d_fetch = nullptr;
   int *d_own[2] = {nullptr, nullptr}, *d_lsl[2] = {nullptr, nullptr};   // replicated owner / slot maps (device)
+  int *d_group = nullptr;   // [Nloc] work group of each local item
   int *d_nchild = nullptr, *d_keeper = nullptr, *d_unsafe = nullptr, *d_inv = nullptr, *d_dead = nullptr, *d_expo = nullptr;
   bool host_plan = false;
+  bool overlap = false;    // RBSLAM_OVERLAP=1: migrants travel while the safe work group runs (measured slower)
   PeerTable peers{};
   bool imported[SH_COUNT][RB_MAXW] = {};
   std::vector<int> owner[2], lslot[2];
@@ -51,6 +53,7 @@ struct ShardWs {
   unsigned long long epoch = 0;
   std::vector<int> h_ai, h_src, h_listA, h_listB, h_glob, h_fetch, h_nchild, h_inv, h_lists[4];
   std::vector<unsigned char> h_unsafe;
+  std::vector<int> h_group;
   int64_t migrated = 0;
 };
 
@@ -64,7 +67,7 @@ void rb_shard_free(rbslam_ctx *ctx) {
       if (s->imported[w][r]) cudaIpcCloseMemHandle(s->peers.p[w][r]);
   void *ptrs[] = {s->g_Xhist, s->g_w, s->g_wc, s->g_logw, s->traj_max, s->traj_mean, s->g_Ahist, s->iwmax,
                   s->flags, s->d_glob, s->d_fetch, s->d_own[0], s->d_own[1], s->d_lsl[0], s->d_lsl[1], s->d_nchild,
-                  s->d_keeper, s->d_unsafe, s->d_inv, s->d_dead, s->d_expo};
+                  s->d_keeper, s->d_unsafe, s->d_inv, s->d_dead, s->d_expo, s->d_group};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete s;
   ctx->shard_ws = nullptr;
@@ -131,29 +134,44 @@ extern "C" int rbslam_plan_shard(int32_t N, int32_t world, const int32_t *ai, co
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-// pull the ancestor state of every migrant out of the exporter's HBM (NVLink peer loads)
+// pull the ancestor state of every migrant out of the exporter's HBM (NVLink peer loads).
+// Work is flattened to (migrant, 64 KiB chunk) units and grid-strided so that a bounded grid
+// (2 CTAs per SM when overlapping: 2 x 256 threads x 32 registers + the 192 x 232 registers of
+// the streaming Kalman CTA still fit the 64 K register file, so both kernels are co-resident on
+// every SM) keeps ~5 MB of loads in flight while the safe work group runs concurrently.
+#define RB_FETCH_CHUNK2 4096   // double2 elements per unit = 64 KiB
 __global__ void __launch_bounds__(256)
 k_peer_fetch(const int *__restrict__ n_fetch_p, const int *__restrict__ fetch, PeerTable pt, int cg, int cx,
              size_t slab, int ld, int M, double *__restrict__ P, double *__restrict__ G4,
              double *__restrict__ KS4, double *__restrict__ xl) {
   const int n_fetch = *n_fetch_p;
-  for (int f = blockIdx.y; f < n_fetch; f += gridDim.y) {
-  const int j = fetch[4 * f], sr = fetch[4 * f + 1], ss = fetch[4 * f + 2];
-  const double2 *srcP = reinterpret_cast<const double2 *>(static_cast<const double *>(pt.p[SH_P][sr]) + (size_t)ss * slab);
-  double2 *dstP = reinterpret_cast<double2 *>(P + (size_t)j * slab);
   const size_t n2 = slab / 2;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n2; idx += (size_t)gridDim.x * blockDim.x)
-    dstP[idx] = srcP[idx];
-  if (blockIdx.x == 0) {
-    const double *sg = static_cast<const double *>(pt.p[cg ? SH_G4B : SH_G4A][sr]) + (size_t)ss * ld * 4;
-    const double *sk = static_cast<const double *>(pt.p[cg ? SH_KS4B : SH_KS4A][sr]) + (size_t)ss * ld * 4;
-    const double *sx = static_cast<const double *>(pt.p[cx ? SH_XLB : SH_XLA][sr]) + (size_t)ss * M;
-    for (int idx = threadIdx.x; idx < ld * 4; idx += blockDim.x) {
-      G4[(size_t)j * ld * 4 + idx] = sg[idx];
-      KS4[(size_t)j * ld * 4 + idx] = sk[idx];
+  const int nchunk = (int)((n2 + RB_FETCH_CHUNK2 - 1) / RB_FETCH_CHUNK2);
+  const long long units = (long long)n_fetch * (nchunk + 1);
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const int f = (int)(u / (nchunk + 1)), c = (int)(u % (nchunk + 1));
+    const int j = fetch[4 * f], sr = fetch[4 * f + 1], ss = fetch[4 * f + 2];
+    if (c < nchunk) {
+      const double2 *srcP =
+          reinterpret_cast<const double2 *>(static_cast<const double *>(pt.p[SH_P][sr]) + (size_t)ss * slab);
+      double2 *dstP = reinterpret_cast<double2 *>(P + (size_t)j * slab);
+      const size_t lo = (size_t)c * RB_FETCH_CHUNK2, hi = lo + RB_FETCH_CHUNK2 < n2 ? lo + RB_FETCH_CHUNK2 : n2;
+      size_t idx = lo + threadIdx.x;
+      for (; idx + 3 * 256 < hi; idx += 4 * 256) {   // four independent 16 B loads in flight per thread
+        const double2 v0 = srcP[idx], v1 = srcP[idx + 256], v2 = srcP[idx + 512], v3 = srcP[idx + 768];
+        dstP[idx] = v0; dstP[idx + 256] = v1; dstP[idx + 512] = v2; dstP[idx + 768] = v3;
+      }
+      for (; idx < hi; idx += 256) dstP[idx] = srcP[idx];
+    } else {   // the thin per-particle arrays: pending downdate pair and the mean
+      const double *sg = static_cast<const double *>(pt.p[cg ? SH_G4B : SH_G4A][sr]) + (size_t)ss * ld * 4;
+      const double *sk = static_cast<const double *>(pt.p[cg ? SH_KS4B : SH_KS4A][sr]) + (size_t)ss * ld * 4;
+      const double *sx = static_cast<const double *>(pt.p[cx ? SH_XLB : SH_XLA][sr]) + (size_t)ss * M;
+      for (int idx = threadIdx.x; idx < ld * 4; idx += blockDim.x) {
+        G4[(size_t)j * ld * 4 + idx] = sg[idx];
+        KS4[(size_t)j * ld * 4 + idx] = sk[idx];
+      }
+      for (int idx = threadIdx.x; idx < M; idx += blockDim.x) xl[(size_t)j * M + idx] = sx[idx];
     }
-    for (int idx = threadIdx.x; idx < M; idx += blockDim.x) xl[(size_t)j * M + idx] = sx[idx];
-  }
   }
 }
 
@@ -235,8 +253,9 @@ int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN) {
   RB_ALLOC(s->d_glob, s->Nloc); RB_ALLOC(s->d_fetch, (size_t)4 * s->Nloc);
   for (int b = 0; b < 2; ++b) { RB_ALLOC(s->d_own[b], gN); RB_ALLOC(s->d_lsl[b], gN); }
   RB_ALLOC(s->d_nchild, gN); RB_ALLOC(s->d_keeper, gN); RB_ALLOC(s->d_unsafe, gN); RB_ALLOC(s->d_inv, s->Nloc);
-  RB_ALLOC(s->d_dead, gN); RB_ALLOC(s->d_expo, gN);
+  RB_ALLOC(s->d_dead, gN); RB_ALLOC(s->d_expo, gN); RB_ALLOC(s->d_group, s->Nloc);
   s->host_plan = getenv("RBSLAM_HOST_PLAN") != nullptr;
+  s->overlap = getenv("RBSLAM_OVERLAP") != nullptr;
   CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned long long)));
   CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_fetch, cudaEventDisableTiming));
@@ -345,19 +364,22 @@ int rb_shard_step(rbslam_ctx *ctx) {
     rs.U = nullptr; rs.seed = ctx->cfg.seed; rs.sweep = 0; rs.t = t;
     size_t smem = sizeof(double) * (size_t)gN;
     smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
-    k_resample<<<1, 1024, smem, ctx->stream>>>(gN, 0, gN, s->g_w, s->g_wc, rs, nullptr, ai, ctx->d_status);
-    ctx->launches += 1;
+    k_resample<<<1, 1024, smem, ctx->stream>>>(gN, 0, -1, s->g_w, s->g_wc, rs, nullptr, ai, ctx->d_status);
+    k_resample_search<<<(gN + 255) / 256, 256, 0, ctx->stream>>>(gN, 0, gN, s->g_wc, rs, nullptr, ai, ctx->d_status);
+    ctx->launches += 2;
+    rb_phase_end(ctx);
+    rb_phase_begin(ctx, RB_PH_INFO);   // reported as the "plan" phase of the sharded filter
     const int o = s->cur, nw = 1 - s->cur;
     if (!s->host_plan) {
       // plan on the device: no host round trip in the step (shard_plan.cuh)
-      PlanArgs pa;
+      PlanArgs pa = {};
       pa.N = gN; pa.world = s->world; pa.rank = s->rank; pa.ai = ai;
       pa.owner_old = s->d_own[o]; pa.lslot_old = s->d_lsl[o]; pa.owner_new = s->d_own[nw]; pa.lslot_new = s->d_lsl[nw];
       pa.n_child = s->d_nchild; pa.keeper = s->d_keeper; pa.unsafe = s->d_unsafe; pa.inv = s->d_inv;
       pa.dead_list = s->d_dead; pa.expo_list = s->d_expo;
       pa.src_slot = ctx->d_src_slot; pa.glob = s->d_glob; pa.listA = ctx->d_listA; pa.listB = ctx->d_listB;
-      pa.fetch = s->d_fetch; pa.counts = ctx->d_counts;
-      k_plan_shard<<<1, 1024, 0, ctx->stream>>>(pa);
+      pa.fetch = s->d_fetch; pa.counts = ctx->d_counts; pa.item_group = s->d_group;
+      CK(launch_plan_shard(pa, ctx->stream));
       ctx->launches += 1;
       s->cur = nw;
       ctx->stream_groups = 2;
@@ -379,7 +401,7 @@ int rb_shard_step(rbslam_ctx *ctx) {
       // exported slab, plus the migrants themselves) runs after the peer barrier.  All local
       // offspring of one ancestor are kept in the same group so that copies still precede the
       // in-place update of their source slab.
-      s->h_src.assign(Nloc, 0); s->h_fetch.clear();
+      s->h_src.assign(Nloc, 0); s->h_fetch.clear(); s->h_group.assign(Nloc, 0);
       for (int q = 0; q < 4; ++q) s->h_lists[q].clear();   // A0, B0, A1, B1
       s->h_nchild.assign(gN, 0); s->h_unsafe.assign(gN, 0); s->h_inv.assign(Nloc, -1);
       for (int i = 0; i < gN; ++i) {
@@ -402,10 +424,11 @@ int rb_shard_step(rbslam_ctx *ctx) {
         if (s->owner[o][a] != s->rank) {          // migrant: fetched into slot j, then updated in place
           s->h_fetch.push_back(j); s->h_fetch.push_back(s->owner[o][a]); s->h_fetch.push_back(s->lslot[o][a]);
           s->h_fetch.push_back(0);
-          s->h_src[j] = j; s->h_lists[3].push_back(j);
+          s->h_src[j] = j; s->h_lists[3].push_back(j); s->h_group[j] = 1;
         } else {
           s->h_src[j] = s->lslot[o][a];
           const int grp = s->h_unsafe[a] ? 1 : 0;
+          s->h_group[j] = grp;
           s->h_lists[2 * grp + (s->h_src[j] == j ? 1 : 0)].push_back(j);
         }
       }
@@ -424,6 +447,7 @@ int rb_shard_step(rbslam_ctx *ctx) {
       }
       CK(cudaMemcpyAsync(ctx->d_counts, counts, sizeof counts, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaMemcpyAsync(s->d_glob, s->h_glob.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(s->d_group, s->h_group.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
       if (nF) CK(cudaMemcpyAsync(s->d_fetch, s->h_fetch.data(), sizeof(int) * 4 * nF, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));   // the host vectors are reused next step
       ctx->h2d += (int64_t)sizeof(int) * (3 * Nloc + 4 * nF);
@@ -444,13 +468,19 @@ int rb_shard_step(rbslam_ctx *ctx) {
     ctx->launches += 1;
     rb_phase_end(ctx);
     // migrants travel on a second stream, concurrently with the "safe" group of the Kalman pass
-    rb_phase_begin(ctx, RB_PH_ANCESTOR);   // reported as the "migration" phase
-    k_peer_fetch<<<dim3(16, std::min(Nloc, 256)), 256, 0, ctx->stream>>>(
+    // migrants travel on a second stream while the families that touch no exported slab
+    // (work group 0) are processed; group 1 waits for the landing + the peer barrier
+    cudaStream_t fs = s->overlap ? ctx->stream2 : ctx->stream;
+    if (s->overlap) {
+      CK(cudaEventRecord(ctx->ev_plan, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_plan, 0));
+    }
+    k_peer_fetch<<<(s->overlap ? 2 : 8) * ctx->num_sms, 256, 0, fs>>>(
         ctx->d_counts + 4, s->d_fetch, s->peers, ctx->cg, ctx->cx, ctx->slab, ctx->ld, M, ctx->d_P,
         ctx->d_G4[ctx->cg], ctx->d_KS4[ctx->cg], ctx->d_xl[ctx->cx]);
     ctx->launches += 1;
-    if ((rc = peer_barrier(ctx))) return rc;   // all remote reads of old slabs are done
-    rb_phase_end(ctx);
+    if (s->overlap) CK(cudaEventRecord(ctx->ev_fetch, ctx->stream2));
+    else if ((rc = peer_barrier(ctx))) return rc;   // default: land everything, then one pass over all families
   } else {
     k_plan_identity<<<(Nloc + 255) / 256, 256, 0, ctx->stream>>>(Nloc, ctx->d_slot[ctx->cs], ctx->d_src_slot,
                                                                 ctx->d_listB, ctx->d_counts);
@@ -465,9 +495,13 @@ int rb_shard_step(rbslam_ctx *ctx) {
   rb_phase_end(ctx);
   rb_phase_begin(ctx, RB_PH_KALMAN);
   ctx->anc_override = ctx->d_src_slot;     // thin arrays are slot-indexed: ancestor index = source slot
-  ctx->stream_groups = 1;
+  ctx->stream_groups = resampled ? 2 : 1;
+  ctx->group_hook = s->overlap ? shard_group_hook : nullptr;
+  ctx->item_group = s->overlap ? s->d_group : nullptr;
   rc = rb_kalman_phase(ctx, ctx->d_y + (size_t)t * d, resampled);
   ctx->anc_override = nullptr;
+  ctx->group_hook = nullptr;
+  ctx->item_group = nullptr;
   ctx->stream_groups = 1;
   ctx->group_off[0][0] = ctx->group_off[0][1] = 0;
   rb_phase_end(ctx);
@@ -570,7 +604,7 @@ extern "C" int rbslam_op_plan_shard(int32_t device, int32_t N, int32_t world, in
   if (cudaMalloc(&buf, total * sizeof(int)) != cudaSuccess) return RBSLAM_ECUDA;
   int *p = buf;
   auto take = [&](size_t n) { int *q = p; p += n; return q; };
-  PlanArgs pa;
+  PlanArgs pa = {};
   pa.N = N; pa.world = world; pa.rank = rank;
   int *d_ai = take(N), *d_oo = take(N), *d_lo = take(N);
   pa.ai = d_ai; pa.owner_old = d_oo; pa.lslot_old = d_lo;
@@ -586,8 +620,8 @@ extern "C" int rbslam_op_plan_shard(int32_t device, int32_t N, int32_t world, in
   cudaMemcpy(d_oo, owner_old, sizeof(int) * N, cudaMemcpyHostToDevice);
   cudaMemcpy(d_lo, lslot_old, sizeof(int) * N, cudaMemcpyHostToDevice);
   cudaMemset(pa.counts, 0, 8 * sizeof(int));
-  k_plan_shard<<<1, 1024>>>(pa);
-  cudaError_t e = cudaDeviceSynchronize();
+  cudaError_t e = launch_plan_shard(pa, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaMemcpy(owner_new, pa.owner_new, sizeof(int) * N, cudaMemcpyDeviceToHost);
   cudaMemcpy(lslot_new, pa.lslot_new, sizeof(int) * N, cudaMemcpyDeviceToHost);
   cudaMemcpy(src_slot, pa.src_slot, sizeof(int) * Nloc, cudaMemcpyDeviceToHost);

@@ -51,6 +51,7 @@ k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__r
     for (int j = threadIdx.x; j < cn; j += blockDim.x) wc[c0 + j] = s_buf[j];
     __syncthreads();
   }
+  if (n_draws < 0) return;                         // scan only: the draws run in k_resample_search
   const double *buf = (N <= chunk) ? s_buf : wc;   // single chunk: search in shared memory
   for (int i = i0 + threadIdx.x; i < i0 + n_draws; i += blockDim.x) {
     int idx;
@@ -72,6 +73,28 @@ k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__r
     }
     ai[i] = idx;
   }
+}
+
+// the draws alone, one thread per draw over the whole grid (large N: the single scanning CTA
+// would otherwise also do N binary searches)
+__global__ void k_resample_search(int N, int i0, int n_draws, const double *__restrict__ wc, RngSrc rng,
+                                  const int *__restrict__ forced, int *__restrict__ ai, DevStatus *status) {
+  const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i0 + n_draws) return;
+  int idx;
+  if (forced != nullptr) {
+    idx = forced[i];
+  } else {
+    const double u = rng.U ? rng.U[i] : philox_uniform(rng.seed, rng.sweep, rng.t, i);
+    int lo = 0, hi = N;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (wc[mid] < u) lo = mid + 1; else hi = mid;
+    }
+    idx = lo;
+    if (idx >= N) { idx = N - 1; atomicAdd(&status->clamp_sample, 1); }
+  }
+  ai[i] = idx;
 }
 
 // ---------------------------------------------------------------------------

@@ -24,8 +24,12 @@ def _problem(rb, m, T):
     return rb.synth.dense_mag_problem(N_T=T, m=m, seed=3, m_sim=300)
 
 
-def _worker(rank, world, port, N, m, T, seed, q):
+def _worker(rank, world, port, N, m, T, seed, q, overlap=False):
     import sys
+    if overlap:   # read by the library when the sharded context is created
+        os.environ["RBSLAM_OVERLAP"] = "1"
+    else:
+        os.environ.pop("RBSLAM_OVERLAP", None)
     for p in (ROOT, PKG):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -53,8 +57,9 @@ def _worker(rank, world, port, N, m, T, seed, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("overlap", [False, True], ids=["barrier-first", "overlap"])
 @pytest.mark.parametrize("world,N,m,T", [(2, 32, 64, 12), (2, 64, 253, 8)])
-def test_sharded_filter_matches_single_gpu_and_oracle(rbslam_lib, world, N, m, T):
+def test_sharded_filter_matches_single_gpu_and_oracle(rbslam_lib, world, N, m, T, overlap):
     rb = rbslam_lib
     from rbslam import _capi
     if _capi.lib().rbslam_device_count() < world:
@@ -65,7 +70,7 @@ def test_sharded_filter_matches_single_gpu_and_oracle(rbslam_lib, world, N, m, T
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = _free_port()
-    procs = [ctxm.Process(target=_worker, args=(r, world, port, N, m, T, seed, q)) for r in range(world)]
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, N, m, T, seed, q, overlap)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -96,11 +101,12 @@ def test_device_planner_equals_host_planner(rbslam_lib, world):
     from rbslam import _capi
     L = _capi.lib()
     rng = np.random.default_rng(world)
-    for N in (64 * world, 1000 * world):
+    # the largest size gives every thread of the 8-CTA planning cluster several particles
+    for N, steps in ((64 * world, 5), (1000 * world, 5), (3000 * world, 2)):
         Nloc = N // world
         owner = (np.arange(N) // Nloc).astype(np.int32)
         lslot = (np.arange(N) % Nloc).astype(np.int32)
-        for step in range(5):
+        for step in range(steps):
             w = rng.random(N) ** (1 + 5 * (step % 3))
             ai = rng.choice(N, size=N, p=w / w.sum()).astype(np.int32)
             ho, hl = np.zeros(N, np.int32), np.zeros(N, np.int32)
