@@ -36,7 +36,7 @@ UNIT = "particle-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--particles", type=int, default=10000, help="N_P per GPU (C4: 10^4)")
@@ -46,7 +46,7 @@ def parse_args():
                     help="N>1: weak = --particles per GPU (default), strong = --particles in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-particles", type=int, default=64)
-    ap.add_argument("--cpu-sample-steps", type=int, default=4)
+    ap.add_argument("--cpu-sample-steps", type=int, default=20)
     return ap.parse_args()
 
 
@@ -62,7 +62,13 @@ def make_problem(m, n_steps):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).
+
+    nvidia-smi takes up to a second to start on an 8-GPU box, longer than a short timed region,
+    so the poller is started before the warm-up and the samples are windowed afterwards:
+    ``mark()`` at the start and ``stop()`` at the end of the timed region.  If the region was
+    shorter than one polling period, the samples taken during the (identical-load) warm-up
+    steps are used and ``window`` says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -71,12 +77,14 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.lines = []
+        self.i_load = 0
+        self.i_timed = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -87,18 +95,18 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+    def mark_load(self):
+        """the GPU is under the benchmark's load from here on (warm-up steps)"""
+        self.i_load = len(self.lines)
+
+    def mark(self):
+        """start of the timed region"""
+        self.i_timed = len(self.lines)
+
+    def _parse(self, lines):
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -110,9 +118,25 @@ class ClockSampler:
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+        return sm, smax, reasons
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        i_end = len(self.lines)          # the GPU has just gone idle: later samples do not count
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        window = "timed"
+        sm, smax, reasons = self._parse(self.lines[self.i_timed:i_end])
+        if not sm:
+            window = "warmup+timed"
+            sm, smax, reasons = self._parse(self.lines[self.i_load:i_end])
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(smax)) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peak():
@@ -229,14 +253,17 @@ def run_cuda(args):
     n_loc = gN // world
     M, d = ctx.M, ctx.d
     # ---- device-resident measurement ------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     ctx.filter_begin(*fargs, pr["dt"])
+    ctx.sync()
+    sampler.mark_load()
     for _ in range(1 + W):
         ctx.filter_step()
     ctx.sync()
     c0 = ctx.counters()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     ctx.phase_timing(True)
     ctx.event_record(0)
     for _ in range(K):
@@ -304,7 +331,10 @@ def run_cuda(args):
                          "kernel": "Kalman update phase (gather + log-weight + rank-%d downdate)" % d,
                          "algorithmic_bytes_per_launch": bytes_alg_step,
                          "kernel_ms_per_step": kal_ms, "peak_source": peak_src,
-                         "phases_ms_per_step": {k: v / K for k, v in phases.items() if v > 0}},
+                         # the sharded step times its migration planner in the slot the
+                         # single-GPU information-form filter uses for its own phase
+                         "phases_ms_per_step": {("plan" if (k == "info" and world > 1) else k): v / K
+                                                for k, v in phases.items() if v > 0}},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(pr, m, args.cpu_sample_particles,

@@ -203,6 +203,12 @@ RBSLAM_API int rbslam_op_propagate(rbslam_ctx *ctx, int32_t N, const double *xn_
    sparse family xl [M x N] is required and yhat [d x N] is also returned */
 RBSLAM_API int rbslam_op_meas_jacobian(rbslam_ctx *ctx, int32_t N, const double *xn, const double *xl,
                             double *dy, double *yhat);
+/* JacobianPhi3D (tools/JacobianPhi3D.m:1, called from run_dense3D_magfield.m:292-294):
+   Hessians of the context's m basis functions at N points.  x [3 x N]; lo = [xl yl zl],
+   hi = [xu yu zu] (the reference's six scalar bounds); out J [3 x 3 x m x N].
+   Dense-mag (3-D basis) contexts only, RBSLAM_EMODEL otherwise. */
+RBSLAM_API int rbslam_op_jacobian_phi3d(rbslam_ctx *ctx, int32_t N, const double *x, const double *lo,
+                             const double *hi, double *J);
 /* fused log-weight + Kalman update (src/particleFilter.m:126-151,164-204):
    in/out xl [M x N], P [M x M x N]; H [N x d x M] MATLAB layout (NULL = evaluate the
    model's measModel at xn); out logw [N] */

@@ -27,7 +27,7 @@ Indices are 0-based here; the reference is 1-based.
 
 from .tools import (sample, expq, qLeft, quat2rmat, quat2rmat_batch, qInv, logq,
                     mcross, chol_lower, domain_cartesian_dx, eigenfun,
-                    eigenfun_dx, eigenval)
+                    eigenfun_dx, eigenval, JacobianPhi3D)
 from .models import DenseMag3D, DenseRadio2D, SparseVisual2D
 from .particle_filter import particleFilter
 from .particle_smoother import particleSmoother

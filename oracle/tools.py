@@ -226,3 +226,38 @@ def eigenfun_dx(NN, x, di, L):
         else:
             v = v * 1.0 / np.sqrt(L[j]) * np.sin(arg)
     return v
+
+
+def JacobianPhi3D(x, N_m, xl, xu, yl, yu, zl, zu, Indices):
+    """J [3 x 3 x N_m x N]: Hessian of each basis function at each point
+    (tools/JacobianPhi3D.m:29-64; called from run_dense3D_magfield.m:292-294).
+
+    x is 3 x N.  Products are evaluated left to right as MATLAB does.
+    """
+    j = np.asarray(Indices, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64).reshape(3, -1)
+    N = x.shape[1]
+    J = np.zeros((3, 3, N_m, N))
+    a = np.array([xl, yl, zl], dtype=np.float64)          # :38
+    b = np.array([xu, yu, zu], dtype=np.float64)          # :39
+    f = np.zeros((N_m, 3))
+    for d in range(3):                                    # :41-44
+        f[:, d] = (np.pi * j[:, d]) / (b[d] - a[d])
+    for i in range(N):                                    # :47
+        s = np.zeros((N_m, 3))
+        c = np.zeros((N_m, 3))
+        for d in range(3):                                # :51-56
+            core = np.pi * j[:, d] * (x[d, i] - a[d]) / (b[d] - a[d])
+            mult = 1.0 / np.sqrt(0.5 * (b[d] - a[d]))
+            s[:, d] = np.sin(core) * mult
+            c[:, d] = np.cos(core) * mult
+        J[0, 0, :, i] = -f[:, 0] ** 2 * s[:, 0] * s[:, 1] * s[:, 2]       # :58-66
+        J[0, 1, :, i] = f[:, 0] * f[:, 1] * c[:, 0] * c[:, 1] * s[:, 2]
+        J[0, 2, :, i] = f[:, 0] * f[:, 2] * c[:, 0] * s[:, 1] * c[:, 2]
+        J[1, 0, :, i] = f[:, 1] * f[:, 0] * c[:, 0] * c[:, 1] * s[:, 2]
+        J[1, 1, :, i] = -f[:, 1] ** 2 * s[:, 0] * s[:, 1] * s[:, 2]
+        J[1, 2, :, i] = f[:, 1] * f[:, 2] * s[:, 0] * c[:, 1] * c[:, 2]
+        J[2, 0, :, i] = f[:, 2] * f[:, 0] * c[:, 0] * s[:, 1] * c[:, 2]
+        J[2, 1, :, i] = f[:, 2] * f[:, 1] * s[:, 0] * c[:, 1] * c[:, 2]
+        J[2, 2, :, i] = -f[:, 2] ** 2 * s[:, 0] * s[:, 1] * s[:, 2]
+    return J

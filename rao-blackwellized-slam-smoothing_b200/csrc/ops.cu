@@ -141,6 +141,24 @@ extern "C" int rbslam_op_meas_jacobian(rbslam_ctx *ctx, int32_t N, const double 
   return RBSLAM_OK;
 }
 
+extern "C" int rbslam_op_jacobian_phi3d(rbslam_ctx *ctx, int32_t N, const double *x, const double *lo,
+                                        const double *hi, double *J) {
+  if (!ctx || !x || !lo || !hi || !J || N < 1) return RBSLAM_EARG;
+  if (ctx->mc.family != FAM_DENSE_MAG3D) return ctx->fail(RBSLAM_EMODEL, "JacobianPhi3D needs the 3-D dense basis");
+  for (int k = 0; k < 3; ++k)
+    if (!(hi[k] > lo[k])) return ctx->fail(RBSLAM_EARG, "JacobianPhi3D: upper bound must exceed lower bound");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int m = ctx->mc.m;
+  TMP_ALLOC(d_x, double, (size_t)3 * N);
+  TMP_ALLOC(d_J, double, (size_t)9 * m * N);
+  int rc;
+  if ((rc = rb_h2d(ctx, d_x, x, sizeof(double) * 3 * N))) return rc;
+  k_jacobian_phi3d<<<N, 128, 0, ctx->stream>>>(ctx->mc, N, d_x, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], d_J);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return rb_d2h(ctx, J, d_J, sizeof(double) * 9 * (size_t)m * N);
+}
+
 __global__ void k_op_unpack(int M, int ld, size_t slab, double *__restrict__ P, const double *__restrict__ in) {
   const int c = blockIdx.x, i = blockIdx.y;
   double *dst = P + (size_t)i * slab + (size_t)c * ld;

@@ -447,4 +447,56 @@ k_normalize(int N, int n, const double *__restrict__ logw, double *__restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// K2b  JacobianPhi3D (tools/JacobianPhi3D.m:29-64): Hessian of every basis function at
+// every point, J [3 x 3 x m x N].  Same separable structure as K2: per point and axis one
+// sin and one cos per distinct index (<= 3*RB_MAXTAB sincos calls instead of 6*m trig).
+//   f_d  = pi*j_d/(b_d-a_d)                          (:41-44)
+//   s_d  = sin(pi*j_d*(x_d-a_d)/(b_d-a_d)) * mult_d  (:51-56), mult_d = 1/sqrt((b_d-a_d)/2)
+//   J_dd = -f_d^2 s1 s2 s3;  J_de = f_d f_e * (cos on axes d,e; sin on the third)  (:58-66)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_jacobian_phi3d(ModelConsts mc, int N, const double *__restrict__ x, double a0, double a1, double a2,
+                 double b0, double b1, double b2, double *__restrict__ J) {
+  const int i = blockIdx.x;
+  if (i >= N) return;
+  __shared__ double s_sin[3][RB_MAXTAB], s_cos[3][RB_MAXTAB];
+  const double a[3] = {a0, a1, a2}, b[3] = {b0, b1, b2};
+  for (int idx = threadIdx.x; idx < 3 * RB_MAXTAB; idx += blockDim.x) {
+    const int dd = idx / RB_MAXTAB, nn = idx % RB_MAXTAB;
+    if (nn >= 1 && nn <= mc.maxn[dd]) {
+      const double core = (RB_PI * (double)nn) * (x[dd + 3 * (size_t)i] - a[dd]) / (b[dd] - a[dd]);
+      const double mult = 1.0 / sqrt(0.5 * (b[dd] - a[dd]));
+      double sv, cv;
+      sincos(core, &sv, &cv);
+      s_sin[dd][nn] = sv * mult;
+      s_cos[dd][nn] = cv * mult;
+    }
+  }
+  __syncthreads();
+  for (int bidx = threadIdx.x; bidx < mc.m; bidx += blockDim.x) {
+    double f[3], sn[3], cs[3];
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+      const int nn = mc.NN[bidx + dd * mc.m];
+      f[dd] = (RB_PI * (double)nn) / (b[dd] - a[dd]);
+      sn[dd] = s_sin[dd][nn];
+      cs[dd] = s_cos[dd][nn];
+    }
+    double *o = J + 9 * ((size_t)bidx + (size_t)mc.m * i);   // J(r,c,bidx,i) at o[r + 3c]
+    const double j12 = f[0] * f[1] * cs[0] * cs[1] * sn[2];
+    const double j13 = f[0] * f[2] * cs[0] * sn[1] * cs[2];
+    const double j23 = f[1] * f[2] * sn[0] * cs[1] * cs[2];
+    o[0] = -(f[0] * f[0]) * sn[0] * sn[1] * sn[2];
+    o[1] = f[1] * f[0] * cs[0] * cs[1] * sn[2];
+    o[2] = f[2] * f[0] * cs[0] * sn[1] * cs[2];
+    o[3] = j12;
+    o[4] = -(f[1] * f[1]) * sn[0] * sn[1] * sn[2];
+    o[5] = f[2] * f[1] * sn[0] * cs[1] * cs[2];
+    o[6] = j13;
+    o[7] = j23;
+    o[8] = -(f[2] * f[2]) * sn[0] * sn[1] * sn[2];
+  }
+}
+
 }  // namespace rb

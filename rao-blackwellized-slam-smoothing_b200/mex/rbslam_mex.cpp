@@ -4,6 +4,7 @@
 //       rbslam_mex('filter',   model, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P, dt, opts)
 //   [XNK,XLK,PK] = ...
 //       rbslam_mex('smoother', model, form, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P, N_K, dt, opts)
+//   J = rbslam_mex('jacobianphi3d', x, N_m, xl, xu, yl, yu, zl, zu, Indices)      (tools/JacobianPhi3D.m:1)
 //
 // `model` is the descriptor struct made by matlab/rbslam_model.m (family, NN, L, camera);
 // `opts` carries device, rng ('philox' | 'compat'), seed and, in compat mode, the
@@ -171,6 +172,39 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     plhs[0] = XNK;
     if (nlhs > 1) plhs[1] = XLK;
     if (nlhs > 2) plhs[2] = PK;
+  } else if (c == "jacobianphi3d") {
+    if (nrhs != 10) mexErrMsgIdAndTxt("rbslam:badArgument", "jacobianphi3d: 9 arguments expected");
+    const int Np = (int)mxGetN(prhs[1]), Nm = (int)mxGetScalar(prhs[2]);
+    const mxArray *Ind = prhs[9];
+    if (mxGetM(prhs[1]) != 3 || (int)mxGetM(Ind) < Nm || mxGetN(Ind) != 3 || Nm < 1 || Np < 1)
+      mexErrMsgIdAndTxt("rbslam:badArgument", "jacobianphi3d: x must be 3 x N and Indices N_m x 3");
+    const double lo[3] = {mxGetScalar(prhs[3]), mxGetScalar(prhs[5]), mxGetScalar(prhs[7])};
+    const double hi[3] = {mxGetScalar(prhs[4]), mxGetScalar(prhs[6]), mxGetScalar(prhs[8])};
+    const double Lh[3] = {0.5 * (hi[0] - lo[0]), 0.5 * (hi[1] - lo[1]), 0.5 * (hi[2] - lo[2])};
+    const size_t rows = mxGetM(Ind);
+    const double *ind = mxGetDoubles(Ind);
+    std::vector<int32_t> nn((size_t)3 * Nm);
+    for (int dcol = 0; dcol < 3; ++dcol)
+      for (int b = 0; b < Nm; ++b) nn[b + (size_t)Nm * dcol] = (int32_t)ind[b + rows * dcol];
+    rbslam_config cfg;   // a private one-particle context: the filter's context is left alone
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = (int32_t)sizeof cfg;
+    cfg.model = RBSLAM_MODEL_DENSE_MAG3D;
+    cfg.N = 1; cfg.T = 1; cfg.m_basis = Nm; cfg.NN = nn.data(); cfg.L = Lh;
+    cfg.rng_mode = RBSLAM_RNG_PHILOX; cfg.world = 1;
+    rbslam_ctx *tmp = nullptr;
+    int rc = rbslam_create(&tmp, &cfg);
+    if (rc) fail(nullptr, rc);
+    const mwSize d4[4] = {3, 3, (mwSize)Nm, (mwSize)Np};
+    mxArray *J = mxCreateNumericArray(4, d4, mxDOUBLE_CLASS, mxREAL);
+    rc = rbslam_op_jacobian_phi3d(tmp, Np, mxGetDoubles(prhs[1]), lo, hi, mxGetDoubles(J));
+    if (rc) {
+      const std::string msg = rbslam_last_error(tmp);
+      rbslam_destroy(tmp);
+      mexErrMsgIdAndTxt(rc == 4 ? "rbslam:unsupportedModel" : "rbslam:cuda", "%s", msg.c_str());
+    }
+    rbslam_destroy(tmp);
+    plhs[0] = J;
   } else if (c == "release") {
     at_exit();
   } else {

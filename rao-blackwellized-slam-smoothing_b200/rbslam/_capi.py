@@ -93,6 +93,7 @@ SYMBOLS = {
                                       c_double_p, c_double_p, c_double_p]),
     "rbslam_op_meas_jacobian": (C.c_int, [_ctx, C.c_int32, c_double_p, c_double_p, c_double_p,
                                           c_double_p]),
+    "rbslam_op_jacobian_phi3d": (C.c_int, [_ctx, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]),
     "rbslam_op_kalman_update": (C.c_int, [_ctx, C.c_int32, c_double_p, c_double_p, c_double_p,
                                           c_double_p, C.c_double, c_double_p, c_double_p, c_double_p]),
     "rbslam_op_dyn_logweight": (C.c_int, [_ctx, C.c_int32, c_double_p, c_double_p, c_double_p,

@@ -346,6 +346,20 @@ class Context:
                                                    _capi.dptr(dy), _capi.dptr(yhat)))
         return dy, yhat
 
+    def op_jacobian_phi3d(self, x, xl, xu, yl, yu, zl, zu):
+        """JacobianPhi3D(x, N_m, xl, xu, yl, yu, zl, zu, Indices) (tools/JacobianPhi3D.m:1) with
+        N_m / Indices taken from the context's basis: x [3 x N] -> J [3 x 3 x m x N]."""
+        x = _capi.fcol(np.atleast_2d(x))
+        if x.shape[0] != 3:
+            raise ValueError("x must be 3 x N")
+        N = x.shape[1]
+        lo = np.array([xl, yl, zl], dtype=np.float64)
+        hi = np.array([xu, yu, zu], dtype=np.float64)
+        J = np.zeros((3, 3, self.M - 3, N), order="F")
+        self._ck(self._lib.rbslam_op_jacobian_phi3d(self._h, N, _capi.dptr(x), _capi.dptr(lo), _capi.dptr(hi),
+                                                    _capi.dptr(J)))
+        return J
+
     def op_kalman_update(self, xl, P, y_t, R, jitter=1e-3, H=None, xn=None):
         """xl [M x N], P [M x M x N] (MATLAB layout), H [N x d x M]; returns updated copies."""
         xl = np.array(xl, dtype=np.float64, order="F")

@@ -112,6 +112,28 @@ def test_meas_jacobian(rbslam_lib, fam):
             assert_close_norm(dy, ref, 1e-11, "dy")
 
 
+@pytest.mark.parametrize("m", [64, 512])
+def test_jacobian_phi3d(rbslam_lib, m):
+    """k_jacobian_phi3d against the oracle's tools/JacobianPhi3D.m restatement, on a centred and
+    on an off-centre domain (the reference takes the six bounds as separate scalars)."""
+    rb = rbslam_lib
+    pr, om, gm = _problem(rb, "mag", m=m)
+    rng = np.random.default_rng(6)
+    N = 23
+    L = np.asarray(pr["L"], dtype=np.float64)
+    with rb.Context(gm, 4, 4) as ctx:
+        for lo, hi in ((-L, L), (-L + np.array([0.3, -0.2, 0.1]), L + np.array([0.5, 0.4, 0.25]))):
+            x = lo[:, None] + (hi - lo)[:, None] * rng.random((3, N))
+            J = ctx.op_jacobian_phi3d(x, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])
+            ref = oracle.JacobianPhi3D(x, m, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], pr["NN"])
+            assert J.shape == ref.shape == (3, 3, m, N)
+            assert_close_norm(J, ref, 1e-12, "JacobianPhi3D")
+    prr, _, gmr = _problem(rb, "radio")
+    with rb.Context(gmr, 4, 4) as ctx:     # 2-D basis: refused, not silently wrong
+        with pytest.raises(rb.UnsupportedModelError):
+            ctx.op_jacobian_phi3d(np.zeros((3, 1)), -1, 1, -1, 1, -1, 1)
+
+
 def _rand_spd(rng, M, scale=1.0):
     A = rng.standard_normal((M, M))
     return scale * (A @ A.T / M + 0.5 * np.eye(M))

@@ -97,6 +97,25 @@ def test_eigenfun_dx_is_gradient_and_basis_is_orthonormal():
     assert_close_norm(Phi.T @ (Phi * W[:, None]), np.eye(12), 1e-3)
 
 
+def test_jacobian_phi3d_is_hessian_of_the_basis():
+    """tools/JacobianPhi3D.m against central differences of eigenfun_dx (centred domain:
+    a = -L, b = +L, so both files describe the same basis), and symmetric in (r, c)."""
+    LL = np.array([[-3.0, -2.0, -1.0], [3.0, 2.0, 1.0]])
+    L, NN = tools.domain_cartesian_dx(20, 3, LL)
+    rng = np.random.default_rng(11)
+    x = (rng.random((4, 3)) - 0.5) * 1.6 * L
+    J = tools.JacobianPhi3D(x.T, 20, LL[0, 0], LL[1, 0], LL[0, 1], LL[1, 1], LL[0, 2], LL[1, 2], NN)
+    assert J.shape == (3, 3, 20, 4)
+    assert_close_norm(J, J.transpose(1, 0, 2, 3), 1e-15)
+    h = 1e-6
+    for c in range(3):
+        e = np.zeros(3)
+        e[c] = h
+        for r in range(3):
+            fd = (tools.eigenfun_dx(NN, x + e, r, L) - tools.eigenfun_dx(NN, x - e, r, L)) / (2 * h)
+            assert_close_norm(J[r, c].T, fd, 1e-7, "J[%d,%d]" % (r, c))
+
+
 # ---------------------------------------------------------------- Kalman update / log-weight
 def _rand_spd(rng, M):
     A = rng.standard_normal((M, M))
