@@ -86,21 +86,23 @@ __global__ void k_final_cov(int N, int M, int ld, size_t slab, const double *__r
                             const double *__restrict__ w, const int *__restrict__ iw_max,
                             const double *__restrict__ means, double *__restrict__ Pmax,
                             double *__restrict__ Pmean, const double *__restrict__ G4,
-                            const double *__restrict__ KS4) {
+                            const double *__restrict__ KS4, int sym) {
   const int c = blockIdx.x;
   const int im = *iw_max, il = N - 1;
-  const double *Pm = P + (size_t)slot[im] * slab + (size_t)c * ld;
-  const double *Pl = P + (size_t)slot[il] * slab + (size_t)c * ld;
+  const double *Pm = P + (size_t)slot[im] * slab;
+  const double *Pl = P + (size_t)slot[il] * slab;
   const double *xll = xl + (size_t)il * M;
   const double *xmean = means + M;
   const double wl = w[il];
   const double dc = xmean[c] - xll[c];
   for (int r = threadIdx.x; r < M; r += blockDim.x) {
-    double pm = Pm[r], pl = Pl[r];
+    // sym: only the lower triangle of a slab is valid -> element (r,c) lives at (max, min)
+    const int rr = sym ? max(r, c) : r, cc = sym ? min(r, c) : c;
+    double pm = Pm[rr + (size_t)cc * ld], pl = Pl[rr + (size_t)cc * ld];
     if (G4) {   // deferred downdate of the streaming path: P(r,c) -= KS(r,b) G(c,b)
       for (int b = 0; b < 4; ++b) {
-        pm = fma(-KS4[((size_t)im * ld + r) * 4 + b], G4[((size_t)im * ld + c) * 4 + b], pm);
-        pl = fma(-KS4[((size_t)il * ld + r) * 4 + b], G4[((size_t)il * ld + c) * 4 + b], pl);
+        pm = fma(-KS4[((size_t)im * ld + rr) * 4 + b], G4[((size_t)im * ld + cc) * 4 + b], pm);
+        pl = fma(-KS4[((size_t)il * ld + rr) * 4 + b], G4[((size_t)il * ld + cc) * 4 + b], pl);
       }
     }
     Pmax[r + (size_t)c * M] = pm;
@@ -110,11 +112,12 @@ __global__ void k_final_cov(int N, int M, int ld, size_t slab, const double *__r
 
 // pack slabs into dense [M x M x cnt] logical order (read_particles)
 __global__ void k_pack_slabs(int M, int ld, size_t slab, const double *__restrict__ P,
-                             const int *__restrict__ slot, int i0, double *__restrict__ out) {
+                             const int *__restrict__ slot, int i0, double *__restrict__ out, int sym) {
   const int c = blockIdx.x, i = blockIdx.y;
-  const double *src = P + (size_t)slot[i0 + i] * slab + (size_t)c * ld;
+  const double *src = P + (size_t)slot[i0 + i] * slab;
   double *dst = out + ((size_t)i * M + c) * M;
-  for (int r = threadIdx.x; r < M; r += blockDim.x) dst[r] = src[r];
+  for (int r = threadIdx.x; r < M; r += blockDim.x)   // sym: mirror the valid lower triangle
+    dst[r] = sym ? src[max(r, c) + (size_t)min(r, c) * ld] : src[r + (size_t)c * ld];
 }
 __global__ void k_unpack_slabs(int M, int ld, size_t slab, double *__restrict__ P,
                                const int *__restrict__ slot, int i0, const double *__restrict__ in) {
@@ -258,7 +261,15 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   const bool can_stream = d <= 4 && ctx->ld <= 4 * 2 * RB_STREAM_THREADS;
   if (cfg->information_form && !can_stream)
     return ctx->fail(RBSLAM_EARG, "information form needs d<=3 and M<=1536");
-  if (small && cfg->kalman_variant != 2 && cfg->kalman_variant != 3 && !cfg->information_form) ctx->kpath = 0;
+  if (cfg->kalman_variant == 4) {   // symmetric (lower-triangle) streaming pass, opt-in, filter only
+    if (!can_stream || d > 3 || ctx->ld > 4 * RB_SYM_THREADS || cfg->information_form)
+      return ctx->fail(RBSLAM_EARG, "kalman_variant 4 needs d<=3, M<=1152 and the covariance form");
+    if (getenv("RBSLAM_NO_FAM")) return ctx->fail(RBSLAM_EARG, "kalman_variant 4 is a family kernel (unset RBSLAM_NO_FAM)");
+    ctx->kpath = 1;
+    ctx->sym = true;
+    if (const char *e = getenv("RBSLAM_SYM_FLAGS")) ctx->sym_flags = atoi(e);
+    if (const char *e = getenv("RBSLAM_SYM_CFG")) { int kc = 8, st = 2; if (sscanf(e, "%d,%d", &kc, &st) == 2) ctx->sym_cfg = kc * 100 + st; }
+  } else if (small && cfg->kalman_variant != 2 && cfg->kalman_variant != 3 && !cfg->information_form) ctx->kpath = 0;
   else if (can_stream && cfg->kalman_variant != 3) ctx->kpath = 1;
   else if (d <= 4 && ctx->ld <= 2048) ctx->kpath = 2;
   else return ctx->fail(RBSLAM_EARG, "unsupported size: d>4 needs M*M*8 B to fit shared memory; "
@@ -316,7 +327,8 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
       RB_ALLOC(ctx->d_G4[b], (size_t)N * ctx->ld * 4);
       RB_ALLOC(ctx->d_KS4[b], (size_t)N * ctx->ld * 4);
     }
-    RB_ALLOC(ctx->d_PHp, (size_t)N * ctx->nsplit * ctx->ld * 4);
+    // the symmetric kernel keeps row-side and column-side partial sums in separate slots
+    RB_ALLOC(ctx->d_PHp, (size_t)N * ctx->nsplit * (ctx->sym ? 2 : 1) * ctx->ld * 4);
     RB_ALLOC(ctx->d_fam, (size_t)17 * N + 8);   // + counters: n_fb, n_fa, work counters [2]
     ctx->use_fam = getenv("RBSLAM_NO_FAM") == nullptr;
   }
@@ -635,11 +647,15 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
     fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
     fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
     fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
+    fb.work_ctr = cnts + 2;
+    fb.cb = RB_CB; fb.kf = RB_KF;
     auto fkern = k_stream_fam<D, R2, KC, S, RB_CB>;
     const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 4 * KC * (1 + RB_CB));
     static bool fattr_done = false;
     if (!fattr_done) {
       CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
+      // same carve-out as the kernels of the sharded step that may share an SM with it (sharded.cu)
+      CK(cudaFuncSetAttribute(fkern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       fattr_done = true;
     }
     if (fsmem > ctx->smem_optin - 1024) return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
@@ -652,7 +668,6 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
       }
       fb.item_group = ngrp > 1 ? ctx->item_group : nullptr;
       fb.group = grp;
-      CK(cudaMemsetAsync(cnts + 2, 0, 2 * sizeof(int), ctx->stream));   // dynamic work counters
       k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
       ctx->launches += 1;
       for (int phase = 0; phase < 2; ++phase) {
@@ -721,6 +736,96 @@ static int launch_stream(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   }
 }
 
+// symmetric streaming path (kalman_variant 4): lower triangle only, k_stream_fam_sym
+template <int D, int R2, int KC, int S>
+static int launch_sym_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  constexpr int CB = RB_SYM_CB;
+  const int N = ctx->N, ld = ctx->ld;
+  StreamArgs sa;
+  sa.hints = ctx->sym_flags; sa.gk_by_particle = 0;
+  sa.M = ctx->M; sa.ld = ld; sa.cw = ctx->cw; sa.nsplit = ctx->nsplit; sa.slab = ctx->slab;
+  sa.P = ctx->d_P; sa.src_slot = a.src_slot; sa.dst_slot = a.dst_slot; sa.anc = a.ai;
+  sa.G4prev = ctx->d_G4[ctx->cg]; sa.KS4prev = ctx->d_KS4[ctx->cg]; sa.H4 = a.H; sa.PHp = ctx->d_PHp;
+  int *fm = ctx->d_fam;
+  FamBuildArgs fb;
+  fb.n_items = N; fb.n_slabs = N; fb.n_items_dev = nullptr;
+  fb.src_slot = a.src_slot; fb.dst_slot = a.dst_slot; fb.anc = a.ai;
+  fb.s_cnt = fm; fb.s_keeper = fm + N; fb.s_cursor = fm + 2 * (size_t)N; fb.s_first = fm + 3 * (size_t)N;
+  fb.s_fid = fm + 4 * (size_t)N; fb.s_xoff = fm + 5 * (size_t)N; fb.s_xfam = fm + 6 * (size_t)N;
+  int *lb = fm + 7 * (size_t)N, *la = fm + 12 * (size_t)N, *cnts = fm + 17 * (size_t)N;
+  fb.fb_src = lb; fb.fb_anc = lb + N; fb.fb_first = lb + 2 * (size_t)N; fb.fb_cnt = lb + 3 * (size_t)N;
+  fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
+  fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
+  fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
+  fb.work_ctr = cnts + 2;
+  fb.cb = CB; fb.kf = 2 * CB;
+  auto fkern = k_stream_fam_sym<D, R2, KC, S, CB>;
+  const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 4 * KC * (1 + CB));
+  static bool fattr_done = false;
+  if (!fattr_done) {
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, fkern));
+    CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(ctx->smem_optin - fa.sharedSizeBytes)));
+    fattr_done = true;
+  }
+  {
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, fkern));
+    if (fsmem + fa.sharedSizeBytes > ctx->smem_optin)
+      return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
+  }
+  const int fgrid = std::min(N * ctx->nsplit, ctx->num_sms);
+  const int ngrp = ctx->item_group ? ctx->stream_groups : 1;
+  for (int grp = 0; grp < ngrp; ++grp) {
+    if (grp > 0 && ctx->group_hook) {
+      int rch = ctx->group_hook(ctx, grp);
+      if (rch) return rch;
+    }
+    fb.item_group = ngrp > 1 ? ctx->item_group : nullptr;
+    fb.group = grp;
+    k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
+    ctx->launches += 1;
+    for (int phase = 0; phase < 2; ++phase) {
+      if (phase == 0 && !resampled) continue;
+      FamLists fl;
+      const int *base = phase == 0 ? la : lb;
+      fl.n_fam = cnts + (phase == 0 ? 1 : 0);
+      fl.work_counter = cnts + 2 + phase;
+      fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
+      fl.child = base + 4 * (size_t)N;
+      fkern<<<fgrid, RB_SYM_THREADS, fsmem, ctx->stream>>>(sa, fl);
+      ctx->launches += 1;
+    }
+  }
+  Innov4Args ia;
+  ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = 2 * ctx->nsplit; ia.PHp = ctx->d_PHp; ia.H4 = a.H;
+  ia.xl_old = a.xl_old; ia.anc = a.ai; ia.xl_new = a.xl_new;
+  ia.G4new = ctx->d_G4[1 - ctx->cg]; ia.KS4new = ctx->d_KS4[1 - ctx->cg];
+  ia.y_t = a.y_t; ia.R = a.R; ia.jitter = a.jitter; ia.logw = a.logw; ia.status = a.status; ia.t = a.t;
+  k_innov4<D><<<N, 128, sizeof(double) * 4 * ld, ctx->stream>>>(ia);
+  ctx->launches += 1;
+  ctx->cg ^= 1;
+  ctx->pending = true;
+  return RBSLAM_OK;
+}
+template <int D, int R2>
+static int launch_sym_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  if (D == 3) {   // tuning knob RBSLAM_SYM_CFG="KC,S"
+    switch (ctx->sym_cfg) {
+      case 404: return launch_sym_cfg<D, R2, 4, 4>(ctx, a, resampled);
+      case 406: return launch_sym_cfg<D, R2, 4, 6>(ctx, a, resampled);
+      case 803: return launch_sym_cfg<D, R2, 8, 3>(ctx, a, resampled);
+      default: break;
+    }
+  }
+  return launch_sym_cfg<D, R2, 8, 2>(ctx, a, resampled);
+}
+template <int D>
+static int launch_sym(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  return ctx->ld / 2 <= RB_SYM_THREADS ? launch_sym_r<D, 1>(ctx, a, resampled) : launch_sym_r<D, 2>(ctx, a, resampled);
+}
+
 // apply the deferred downdate to every slab (before the state is read out as a whole)
 int rb_flush_pending(rbslam_ctx *ctx) {
   if (ctx->kpath != 1 || !ctx->pending) return RBSLAM_OK;
@@ -770,6 +875,14 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled) {
                                                        ctx->d_counts + phase);
       ctx->launches += 1;
     }
+  } else if (ctx->kpath == 1 && ctx->sym) {
+    int rc;
+    switch (d) {
+      case 1: rc = launch_sym<1>(ctx, a, resampled); break;
+      case 2: rc = launch_sym<2>(ctx, a, resampled); break;
+      default: rc = launch_sym<3>(ctx, a, resampled); break;
+    }
+    if (rc) return rc;
   } else if (ctx->kpath == 1) {
     int rc;
     switch (d) {
@@ -953,7 +1066,8 @@ extern "C" int rbslam_filter_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
     k_final_cov<<<M, 128, 0, ctx->stream>>>(N, M, ctx->ld, ctx->slab, ctx->d_P, ctx->d_slot[ctx->cs], xl,
                                             ctx->d_w, iw, means, Pmax, Pmean,
                                             (ctx->kpath == 1 && ctx->pending) ? ctx->d_G4[ctx->cg] : nullptr,
-                                            (ctx->kpath == 1 && ctx->pending) ? ctx->d_KS4[ctx->cg] : nullptr);
+                                            (ctx->kpath == 1 && ctx->pending) ? ctx->d_KS4[ctx->cg] : nullptr,
+                                            ctx->sym ? 1 : 0);
     ctx->launches += 1;
   }
   CK(cudaGetLastError());
@@ -1027,7 +1141,8 @@ int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host) {
   int rc = RBSLAM_OK;
   for (int i0 = 0; i0 < N && !rc; i0 += chunk) {
     const int cnt = std::min(chunk, N - i0);
-    k_pack_slabs<<<dim3(M, cnt), 128, 0, ctx->stream>>>(M, ctx->ld, ctx->slab, slabs, ctx->d_slot[ctx->cs], i0, tmp);
+    k_pack_slabs<<<dim3(M, cnt), 128, 0, ctx->stream>>>(M, ctx->ld, ctx->slab, slabs, ctx->d_slot[ctx->cs], i0, tmp,
+                                                        (ctx->sym && slabs == ctx->d_P) ? 1 : 0);
     ctx->launches += 1;
     rc = rb_d2h(ctx, host + (size_t)i0 * per, tmp, per * cnt * 8);
   }

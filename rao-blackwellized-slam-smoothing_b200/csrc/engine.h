@@ -42,6 +42,9 @@ struct rbslam_ctx {
   // sibling fusion (family_kernels.cuh): scratch [7][N], main/surplus family lists [2][5][N], counters
   int *d_fam = nullptr;
   bool use_fam = true;
+  bool sym = false;          // kalman_variant 4: only the lower triangle of every slab is streamed / valid
+  int sym_flags = 0;         // RBSLAM_SYM_FLAGS: 2 = copy whole columns (diagnostic: full traffic, triangle arithmetic)
+  int sym_cfg = 802;         // RBSLAM_SYM_CFG="KC,S"
   const int *item_group = nullptr;   // sharded engine: work group of each local item (see stream_groups)
   int stream_cfg = 802, stream_ctas_per_sm = 0, stream_hints = 0;   // tuning knobs (env)
   size_t hs_p = 0; int hs_a = 0, hs_c = 1;   // layout of d_H: H_i(a,c) at i*hs_p + a*hs_a + c*hs_c

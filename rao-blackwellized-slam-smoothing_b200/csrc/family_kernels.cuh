@@ -45,6 +45,8 @@ struct FamBuildArgs {
   // main families (launch 2) and surplus families (launch 1)
   int *fb_src, *fb_anc, *fb_first, *fb_cnt, *fb_child, *n_fb;
   int *fa_src, *fa_anc, *fa_first, *fa_cnt, *fa_child, *n_fa;
+  int *work_ctr;            // [2] dynamic work counters of the two k_stream_fam launches, zeroed here
+  int cb, kf;               // siblings per pass / per main family (RB_CB, RB_KF; 2, 4 for the symmetric kernel)
 };
 
 __global__ void __launch_bounds__(1024) k_build_families(FamBuildArgs p) {
@@ -65,27 +67,27 @@ __global__ void __launch_bounds__(1024) k_build_families(FamBuildArgs p) {
   for (int s = b; s < e; ++s) {
     const int c = p.s_cnt[s];
     if (!c) continue;
-    const int x = max(0, c - RB_KF);
-    v[0] += 1; v[1] += min(c, RB_KF); v[2] += (x + RB_CB - 1) / RB_CB; v[3] += x;
+    const int x = max(0, c - p.kf);
+    v[0] += 1; v[1] += min(c, p.kf); v[2] += (x + p.cb - 1) / p.cb; v[3] += x;
   }
   block_scan_vec<4>(v, tot, s_w);
   for (int s = b; s < e; ++s) {
     const int c = p.s_cnt[s];
     if (!c) continue;
-    const int x = max(0, c - RB_KF), nm = min(c, RB_KF);
+    const int x = max(0, c - p.kf), nm = min(c, p.kf);
     p.s_fid[s] = v[0]; p.s_first[s] = v[1]; p.s_xfam[s] = v[2]; p.s_xoff[s] = v[3];
     p.fb_src[v[0]] = s; p.fb_first[v[0]] = v[1]; p.fb_cnt[v[0]] = nm;
-    for (int q = 0; q * RB_CB < x; ++q) {
-      p.fa_src[v[2] + q] = s; p.fa_first[v[2] + q] = v[3] + q * RB_CB; p.fa_cnt[v[2] + q] = min(RB_CB, x - q * RB_CB);
+    for (int q = 0; q * p.cb < x; ++q) {
+      p.fa_src[v[2] + q] = s; p.fa_first[v[2] + q] = v[3] + q * p.cb; p.fa_cnt[v[2] + q] = min(p.cb, x - q * p.cb);
     }
-    v[0] += 1; v[1] += nm; v[2] += (x + RB_CB - 1) / RB_CB; v[3] += x;
+    v[0] += 1; v[1] += nm; v[2] += (x + p.cb - 1) / p.cb; v[3] += x;
   }
-  if (tid == 0) { *p.n_fb = tot[0]; *p.n_fa = tot[2]; }
+  if (tid == 0) { *p.n_fb = tot[0]; *p.n_fa = tot[2]; p.work_ctr[0] = 0; p.work_ctr[1] = 0; }
   __syncthreads();
   for (int j = tid; j < n; j += blockDim.x) {
     if (p.item_group && p.item_group[j] != p.group) continue;
     const int s = p.src_slot[j];
-    const int c = p.s_cnt[s], nm = min(c, RB_KF), kp = p.s_keeper[s];
+    const int c = p.s_cnt[s], nm = min(c, p.kf), kp = p.s_keeper[s];
     const int an = p.anc ? p.anc[j] : s;
     const int fid = p.s_fid[s];
     if (j == kp) {
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(1024) k_build_families(FamBuildArgs p) {
       } else {
         const int x = pos - lim;
         p.fa_child[p.s_xoff[s] + x] = j;
-        if (x % RB_CB == 0) p.fa_anc[p.s_xfam[s] + x / RB_CB] = an;
+        if (x % p.cb == 0) p.fa_anc[p.s_xfam[s] + x / p.cb] = an;
       }
     }
   }
@@ -261,6 +263,269 @@ k_stream_fam(StreamArgs a, FamLists f) {
 #pragma unroll
           for (int k = 0; k < R2; ++k) {
             const int rp = tid + k * RB_STREAM_THREADS;
+            if (rp < npairs) {
+              double o0[4] = {0, 0, 0, 0}, o1[4] = {0, 0, 0, 0};
+#pragma unroll
+              for (int bq = 0; bq < D; ++bq) { o0[bq] = acc[s][k][bq].x; o1[bq] = acc[s][k][bq].y; }
+              double4 *op = reinterpret_cast<double4 *>(out + (size_t)2 * rp * 4);
+              op[0] = make_double4(o0[0], o0[1], o0[2], o0[3]);
+              op[1] = make_double4(o1[0], o1[1], o1[2], o1[3]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Symmetric variant (kalman_variant 4, opt-in): stream only the LOWER triangle of each slab.
+//
+// P is symmetric and the downdate K SS K' = G SS G' is symmetric, so the strictly upper
+// triangle carries no information.  This kernel reads and writes, per column c, only the
+// rows r >= c (one TMA bulk copy per column, starting at the even row 2*(c>>1)); the upper
+// triangle of the slab is never touched again after initialisation and is not valid.
+// P H' is assembled from the triangle: element (r,c), r > c, contributes P(r,c) H(b,c) to
+// row r ("row side", per-thread register accumulators as in k_stream_fam) and
+// P(r,c) H(b,r) to row c ("column side": per column a block-wide reduction - warp shuffles,
+// then one partial per warp in shared memory, summed after the stage).  The column-side
+// sums go to a second partial slot of PHp (k_innov4 adds all slots).  HBM traffic per
+// particle-step halves; the arithmetic per stored element doubles (still far under the
+// fp64 ridge).  Results differ from the full-storage kernels by rounding only (the
+// reference does not symmetrise P, its two triangles differ by O(eps)).
+//   threads: 288 (9 warps) so that R2 = 2 row pairs per thread cover ld <= 1152 and the
+//   sibling's H rows fit the register file next to the accumulators; CB = 2 siblings per pass.
+// ---------------------------------------------------------------------------
+#define RB_SYM_THREADS 288
+#define RB_SYM_CB 2
+#define RB_SYM_WARPS (RB_SYM_THREADS / 32)
+
+template <int D, int R2, int KC, int S, int CB>
+__global__ void __launch_bounds__(RB_SYM_THREADS, 1)
+k_stream_fam_sym(StreamArgs a, FamLists f) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ double s_col[2][KC][RB_SYM_WARPS][CB * D];   // column-side partials, one per warp
+  __shared__ int s_ring[8];
+  const int ld = a.ld, M = a.M;
+  const int npairs = ld >> 1;
+  const size_t stage_doubles = (size_t)KC * ld + (size_t)4 * KC * (1 + CB);
+  double *stages = reinterpret_cast<double *>(smraw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_items = (*f.n_fam) * a.nsplit;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // ---- producer (thread 0), same item -> batch -> chunk walk as k_stream_fam --------------
+  int p_claim = 0;
+  int p_it = 0, p_b = 0, p_c = 0, p_q = 0;
+  auto claim = [&]() {
+    p_it = atomicAdd(f.work_counter, 1);
+    s_ring[p_claim & 7] = p_it;
+    ++p_claim;
+  };
+  if (tid == 0) claim();
+  auto issue = [&]() {
+    if (p_it >= n_items) return;
+    const int fam = p_it / a.nsplit, sp = p_it % a.nsplit;
+    const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);
+    const int c = c0 + p_c, ncols = min(KC, c1 - c);
+    const int cnt = f.cnt[fam], first = f.first[fam];
+    const int nbat = (cnt + CB - 1) / CB;
+    const int nv = min(CB, cnt - p_b * CB);
+    double *st = stages + (size_t)(p_q % S) * stage_doubles;
+    uint64_t *bar = &full[p_q % S];
+    const uint32_t bytes_v = (uint32_t)ncols * 32u;
+    const double *src = a.P + (size_t)f.src[fam] * a.slab;
+    if (a.hints & 2) {   // diagnostic: whole columns in one copy (full-storage traffic, triangle arithmetic)
+      const uint32_t bytes_p = (uint32_t)ncols * ld * 8u;
+      mbar_expect_tx(bar, bytes_p + (1 + nv) * bytes_v);
+      tma_load_1d(st, src + (size_t)c * ld, bytes_p, bar);
+    } else {
+      uint32_t bytes_p = 0;
+      for (int u = 0; u < ncols; ++u) bytes_p += (uint32_t)(ld - (((c + u) >> 1) << 1)) * 8u;
+      mbar_expect_tx(bar, bytes_p + (1 + nv) * bytes_v);
+      for (int u = 0; u < ncols; ++u) {   // rows r0.. of column c+u, r0 = the even row at or above the diagonal
+        const int r0 = ((c + u) >> 1) << 1;
+        tma_load_1d(st + (size_t)u * ld + r0, src + (size_t)(c + u) * ld + r0, (uint32_t)(ld - r0) * 8u, bar);
+      }
+    }
+    tma_load_1d(st + (size_t)KC * ld, a.G4prev + ((size_t)f.anc[fam] * ld + c) * 4, bytes_v, bar);
+    for (int q = 0; q < nv; ++q) {
+      const int ch = f.child[first + p_b * CB + q];
+      tma_load_1d(st + (size_t)KC * ld + 4 * KC * (1 + q), a.H4 + ((size_t)ch * ld + c) * 4, bytes_v, bar);
+    }
+    ++p_q;
+    p_c += KC;
+    if (c0 + p_c >= c1) {
+      p_c = 0;
+      if (++p_b >= nbat) { p_b = 0; claim(); }
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) issue();
+  }
+
+  // ---- consumers ---------------------------------------------------------------------
+  int q = 0;
+  __syncthreads();
+  for (int c_claim = 0;; ++c_claim) {
+    const int it = s_ring[c_claim & 7];
+    if (it >= n_items) break;
+    const int fam = it / a.nsplit, sp = it % a.nsplit;
+    const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);
+    const int an = f.anc[fam], cnt = f.cnt[fam], first = f.first[fam];
+    double2 ks[R2][D];
+#pragma unroll
+    for (int k = 0; k < R2; ++k) {
+      const int rp = tid + k * RB_SYM_THREADS;
+      if (rp < npairs) {
+        const double4 *kp = reinterpret_cast<const double4 *>(a.KS4prev + ((size_t)an * ld + 2 * rp) * 4);
+        const double4 k0 = kp[0], k1 = kp[1];
+        const double r0[4] = {k0.x, k0.y, k0.z, k0.w}, r1[4] = {k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+        for (int bq = 0; bq < D; ++bq) ks[k][bq] = make_double2(r0[bq], r1[bq]);
+      } else {
+#pragma unroll
+        for (int bq = 0; bq < D; ++bq) ks[k][bq] = make_double2(0.0, 0.0);
+      }
+    }
+    for (int b0 = 0; b0 < cnt; b0 += CB) {
+      const int nv = min(CB, cnt - b0);
+      int child[CB];
+      double *Pd[CB];
+#pragma unroll
+      for (int s = 0; s < CB; ++s) {
+        child[s] = s < nv ? f.child[first + b0 + s] : -1;
+        Pd[s] = s < nv ? a.P + (size_t)a.dst_slot[child[s]] * a.slab : nullptr;
+      }
+      // H of every sibling at this thread's own rows (column side) and zeroed accumulators
+      double2 acc[CB][R2][D], hrow[CB][R2][D];
+#pragma unroll
+      for (int s = 0; s < CB; ++s)
+#pragma unroll
+        for (int k = 0; k < R2; ++k) {
+          const int rp = tid + k * RB_SYM_THREADS;
+          double h0[4] = {0, 0, 0, 0}, h1[4] = {0, 0, 0, 0};
+          if (s < nv && rp < npairs) {
+            const double4 *hp = reinterpret_cast<const double4 *>(a.H4 + ((size_t)child[s] * ld + 2 * rp) * 4);
+            const double4 x0 = hp[0], x1 = hp[1];
+            h0[0] = x0.x; h0[1] = x0.y; h0[2] = x0.z; h0[3] = x0.w;
+            h1[0] = x1.x; h1[1] = x1.y; h1[2] = x1.z; h1[3] = x1.w;
+          }
+#pragma unroll
+          for (int bq = 0; bq < D; ++bq) {
+            hrow[s][k][bq] = make_double2(h0[bq], h1[bq]);
+            acc[s][k][bq] = make_double2(0.0, 0.0);
+          }
+        }
+      // the column-side slot of PHp: this item writes columns [c0, c1), everything else is zero
+#pragma unroll
+      for (int s = 0; s < CB; ++s) {
+        if (s < nv) {
+          double4 *oc = reinterpret_cast<double4 *>(a.PHp + ((size_t)child[s] * (2 * a.nsplit) + a.nsplit + sp) * ld * 4);
+          for (int r = tid; r < ld; r += RB_SYM_THREADS)
+            if (r < c0 || r >= c1) oc[r] = make_double4(0.0, 0.0, 0.0, 0.0);
+        }
+      }
+      for (int c = c0; c < c1; c += KC, ++q) {
+        const double *st = stages + (size_t)(q % S) * stage_doubles;
+        mbar_wait(&full[q % S], (uint32_t)((q / S) & 1));
+        const int ncols = min(KC, c1 - c);
+#pragma unroll
+        for (int u = 0; u < KC; ++u) {
+          if (u < ncols) {
+            const int cc = c + u, p0 = cc >> 1;
+            const bool odd = cc & 1;
+            const double4 g4 = *reinterpret_cast<const double4 *>(st + (size_t)KC * ld + 4 * u);
+            const double g[4] = {g4.x, g4.y, g4.z, g4.w};
+            double h[CB][4];
+#pragma unroll
+            for (int s = 0; s < CB; ++s) {
+              const double4 h4 = *reinterpret_cast<const double4 *>(st + (size_t)KC * ld + 4 * KC * (1 + s) + 4 * u);
+              h[s][0] = h4.x; h[s][1] = h4.y; h[s][2] = h4.z; h[s][3] = h4.w;
+            }
+            double colacc[CB][D];
+#pragma unroll
+            for (int s = 0; s < CB; ++s)
+#pragma unroll
+              for (int bq = 0; bq < D; ++bq) colacc[s][bq] = 0.0;
+            const double2 *col = reinterpret_cast<const double2 *>(st + (size_t)u * ld);
+#pragma unroll
+            for (int k = 0; k < R2; ++k) {
+              const int rp = tid + k * RB_SYM_THREADS;
+              if (rp < npairs && rp >= p0) {
+                double2 v = col[rp];
+#pragma unroll
+                for (int bq = 0; bq < D; ++bq) {   // the ancestor's pending downdate, once per element
+                  v.x = fma(-ks[k][bq].x, g[bq], v.x);
+                  v.y = fma(-ks[k][bq].y, g[bq], v.y);
+                }
+                // pair holding the diagonal: odd column -> (upper, diagonal), even -> (diagonal, lower)
+                const bool dg = rp == p0;
+                if (dg && odd) v.x = 0.0;                       // strictly upper: not part of the triangle
+                const double wx = dg ? 0.0 : v.x;               // strictly lower elements feed the column side
+                const double wy = (dg && odd) ? 0.0 : v.y;
+#pragma unroll
+                for (int s = 0; s < CB; ++s) {
+                  if (s < nv) {
+#pragma unroll
+                    for (int bq = 0; bq < D; ++bq) {
+                      acc[s][k][bq].x = fma(v.x, h[s][bq], acc[s][k][bq].x);      // row side: P(r,c) H(b,c)
+                      acc[s][k][bq].y = fma(v.y, h[s][bq], acc[s][k][bq].y);
+                      colacc[s][bq] = fma(wx, hrow[s][k][bq].x, colacc[s][bq]);   // column side: P(r,c) H(b,r)
+                      colacc[s][bq] = fma(wy, hrow[s][k][bq].y, colacc[s][bq]);
+                    }
+                    reinterpret_cast<double2 *>(Pd[s] + (size_t)cc * ld)[rp] = v;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int s = 0; s < CB; ++s) {
+              if (s < nv) {   // block-uniform: no shuffles for absent siblings
+#pragma unroll
+                for (int bq = 0; bq < D; ++bq) {
+                  const double r = warp_sum(colacc[s][bq]);
+                  if (lane == 0) s_col[q & 1][u][wid][s * D + bq] = r;
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) issue();
+        if (tid < KC * CB) {   // one thread per (column, sibling): add the warps' partials in fixed order
+          const int u = tid / CB, s = tid % CB;
+          if (u < ncols && s < nv) {
+            double o[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int bq = 0; bq < D; ++bq) {
+              double t = 0.0;
+#pragma unroll
+              for (int w = 0; w < RB_SYM_WARPS; ++w) t += s_col[q & 1][u][w][s * D + bq];
+              o[bq] = t;
+            }
+            int ch = child[0];
+#pragma unroll
+            for (int s2 = 1; s2 < CB; ++s2) if (s == s2) ch = child[s2];
+            double4 *oc = reinterpret_cast<double4 *>(a.PHp + ((size_t)ch * (2 * a.nsplit) + a.nsplit + sp) * ld * 4);
+            oc[c + u] = make_double4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < CB; ++s) {
+        if (s < nv) {
+          double *out = a.PHp + ((size_t)child[s] * (2 * a.nsplit) + sp) * ld * 4;
+#pragma unroll
+          for (int k = 0; k < R2; ++k) {
+            const int rp = tid + k * RB_SYM_THREADS;
             if (rp < npairs) {
               double o0[4] = {0, 0, 0, 0}, o1[4] = {0, 0, 0, 0};
 #pragma unroll

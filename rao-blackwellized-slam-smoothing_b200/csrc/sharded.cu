@@ -219,15 +219,16 @@ __global__ void k_final_cov_sharded(int M, int ld, const double *__restrict__ Pm
                                     const double *__restrict__ G4m, const double *__restrict__ KS4m,
                                     const double *__restrict__ G4l, const double *__restrict__ KS4l,
                                     const double *__restrict__ xll, double wl, const double *__restrict__ means,
-                                    double *__restrict__ Pmax, double *__restrict__ Pmean) {
+                                    double *__restrict__ Pmax, double *__restrict__ Pmean, int sym) {
   const int c = blockIdx.x;
   const double *xmean = means + M;
   const double dc = xmean[c] - xll[c];
   for (int r = threadIdx.x; r < M; r += blockDim.x) {
-    double pm = Pm[r + (size_t)c * ld], pl = Pl[r + (size_t)c * ld];
+    const int rr = sym ? max(r, c) : r, cc = sym ? min(r, c) : c;   // sym: lower triangle only
+    double pm = Pm[rr + (size_t)cc * ld], pl = Pl[rr + (size_t)cc * ld];
     for (int b = 0; b < 4; ++b) {
-      pm = fma(-KS4m[(size_t)r * 4 + b], G4m[(size_t)c * 4 + b], pm);
-      pl = fma(-KS4l[(size_t)r * 4 + b], G4l[(size_t)c * 4 + b], pl);
+      pm = fma(-KS4m[(size_t)rr * 4 + b], G4m[(size_t)cc * 4 + b], pm);
+      pl = fma(-KS4l[(size_t)rr * 4 + b], G4l[(size_t)cc * 4 + b], pl);
     }
     Pmax[r + (size_t)c * M] = pm;
     Pmean[r + (size_t)c * M] = wl * (pl + (xmean[r] - xll[r]) * dc);
@@ -256,6 +257,14 @@ int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN) {
   RB_ALLOC(s->d_dead, gN); RB_ALLOC(s->d_expo, gN); RB_ALLOC(s->d_group, s->Nloc);
   s->host_plan = getenv("RBSLAM_HOST_PLAN") != nullptr;
   s->overlap = getenv("RBSLAM_OVERLAP") != nullptr;
+  if (s->overlap) {
+    // An SM cannot change its L1/shared carve-out while CTAs are resident, so kernels that are
+    // meant to share SMs with the streaming Kalman kernel (134 KB ring -> maximum carve-out)
+    // must ask for the same carve-out, or the block scheduler serialises them.
+    CK(cudaFuncSetAttribute(k_peer_fetch, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_meas, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_build_families, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
   CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned long long)));
   CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_fetch, cudaEventDisableTiming));
@@ -551,7 +560,8 @@ int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
     const size_t t4 = (size_t)ld * 4;
     k_final_cov_sharded<<<M, 128, 0, ctx->stream>>>(M, ld, at(SH_P, im, ctx->slab), at(SH_P, gN - 1, ctx->slab),
                                                     at(gsel, im, t4), at(ksel, im, t4), at(gsel, gN - 1, t4),
-                                                    at(ksel, gN - 1, t4), at(xsel, gN - 1, M), wl, means, Pmax, Pmean);
+                                                    at(ksel, gN - 1, t4), at(xsel, gN - 1, M), wl, means, Pmax, Pmean,
+                                                    ctx->sym ? 1 : 0);
     ctx->launches += 1;
     CK(cudaGetLastError());
     if (out->traj_max && (rc = rb_d2h(ctx, out->traj_max, s->traj_max, sizeof(double) * n * T))) return rc;

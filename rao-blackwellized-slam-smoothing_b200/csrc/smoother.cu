@@ -622,6 +622,7 @@ extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int
                                    rbslam_smoother_outputs *out) {
   if (!ctx || !in || !out || N_K < 1 || (form != 0 && form != 1)) return RBSLAM_EARG;
   if (!ctx->cfg.keep_history) return ctx->fail(RBSLAM_EARG, "the smoother needs keep_history=1");
+  if (ctx->sym) return ctx->fail(RBSLAM_EARG, "kalman_variant 4 (symmetric storage) is filter-only");
   const bool sparse = ctx->mc.family == FAM_SPARSE_VISUAL2D;
   if (form == 1 && sparse)
     return ctx->fail(RBSLAM_EARG, "This code has only been implemented for dense features");   // :77-80
@@ -816,7 +817,7 @@ extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int
     if (out->PK) {
       if ((rc = rb_flush_pending(ctx))) return rc;
       double *tmp = ctx->d_scratch + 2 * (size_t)M + 64;
-      k_pack_slabs<<<dim3(M, 1), 128, 0, ctx->stream>>>(M, ctx->ld, ctx->slab, ctx->d_P, ctx->d_slot[ctx->cs], h_ak[k], tmp);
+      k_pack_slabs<<<dim3(M, 1), 128, 0, ctx->stream>>>(M, ctx->ld, ctx->slab, ctx->d_P, ctx->d_slot[ctx->cs], h_ak[k], tmp, 0);
       ctx->launches += 1;
       if ((rc = rb_d2h(ctx, out->PK + (size_t)k * M * M, tmp, sizeof(double) * M * M))) return rc;
     }
