@@ -654,8 +654,6 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
     static bool fattr_done = false;
     if (!fattr_done) {
       CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
-      // same carve-out as the kernels of the sharded step that may share an SM with it (sharded.cu)
-      CK(cudaFuncSetAttribute(fkern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       fattr_done = true;
     }
     if (fsmem > ctx->smem_optin - 1024) return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");

@@ -257,14 +257,6 @@ int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN) {
   RB_ALLOC(s->d_dead, gN); RB_ALLOC(s->d_expo, gN); RB_ALLOC(s->d_group, s->Nloc);
   s->host_plan = getenv("RBSLAM_HOST_PLAN") != nullptr;
   s->overlap = getenv("RBSLAM_OVERLAP") != nullptr;
-  if (s->overlap) {
-    // An SM cannot change its L1/shared carve-out while CTAs are resident, so kernels that are
-    // meant to share SMs with the streaming Kalman kernel (134 KB ring -> maximum carve-out)
-    // must ask for the same carve-out, or the block scheduler serialises them.
-    CK(cudaFuncSetAttribute(k_peer_fetch, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_meas, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(k_build_families, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  }
   CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned long long)));
   CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_fetch, cudaEventDisableTiming));
