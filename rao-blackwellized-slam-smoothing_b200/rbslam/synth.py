@@ -221,13 +221,15 @@ def dense_radio_problem(traj="line_3D", m=128, seed=1, theta=(0.25, 1.0, 0.01), 
 # ----------------------------------------------------------------------------
 def sparse_visual_problem(N_T=197, n_landmarks=20, N_P=100, seed=1, f=1.5, fp=0.0, fw=1.0,
                           noise_var=0.01 ** 2, init_map_var=1.0, guess_map_var=0.0,
-                          pos_var=0.01 ** 2, angle_var=0.001 ** 2, fixture=None):
+                          pos_var=0.01 ** 2, angle_var=0.001 ** 2, fixture=None, pos_bias=0.0,
+                          meas_noise_std=None):
     """Visual SLAM inputs shaped like pfslam.m:78-97 / load_data.m:58-89.
 
     With ``fixture`` (a dict holding the arrays of the reference's
     ``curve-x2.mat``: Yclean, map, p, th) the real path/landmarks are used;
     otherwise a loop path with a ring of landmarks is synthesised.  Unobserved
     landmarks are NaN in ``y`` (behind the camera or outside the image width).
+    ``c3_problem`` fills in the example's own parameter values.
     """
     rng = np.random.default_rng(seed)
     if fixture is not None:
@@ -251,10 +253,12 @@ def sparse_visual_problem(N_T=197, n_landmarks=20, N_P=100, seed=1, f=1.5, fp=0.
             yy = (f * lx + fp * ly) / ly
             vis = (ly > 0) & (np.abs(yy) <= fw)
             Yclean[vis, t] = yy[vis]
-    Y = Yclean + np.sqrt(noise_var) * rng.standard_normal(Yclean.shape)
+    # load_data.m:86 adds noise of a fixed 0.01 std while R = noiseVar*I comes from main.m:28
+    sd = np.sqrt(noise_var) if meas_noise_std is None else meas_noise_std
+    Y = Yclean + sd * rng.standard_normal(Yclean.shape)
     dth = np.diff(np.unwrap(th))
     u = np.hstack([np.diff(p, axis=1).T, dth.reshape(-1, 1)])
-    u[:, 0:2] += np.sqrt(pos_var) * rng.standard_normal((N_T - 1, 2))
+    u[:, 0:2] += np.sqrt(pos_var) * rng.standard_normal((N_T - 1, 2)) + pos_bias   # load_data.m:82
     u[:, 2] += np.sqrt(angle_var) * rng.standard_normal(N_T - 1)
     odometry = np.vstack([u, np.zeros((1, 3))])
     M = 2 * n_landmarks
@@ -264,3 +268,15 @@ def sparse_visual_problem(N_T=197, n_landmarks=20, N_P=100, seed=1, f=1.5, fp=0.
                 P0_lin=init_map_var * np.eye(M), Q=np.diag([0.1 ** 2, 0.1 ** 2, 0.001 ** 2]),
                 R=noise_var * np.eye(n_landmarks), dt=1.0, camera=(f, fp, fw),
                 n_landmarks=n_landmarks, truth=dict(p=p, th=th, map=lm))
+
+
+def c3_problem(fixture, N_P=100, seed=42):
+    """The sparse visual-SLAM example as its runner configures it (C3): the path, landmarks and
+    noise-free observations of ``curve-x2.mat`` (``fixture``), odometry noise + drift and
+    observation noise of load_data.m:44-54,80-86, map / noise scales of
+    slam-sparse-visual/main.m:27-29, Q and x0_lin of pfslam.m:89-95.  NumPy random numbers
+    replace MATLAB's (the streams cannot be reproduced)."""
+    return sparse_visual_problem(N_P=N_P, seed=seed, f=1.5, fp=0.0, fw=1.0, noise_var=0.1 ** 2,
+                                 init_map_var=4.0 ** 2, guess_map_var=1.0 ** 2, pos_var=0.04 ** 2,
+                                 angle_var=(0.001 ** 2) ** 2, fixture=fixture, pos_bias=0.01,
+                                 meas_noise_std=0.01)
