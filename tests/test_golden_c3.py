@@ -48,6 +48,19 @@ def test_oracle_projection_reproduces_the_fixture_observations():
     assert worst < 1e-12, worst
 
 
+def test_odometry_recipe_reproduces_the_fixture_increments():
+    """load_data.m:73-78 (dPos = diff(p,[],2), dTheta = diff(unwrap(th))) as restated in
+    rbslam/synth.py, with the noise switched off, against the increments stored in the fixture."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "rao-blackwellized-slam-smoothing_b200"))
+    from rbslam import synth
+    fx = _fixture()
+    pr = synth.sparse_visual_problem(fixture=fx, pos_var=0.0, angle_var=0.0, pos_bias=0.0, noise_var=0.0)
+    assert_close_norm(pr["odometry"][:196, :2], fx["dPos"].T, 1e-14, "dPos")
+    assert_close_norm(pr["odometry"][:196, 2], fx["dTheta"].reshape(-1), 1e-14, "dTheta")
+    assert np.array_equal(np.isnan(pr["y"]), np.isnan(fx["Yclean"].T))
+
+
 def test_oracle_filter_on_fixture_tracks_the_path():
     import sys
     sys.path.insert(0, os.path.join(ROOT, "rao-blackwellized-slam-smoothing_b200"))
