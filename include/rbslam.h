@@ -87,7 +87,11 @@ typedef struct {
   int32_t information_form;/* also carry ivec/Imat/halfLogDetP (information-form smoother) */
   int32_t keep_history;    /* 1: keep xn history for xn_traj / traj_sample outputs */
   int32_t rank, world;     /* particle sharding: this context owns N/world particles */
-  int32_t kalman_variant;  /* 0 = auto; >0 selects a specific kernel (profiling) */
+  int32_t kalman_variant;  /* Kalman-update kernel: 0 = auto (shared-memory single pass when the
+                              slab fits one CTA, else the streaming pass with sibling fusion);
+                              2 = force the streaming pass; 3 = legacy three-kernel path (A/B
+                              baseline); 4 = symmetric streaming pass, lower triangle only
+                              (experimental, filter only, slower than 0 - see DESIGN.md) */
 } rbslam_config;
 
 typedef struct {
