@@ -90,8 +90,9 @@ typedef struct {
   int32_t kalman_variant;  /* Kalman-update kernel: 0 = auto (shared-memory single pass when the
                               slab fits one CTA, else the streaming pass with sibling fusion);
                               2 = force the streaming pass; 3 = legacy three-kernel path (A/B
-                              baseline); 4 = symmetric streaming pass, lower triangle only
-                              (experimental, filter only, slower than 0 - see DESIGN.md) */
+                              baseline); 4 / 5 = symmetric streaming pass, lower triangle
+                              only, in SIMT form / on the fp64 tensor cores (experimental, filter
+                              only, parity-green but slower than 0 - see DESIGN.md section 8) */
 } rbslam_config;
 
 typedef struct {

@@ -261,12 +261,13 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   const bool can_stream = d <= 4 && ctx->ld <= 4 * 2 * RB_STREAM_THREADS;
   if (cfg->information_form && !can_stream)
     return ctx->fail(RBSLAM_EARG, "information form needs d<=3 and M<=1536");
-  if (cfg->kalman_variant == 4) {   // symmetric (lower-triangle) streaming pass, opt-in, filter only
-    if (!can_stream || d > 3 || ctx->ld > 4 * RB_SYM_THREADS || cfg->information_form)
-      return ctx->fail(RBSLAM_EARG, "kalman_variant 4 needs d<=3, M<=1152 and the covariance form");
-    if (getenv("RBSLAM_NO_FAM")) return ctx->fail(RBSLAM_EARG, "kalman_variant 4 is a family kernel (unset RBSLAM_NO_FAM)");
+  if (cfg->kalman_variant == 4 || cfg->kalman_variant == 5) {   // symmetric (lower-triangle) streaming pass, opt-in, filter only
+    if (!can_stream || d > 3 || ctx->ld > (cfg->kalman_variant == 5 ? 1088 : 4 * RB_SYM_THREADS) || cfg->information_form)
+      return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5 need d<=3, M<=1152 (4) / M<=1088 (5) and the covariance form");
+    if (getenv("RBSLAM_NO_FAM")) return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5 are family kernels (unset RBSLAM_NO_FAM)");
     ctx->kpath = 1;
     ctx->sym = true;
+    ctx->sym_mma = cfg->kalman_variant == 5;
     if (const char *e = getenv("RBSLAM_SYM_FLAGS")) ctx->sym_flags = atoi(e);
     if (const char *e = getenv("RBSLAM_SYM_CFG")) { int kc = 8, st = 2; if (sscanf(e, "%d,%d", &kc, &st) == 2) ctx->sym_cfg = kc * 100 + st; }
   } else if (small && cfg->kalman_variant != 2 && cfg->kalman_variant != 3 && !cfg->information_form) ctx->kpath = 0;
@@ -282,6 +283,7 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
     if (const char *e = getenv("RBSLAM_CTAS_PER_SM")) ctx->stream_ctas_per_sm = atoi(e);
     if (const char *e = getenv("RBSLAM_STREAM_HINTS")) ctx->stream_hints = atoi(e);
     int cw = ((M + ns - 1) / ns + 3) / 4 * 4;
+    if (ctx->sym_mma) cw = (cw + 7) / 8 * 8;   // 8-column MMA blocks
     ctx->nsplit = (M + cw - 1) / cw; ctx->cw = cw;
   } else {
     ctx->hs_p = (size_t)d * ctx->ldh; ctx->hs_a = ctx->ldh; ctx->hs_c = 1;
@@ -317,6 +319,7 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   RB_ALLOC(ctx->d_src_slot, N); RB_ALLOC(ctx->d_first_child, N); RB_ALLOC(ctx->d_free_list, N);
   RB_ALLOC(ctx->d_listA, N); RB_ALLOC(ctx->d_listB, N); RB_ALLOC(ctx->d_counts, 8);
   RB_ALLOC(ctx->d_H, (size_t)N * ctx->hs_p);
+  CK(cudaMemsetAsync(ctx->d_H, 0, sizeof(double) * (size_t)N * ctx->hs_p, ctx->stream));   // unused lanes of the 4-wide layout stay 0
   RB_ALLOC(ctx->d_yhat, (size_t)N * d);
   if (ctx->kpath == 2) {
     RB_ALLOC(ctx->d_PHpart, (size_t)N * ctx->nsplit * d * ctx->ld);
@@ -824,6 +827,81 @@ static int launch_sym(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   return ctx->ld / 2 <= RB_SYM_THREADS ? launch_sym_r<D, 1>(ctx, a, resampled) : launch_sym_r<D, 2>(ctx, a, resampled);
 }
 
+// symmetric pass on the fp64 tensor cores (kalman_variant 5): k_stream_fam_symt
+template <int D, int MAXQ>
+static int launch_symt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  constexpr int KC = 8, S = 2, CB = 2;
+  const int N = ctx->N, ld = ctx->ld;
+  StreamArgs sa;
+  sa.hints = 0; sa.gk_by_particle = 0;
+  sa.M = ctx->M; sa.ld = ld; sa.cw = ctx->cw; sa.nsplit = ctx->nsplit; sa.slab = ctx->slab;
+  sa.P = ctx->d_P; sa.src_slot = a.src_slot; sa.dst_slot = a.dst_slot; sa.anc = a.ai;
+  sa.G4prev = ctx->d_G4[ctx->cg]; sa.KS4prev = ctx->d_KS4[ctx->cg]; sa.H4 = a.H; sa.PHp = ctx->d_PHp;
+  int *fm = ctx->d_fam;
+  FamBuildArgs fb;
+  fb.n_items = N; fb.n_slabs = N; fb.n_items_dev = nullptr;
+  fb.src_slot = a.src_slot; fb.dst_slot = a.dst_slot; fb.anc = a.ai;
+  fb.s_cnt = fm; fb.s_keeper = fm + N; fb.s_cursor = fm + 2 * (size_t)N; fb.s_first = fm + 3 * (size_t)N;
+  fb.s_fid = fm + 4 * (size_t)N; fb.s_xoff = fm + 5 * (size_t)N; fb.s_xfam = fm + 6 * (size_t)N;
+  int *lb = fm + 7 * (size_t)N, *la = fm + 12 * (size_t)N, *cnts = fm + 17 * (size_t)N;
+  fb.fb_src = lb; fb.fb_anc = lb + N; fb.fb_first = lb + 2 * (size_t)N; fb.fb_cnt = lb + 3 * (size_t)N;
+  fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
+  fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
+  fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
+  fb.work_ctr = cnts + 2;
+  fb.cb = CB; fb.kf = 2 * CB;
+  auto fkern = k_stream_fam_symt<MAXQ>;
+  const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * (ld + 2) + 4 * KC * (1 + CB));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, fkern));
+  static bool fattr_done = false;
+  if (!fattr_done) {
+    CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(ctx->smem_optin - fa.sharedSizeBytes)));
+    fattr_done = true;
+  }
+  if (fsmem + fa.sharedSizeBytes > ctx->smem_optin)
+    return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
+  const int fgrid = std::min(N * ctx->nsplit, ctx->num_sms);
+  const int ngrp = ctx->item_group ? ctx->stream_groups : 1;
+  for (int grp = 0; grp < ngrp; ++grp) {
+    if (grp > 0 && ctx->group_hook) {
+      int rch = ctx->group_hook(ctx, grp);
+      if (rch) return rch;
+    }
+    fb.item_group = ngrp > 1 ? ctx->item_group : nullptr;
+    fb.group = grp;
+    k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
+    ctx->launches += 1;
+    for (int phase = 0; phase < 2; ++phase) {
+      if (phase == 0 && !resampled) continue;
+      FamLists fl;
+      const int *base = phase == 0 ? la : lb;
+      fl.n_fam = cnts + (phase == 0 ? 1 : 0);
+      fl.work_counter = cnts + 2 + phase;
+      fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
+      fl.child = base + 4 * (size_t)N;
+      fkern<<<fgrid, RB_SYMT_THREADS, fsmem, ctx->stream>>>(sa, fl);
+      ctx->launches += 1;
+    }
+  }
+  Innov4Args ia;
+  ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = 2 * ctx->nsplit; ia.PHp = ctx->d_PHp; ia.H4 = a.H;
+  ia.xl_old = a.xl_old; ia.anc = a.ai; ia.xl_new = a.xl_new;
+  ia.G4new = ctx->d_G4[1 - ctx->cg]; ia.KS4new = ctx->d_KS4[1 - ctx->cg];
+  ia.y_t = a.y_t; ia.R = a.R; ia.jitter = a.jitter; ia.logw = a.logw; ia.status = a.status; ia.t = a.t;
+  ia.G4prev = ctx->d_G4[ctx->cg]; ia.KS4prev = ctx->d_KS4[ctx->cg];   // the products used the slab before its downdate
+  k_innov4<D><<<N, 128, sizeof(double) * 4 * ld, ctx->stream>>>(ia);
+  ctx->launches += 1;
+  ctx->cg ^= 1;
+  ctx->pending = true;
+  return RBSLAM_OK;
+}
+template <int D>
+static int launch_symt(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  return ctx->ld / 8 <= 72 ? launch_symt_q<D, 9>(ctx, a, resampled) : launch_symt_q<D, 17>(ctx, a, resampled);
+}
+
 // apply the deferred downdate to every slab (before the state is read out as a whole)
 int rb_flush_pending(rbslam_ctx *ctx) {
   if (ctx->kpath != 1 || !ctx->pending) return RBSLAM_OK;
@@ -873,6 +951,14 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled) {
                                                        ctx->d_counts + phase);
       ctx->launches += 1;
     }
+  } else if (ctx->kpath == 1 && ctx->sym_mma) {
+    int rc;
+    switch (d) {
+      case 1: rc = launch_symt<1>(ctx, a, resampled); break;
+      case 2: rc = launch_symt<2>(ctx, a, resampled); break;
+      default: rc = launch_symt<3>(ctx, a, resampled); break;
+    }
+    if (rc) return rc;
   } else if (ctx->kpath == 1 && ctx->sym) {
     int rc;
     switch (d) {

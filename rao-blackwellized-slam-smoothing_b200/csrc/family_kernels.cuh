@@ -541,4 +541,205 @@ k_stream_fam_sym(StreamArgs a, FamLists f) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Symmetric variant on the fp64 tensor cores (kalman_variant 5, opt-in).
+//
+// Same data movement as k_stream_fam_sym (lower triangle only; here in 8-row blocks, so a
+// stage of 8 columns c..c+7 holds the row blocks j >= c/8), but every product is an
+// mma.sync.m8n8k4.f64 on an 8x8 tile T = P_old(8j.., c..) read from the shared-memory stage:
+//   downdate  T_new = T - KS_blk G_blk'           1 MMA, accumulators = T, stored to every sibling
+//   row side  PHrow(8j.., n) += T(:, u) H_n(c+u)   2 MMAs (k = 4 columns each)
+//   col side  PHcol(c.., n)  += T(r, :)' H_n(r)    2 MMAs (k = 4 rows each); the reduction over
+//             rows, which costs the SIMT version a shuffle tree per column, happens in the MMA
+// with n = (sibling, measurement row) = 2 x 4 output columns.  The products use the tile BEFORE
+// its pending downdate; k_innov4 completes them (Innov4Args::G4prev).  Only the diagonal block
+// needs masking.  Warp w owns the row blocks j = w (mod 8): every warp gets the same share of a
+// triangular stage, and the row-side accumulators of its <= MAXQ blocks stay in registers.
+// Stage columns are padded to ld + 2 doubles: every fragment read is two shared-memory wavefronts.
+// ---------------------------------------------------------------------------
+#define RB_SYMT_THREADS 256
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int MAXQ>
+__global__ void __launch_bounds__(RB_SYMT_THREADS, 1)
+k_stream_fam_symt(StreamArgs a, FamLists f) {
+  constexpr int KC = 8, S = 2, CB = 2, NW = RB_SYMT_THREADS / 32;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ __align__(16) double s_colp[2][NW][64];   // column-side accumulator tiles, one per warp
+  __shared__ int s_ring[8];
+  const int ld = a.ld, M = a.M, lds = a.ld + 2, nblk = a.ld >> 3;
+  const size_t stage_doubles = (size_t)KC * lds + (size_t)4 * KC * (1 + CB);
+  double *stages = reinterpret_cast<double *>(smraw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;   // MMA fragment coordinates
+  const int n_items = (*f.n_fam) * a.nsplit;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // ---- producer (thread 0): item -> batch -> 8-column chunk, S stages ahead -------------
+  int p_claim = 0;
+  int p_it = 0, p_b = 0, p_c = 0, p_q = 0;
+  auto claim = [&]() {
+    p_it = atomicAdd(f.work_counter, 1);
+    s_ring[p_claim & 7] = p_it;
+    ++p_claim;
+  };
+  if (tid == 0) claim();
+  auto issue = [&]() {
+    if (p_it >= n_items) return;
+    const int fam = p_it / a.nsplit, sp = p_it % a.nsplit;
+    const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);        // cw is a multiple of 8
+    const int c = c0 + p_c, ncols = min(KC, c1 - c);
+    const int cnt = f.cnt[fam], first = f.first[fam];
+    const int nbat = (cnt + CB - 1) / CB;
+    const int nv = min(CB, cnt - p_b * CB);
+    double *st = stages + (size_t)(p_q % S) * stage_doubles;
+    uint64_t *bar = &full[p_q % S];
+    const uint32_t bytes_v = (uint32_t)ncols * 32u, bytes_c = (uint32_t)(ld - c) * 8u;
+    mbar_expect_tx(bar, (uint32_t)ncols * bytes_c + (1 + nv) * bytes_v);
+    const double *src = a.P + (size_t)f.src[fam] * a.slab;
+    for (int u = 0; u < ncols; ++u)   // rows c.. (the diagonal block and everything below) of column c+u
+      tma_load_1d(st + (size_t)u * lds + c, src + (size_t)(c + u) * ld + c, bytes_c, bar);
+    tma_load_1d(st + (size_t)KC * lds, a.G4prev + ((size_t)f.anc[fam] * ld + c) * 4, bytes_v, bar);
+    for (int q = 0; q < nv; ++q) {
+      const int ch = f.child[first + p_b * CB + q];
+      tma_load_1d(st + (size_t)KC * lds + 4 * KC * (1 + q), a.H4 + ((size_t)ch * ld + c) * 4, bytes_v, bar);
+    }
+    ++p_q;
+    p_c += KC;
+    if (c0 + p_c >= c1) {
+      p_c = 0;
+      if (++p_b >= nbat) { p_b = 0; claim(); }
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) issue();
+  }
+
+  // ---- consumers ---------------------------------------------------------------------
+  int q = 0;
+  __syncthreads();
+  for (int c_claim = 0;; ++c_claim) {
+    const int it = s_ring[c_claim & 7];
+    if (it >= n_items) break;
+    const int fam = it / a.nsplit, sp = it % a.nsplit;
+    const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);
+    const int an = f.anc[fam], cnt = f.cnt[fam], first = f.first[fam];
+    const double *KSa = a.KS4prev + (size_t)an * ld * 4;
+    for (int b0 = 0; b0 < cnt; b0 += CB) {
+      const int nv = min(CB, cnt - b0);
+      int child[CB];
+      double *Pd[CB];
+#pragma unroll
+      for (int s = 0; s < CB; ++s) {
+        child[s] = s < nv ? f.child[first + b0 + s] : -1;
+        Pd[s] = s < nv ? a.P + (size_t)a.dst_slot[child[s]] * a.slab : nullptr;
+      }
+      // this lane's sibling in the B operands / outputs: output column n = 4 s + b
+      const int sB = g >> 2;                          // B operand: n = g
+      const double *HrB = sB < nv ? a.H4 + (size_t)child[sB] * ld * 4 + (g & 3) : nullptr;
+      // the column-side slot of PHp: this item writes columns [c0, c1), everything else is zero
+#pragma unroll
+      for (int s = 0; s < CB; ++s) {
+        if (s < nv) {
+          double4 *oc = reinterpret_cast<double4 *>(a.PHp + ((size_t)child[s] * (2 * a.nsplit) + a.nsplit + sp) * ld * 4);
+          for (int r = tid; r < ld; r += RB_SYMT_THREADS)
+            if (r < c0 || r >= c1) oc[r] = make_double4(0.0, 0.0, 0.0, 0.0);
+        }
+      }
+      double acc[MAXQ][2];   // row side: PHrow(8 j + g, n = 2 tg + e), j = wid + 8 qq
+#pragma unroll
+      for (int qq = 0; qq < MAXQ; ++qq) acc[qq][0] = acc[qq][1] = 0.0;
+      for (int c = c0; c < c1; c += KC, ++q) {
+        const double *st = stages + (size_t)(q % S) * stage_doubles;
+        mbar_wait(&full[q % S], (uint32_t)((q / S) & 1));
+        const int ncols = min(KC, c1 - c), j0 = c >> 3;
+        const double *thin = st + (size_t)KC * lds;
+        // per-stage B operands: G(c+g, tg) for the downdate, H_s(b, c + 4h + tg) for the row side;
+        // columns that were not loaded (u >= ncols) and absent siblings are exact zeros
+        const double gB = g < ncols ? thin[4 * g + tg] : 0.0;
+        double hB[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          hB[h] = (4 * h + tg < ncols && sB < nv) ? thin[4 * KC * (1 + sB) + 4 * (4 * h + tg) + (g & 3)] : 0.0;
+        double col0 = 0.0, col1 = 0.0;   // column side: PHcol(c + g, n = 2 tg + e)
+#pragma unroll
+        for (int qq = 0; qq < MAXQ; ++qq) {
+          const int j = wid + NW * qq;
+          if (j >= j0 && j < nblk) {
+            const int r = 8 * j + g;
+            const bool diag = j == j0;
+            // downdate: T_new(r, u) = T(r, u) - sum_k KS(r, k) G(c+u, k)
+            const double ksA = -KSa[(size_t)r * 4 + tg];
+            double t0 = st[(size_t)(2 * tg) * lds + r], t1 = st[(size_t)(2 * tg + 1) * lds + r];
+            dmma_m8n8k4(t0, t1, ksA, gB);
+#pragma unroll
+            for (int s = 0; s < CB; ++s) {
+              if (s < nv) {
+                if (2 * tg < ncols) Pd[s][(size_t)(c + 2 * tg) * ld + r] = t0;
+                if (2 * tg + 1 < ncols) Pd[s][(size_t)(c + 2 * tg + 1) * ld + r] = t1;
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              // row side, A(row g, k tg) = T(r, u), u = 4h + tg: valid on and below the diagonal
+              const int u = 4 * h + tg;
+              double aR = st[(size_t)u * lds + r];
+              if (u >= ncols || (diag && g < u)) aR = 0.0;
+              dmma_m8n8k4(acc[qq][0], acc[qq][1], aR, hB[h]);
+              // column side, A(row u = g, k tg) = T(8j + rho, c + g), rho = 4h + tg: strictly below
+              const int rho = 4 * h + tg;
+              double aC = st[(size_t)g * lds + 8 * j + rho];
+              if (g >= ncols || (diag && rho <= g)) aC = 0.0;
+              const double bC = HrB != nullptr ? HrB[(size_t)(8 * j + rho) * 4] : 0.0;
+              dmma_m8n8k4(col0, col1, aC, bC);
+            }
+          }
+        }
+        *reinterpret_cast<double2 *>(&s_colp[q & 1][wid][g * 8 + 2 * tg]) = make_double2(col0, col1);
+        __syncthreads();
+        if (tid == 0) issue();
+        if (tid < 64) {   // (column u, output n): add the warps' tiles in fixed order
+          const int u = tid >> 3, n = tid & 7, s = n >> 2;
+          if (u < ncols && s < nv) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) t += s_colp[q & 1][w][tid];
+            int ch = child[0];
+#pragma unroll
+            for (int s2 = 1; s2 < CB; ++s2) if (s == s2) ch = child[s2];
+            a.PHp[(((size_t)ch * (2 * a.nsplit) + a.nsplit + sp) * ld + (c + u)) * 4 + (n & 3)] = t;
+          }
+        }
+      }
+      // row-side slot: lane holds PHrow(8j+g, n = 2tg, 2tg+1) -> sibling tg>>1, entries 2(tg&1), +1
+      {
+        const int s = tg >> 1;
+        if (s < nv) {
+          int ch = child[0];
+#pragma unroll
+          for (int s2 = 1; s2 < CB; ++s2) if (s == s2) ch = child[s2];
+          double *out = a.PHp + ((size_t)ch * (2 * a.nsplit) + sp) * ld * 4;
+#pragma unroll
+          for (int qq = 0; qq < MAXQ; ++qq) {
+            const int j = wid + NW * qq;
+            if (j < nblk)
+              *reinterpret_cast<double2 *>(out + (size_t)(8 * j + g) * 4 + 2 * (tg & 1)) = make_double2(acc[qq][0], acc[qq][1]);
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace rb

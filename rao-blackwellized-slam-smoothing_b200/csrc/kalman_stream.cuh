@@ -236,6 +236,10 @@ struct Innov4Args {
   double *logw;
   DevStatus *status;
   int t;
+  // tensor-core symmetric pass (k_stream_fam_symt): the partial sums are P_old H' of the slab
+  // BEFORE its pending downdate; the innovation kernel completes them,
+  //   P_new H' = P_old H' - KS_anc (G_anc' H'),   W = G_anc' H' is d x d per particle
+  const double *G4prev = nullptr, *KS4prev = nullptr;   // [N][ld][4] pending pair, indexed by ancestor
 };
 
 template <int D>
@@ -249,6 +253,36 @@ k_innov4(Innov4Args a) {
   const int i = blockIdx.x;
   const double *Hi = a.H4 + (size_t)i * ld * 4;
   const double *xls = a.xl_old + (size_t)(a.anc ? a.anc[i] : i) * M;
+  __shared__ double s_W[D * D];   // W(k,b) = sum_c G_anc(c,k) H(b,c)
+  const double *KSa = nullptr;
+  if (a.G4prev != nullptr) {
+    const int an = a.anc ? a.anc[i] : i;
+    const double *Ga = a.G4prev + (size_t)an * ld * 4;
+    KSa = a.KS4prev + (size_t)an * ld * 4;
+    double wp[D * D];
+#pragma unroll
+    for (int q = 0; q < D * D; ++q) wp[q] = 0.0;
+    for (int c = threadIdx.x; c < M; c += blockDim.x) {
+      const double4 gv = *reinterpret_cast<const double4 *>(Ga + (size_t)c * 4);
+      const double4 hv = *reinterpret_cast<const double4 *>(Hi + (size_t)c * 4);
+      const double g[4] = {gv.x, gv.y, gv.z, gv.w}, h[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+      for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int bb = 0; bb < D; ++bb) wp[k + bb * D] = fma(g[k], h[bb], wp[k + bb * D]);
+    }
+    __shared__ double s_wred[4][D * D];
+#pragma unroll
+    for (int q = 0; q < D * D; ++q) {
+      const double v = warp_sum(wp[q]);
+      if ((threadIdx.x & 31) == 0) s_wred[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < D * D)
+      s_W[threadIdx.x] = (s_wred[0][threadIdx.x] + s_wred[1][threadIdx.x]) +
+                         (s_wred[2][threadIdx.x] + s_wred[3][threadIdx.x]);
+    __syncthreads();
+  }
   double part[D * D + D];
 #pragma unroll
   for (int q = 0; q < D * D + D; ++q) part[q] = 0.0;
@@ -257,6 +291,14 @@ k_innov4(Innov4Args a) {
     for (int sp = 0; sp < a.nsplit; ++sp) {   // fixed order: deterministic
       const double4 v = *reinterpret_cast<const double4 *>(a.PHp + (((size_t)i * a.nsplit + sp) * ld + r) * 4);
       ph[0] += v.x; ph[1] += v.y; ph[2] += v.z; ph[3] += v.w;
+    }
+    if (KSa != nullptr) {   // complete P_new H' (see Innov4Args)
+      const double4 kv = *reinterpret_cast<const double4 *>(KSa + (size_t)r * 4);
+      const double ks[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int bb = 0; bb < D; ++bb)
+#pragma unroll
+        for (int k = 0; k < D; ++k) ph[bb] = fma(-ks[k], s_W[k + bb * D], ph[bb]);
     }
     if (r >= M) { ph[0] = ph[1] = ph[2] = ph[3] = 0.0; }
     *reinterpret_cast<double4 *>(sPH + (size_t)r * 4) = make_double4(ph[0], ph[1], ph[2], ph[3]);

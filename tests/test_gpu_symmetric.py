@@ -1,5 +1,5 @@
-"""kalman_variant 4: the symmetric streaming pass (lower triangle of every covariance slab
-only, k_stream_fam_sym) against the oracle.  Same bars as the full-storage kernels: ancestor
+"""kalman_variant 4 / 5: the symmetric streaming passes (lower triangle of every covariance slab
+only; k_stream_fam_sym in SIMT form, k_stream_fam_symt on the fp64 tensor cores) against the oracle.  Same bars as the full-storage kernels: ancestor
 indices bit-exact, means / covariances / log-weights within 1e-8 (norm-wise for matrices).
 The reference never symmetrises P (src/particleFilter.m:198), so its two triangles differ by
 rounding; the tolerance absorbs that."""
@@ -12,11 +12,16 @@ from test_gpu_filter import _setup, _args, _run_oracle, _compare, TOL
 from test_gpu_kernels import _problem, _rand_spd, _oracle_update
 
 pytestmark = pytest.mark.gpu
-SYM = 4
+
+
+@pytest.fixture(params=[4, 5], ids=["simt", "dmma"])
+def SYM(request):
+    """4 = k_stream_fam_sym (SIMT, shuffle reduction), 5 = k_stream_fam_symt (fp64 tensor cores)."""
+    return request.param
 
 
 @pytest.mark.parametrize("fam,m", [("mag", 64), ("mag", 253), ("mag", 512), ("mag", 1024), ("radio", 300)])
-def test_sym_kalman_update(rbslam_lib, fam, m):
+def test_sym_kalman_update(rbslam_lib, SYM, fam, m):
     """One update from a zero pending pair: triangle streaming, column-side reduction, mirror on
     read-out (rbslam_op_kalman_update flushes the deferred downdate and packs the slabs)."""
     rb = rbslam_lib
@@ -45,7 +50,7 @@ def test_sym_kalman_update(rbslam_lib, fam, m):
     ("mag", 40, {"m": 1024, "T": 5}),      # C4 slab size, M=1027: two row pairs per thread
     ("radio", 64, {"m": 300}),             # d=1
 ])
-def test_sym_filter_teacher_forced(rbslam_lib, fam, N, kw):
+def test_sym_filter_teacher_forced(rbslam_lib, SYM, fam, N, kw):
     """Ancestors from the oracle run (families of 1..many siblings, surplus families, copies
     and in-place offspring): every step's logw and all 8 outputs."""
     rb = rbslam_lib
@@ -59,7 +64,7 @@ def test_sym_filter_teacher_forced(rbslam_lib, fam, N, kw):
     _compare(o, ref, taps, T)
 
 
-def test_sym_filter_free_running_and_read_particles(rbslam_lib):
+def test_sym_filter_free_running_and_read_particles(rbslam_lib, SYM):
     """Device draws its own ancestors (bit-exact), and the per-step tap returns full symmetric
     covariances although only the triangle is maintained."""
     rb = rbslam_lib
@@ -87,7 +92,7 @@ def test_sym_filter_free_running_and_read_particles(rbslam_lib):
     _compare(o, ref, taps, T)
 
 
-def test_sym_is_filter_only(rbslam_lib):
+def test_sym_is_filter_only(rbslam_lib, SYM):
     rb = rbslam_lib
     pr, om, gm = _setup(rb, "mag", 8, m=253, T=4)
     with pytest.raises(rb.RbslamError):

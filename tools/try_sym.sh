@@ -1,5 +1,8 @@
 #!/bin/bash
-# symmetric streaming kernel (kalman_variant 4): parity tests, then the C4 bench next to the default kernel
+# symmetric streaming kernels (kalman_variant 4 = SIMT, 5 = DMMA): parity tests, then the C4 bench
 mkdir -p gpurun_out
-timeout -s KILL 400 python -m pytest tests/test_gpu_symmetric.py -q -m gpu 2>&1 | tail -8 | cut -c1-250
-tools/tune_sym.sh "$@"
+timeout -s KILL 400 python -m pytest tests/test_gpu_symmetric.py -q -m gpu -k "${SYM_K:-dmma}" 2>&1 | tail -12 | cut -c1-250
+for v in "$@"; do
+  timeout -s KILL 200 python bench.py --variant $v --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('variant $v', round(d['value']), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), 'kalman', round(d['roofline']['phases_ms_per_step']['kalman'],2), d['clocks']['sm_mhz'], d['clocks']['reasons'])"
+done
