@@ -31,6 +31,7 @@ for p in (ROOT, PKG):
 
 METRIC = "particle-steps/sec (N*T/s) at m basis fns"
 UNIT = "particle-steps/s"
+WORKLOAD = "C4 synthetic 3D dense-mag scale-up (BASELINE.json configs[3])"
 
 
 def parse_args():
@@ -199,8 +200,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 dense-mag scale-up, m=%d (M=%d), bounded sample of %d particles"
-                                   % (args.basis, args.basis + 3, Np)},
+            "config": {"workload": WORKLOAD, "m_basis": args.basis, "M_linear_states": args.basis + 3,
+                       "d_meas": 3, "sample_particles_per_step": Np,
+                       "note": "same workload as the CUDA arm; each step is a bounded sample of its particles"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -309,7 +311,7 @@ def run_cuda(args):
             "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 synthetic 3D dense-mag scale-up (BASELINE.json configs[3])",
+            "config": {"workload": WORKLOAD,
                        "N_particles_total": gN, "N_particles_per_gpu": n_loc, "m_basis": m,
                        "M_linear_states": M, "d_meas": d,
                        "state_bytes_per_gpu": n_loc * ctx.ld * M * 8,
