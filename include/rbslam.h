@@ -92,7 +92,8 @@ typedef struct {
                               2 = force the streaming pass; 3 = legacy three-kernel path (A/B
                               baseline); 4 / 5 = symmetric streaming pass, lower triangle
                               only, in SIMT form / on the fp64 tensor cores (experimental, filter
-                              only, parity-green but slower than 0 - see DESIGN.md section 8) */
+                              only, parity-green but slower than 0 - see DESIGN.md section 8); 6 = variant 5
+                              with a producer warp and a deeper ring, not yet verified on a GPU */
 } rbslam_config;
 
 typedef struct {

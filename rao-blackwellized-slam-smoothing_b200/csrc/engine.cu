@@ -261,13 +261,14 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   const bool can_stream = d <= 4 && ctx->ld <= 4 * 2 * RB_STREAM_THREADS;
   if (cfg->information_form && !can_stream)
     return ctx->fail(RBSLAM_EARG, "information form needs d<=3 and M<=1536");
-  if (cfg->kalman_variant == 4 || cfg->kalman_variant == 5) {   // symmetric (lower-triangle) streaming pass, opt-in, filter only
-    if (!can_stream || d > 3 || ctx->ld > (cfg->kalman_variant == 5 ? 1088 : 4 * RB_SYM_THREADS) || cfg->information_form)
-      return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5 need d<=3, M<=1152 (4) / M<=1088 (5) and the covariance form");
-    if (getenv("RBSLAM_NO_FAM")) return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5 are family kernels (unset RBSLAM_NO_FAM)");
+  if (cfg->kalman_variant >= 4 && cfg->kalman_variant <= 6) {   // symmetric (lower-triangle) streaming pass, opt-in, filter only
+    if (!can_stream || d > 3 || ctx->ld > (cfg->kalman_variant >= 5 ? 1088 : 4 * RB_SYM_THREADS) || cfg->information_form)
+      return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5/6 need d<=3, M<=1152 (4) / M<=1088 (5, 6) and the covariance form");
+    if (getenv("RBSLAM_NO_FAM")) return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5/6 are family kernels (unset RBSLAM_NO_FAM)");
     ctx->kpath = 1;
     ctx->sym = true;
-    ctx->sym_mma = cfg->kalman_variant == 5;
+    ctx->sym_mma = cfg->kalman_variant >= 5;
+    ctx->sym_pipe = cfg->kalman_variant == 6;
     if (const char *e = getenv("RBSLAM_SYM_FLAGS")) ctx->sym_flags = atoi(e);
     if (const char *e = getenv("RBSLAM_SYM_CFG")) { int kc = 8, st = 2; if (sscanf(e, "%d,%d", &kc, &st) == 2) ctx->sym_cfg = kc * 100 + st; }
   } else if (small && cfg->kalman_variant != 2 && cfg->kalman_variant != 3 && !cfg->information_form) ctx->kpath = 0;
@@ -828,7 +829,7 @@ static int launch_sym(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
 }
 
 // symmetric pass on the fp64 tensor cores (kalman_variant 5): k_stream_fam_symt
-template <int D, int MAXQ>
+template <int D, int MAXQ, bool PIPE>
 static int launch_symt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   constexpr int KC = 8, S = 2, CB = 2;
   const int N = ctx->N, ld = ctx->ld;
@@ -850,8 +851,12 @@ static int launch_symt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
   fb.work_ctr = cnts + 2;
   fb.cb = CB; fb.kf = 2 * CB;
-  auto fkern = k_stream_fam_symt<MAXQ>;
-  const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * (ld + 2) + 4 * KC * (1 + CB));
+  // PIPE: kalman_variant 6 (producer warp, six-slot ring of 8 x 512 stages), else variant 5
+  void (*fkern)(StreamArgs, FamLists);
+  if constexpr (PIPE) fkern = k_stream_fam_symp<MAXQ>; else fkern = k_stream_fam_symt<MAXQ>;
+  const size_t fsmem = PIPE ? sizeof(double) * (size_t)RB_SYMP_SLOTS * RB_SYMP_SLOT_DOUBLES
+                            : sizeof(double) * (size_t)S * ((size_t)KC * (ld + 2) + 4 * KC * (1 + CB));
+  const int fthreads = PIPE ? RB_SYMP_THREADS : RB_SYMT_THREADS;
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, fkern));
   static bool fattr_done = false;
@@ -881,7 +886,7 @@ static int launch_symt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
       fl.work_counter = cnts + 2 + phase;
       fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
       fl.child = base + 4 * (size_t)N;
-      fkern<<<fgrid, RB_SYMT_THREADS, fsmem, ctx->stream>>>(sa, fl);
+      fkern<<<fgrid, fthreads, fsmem, ctx->stream>>>(sa, fl);
       ctx->launches += 1;
     }
   }
@@ -899,7 +904,10 @@ static int launch_symt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
 }
 template <int D>
 static int launch_symt(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
-  return ctx->ld / 8 <= 72 ? launch_symt_q<D, 9>(ctx, a, resampled) : launch_symt_q<D, 17>(ctx, a, resampled);
+  // MAXQ = row blocks per consumer warp: 8 warps (variant 5) or 7 (variant 6) share ld / 8 blocks
+  if (ctx->sym_pipe)
+    return ctx->ld / 8 <= 72 ? launch_symt_q<D, 11, true>(ctx, a, resampled) : launch_symt_q<D, 20, true>(ctx, a, resampled);
+  return ctx->ld / 8 <= 72 ? launch_symt_q<D, 9, false>(ctx, a, resampled) : launch_symt_q<D, 17, false>(ctx, a, resampled);
 }
 
 // apply the deferred downdate to every slab (before the state is read out as a whole)

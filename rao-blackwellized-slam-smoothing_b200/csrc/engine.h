@@ -43,7 +43,8 @@ struct rbslam_ctx {
   int *d_fam = nullptr;
   bool use_fam = true;
   bool sym = false;          // kalman_variant 4: only the lower triangle of every slab is streamed / valid
-  bool sym_mma = false;      // kalman_variant 5: the symmetric pass on the fp64 tensor cores (k_stream_fam_symt)
+  bool sym_mma = false;      // kalman_variant 5, 6: the symmetric pass on the fp64 tensor cores (k_stream_fam_symt)
+  bool sym_pipe = false;     // kalman_variant 6: producer-warp / deep-ring version (k_stream_fam_symp), unverified
   int sym_flags = 0;         // RBSLAM_SYM_FLAGS: 2 = copy whole columns (diagnostic: full traffic, triangle arithmetic)
   int sym_cfg = 802;         // RBSLAM_SYM_CFG="KC,S"
   const int *item_group = nullptr;   // sharded engine: work group of each local item (see stream_groups)

@@ -742,4 +742,231 @@ k_stream_fam_symt(StreamArgs a, FamLists f) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// kalman_variant 6 (opt-in; NOT YET RUN ON A GPU - written after the round's GPU budget was
+// spent, tests are gated behind RBSLAM_TEST_UNVERIFIED=1): the tensor-core symmetric pass of
+// k_stream_fam_symt with the data movement rebuilt around what limited it (tuning_r1.md, 7):
+//   * a dedicated producer warp (warp 7 of 8); the 8 column copies of a stage are issued by 8 lanes
+//     at once; full/empty mbarriers per ring slot instead of a block-wide barrier per stage,
+//   * uniform stages of 8 columns x <= 512 rows (a panel taller than 512 rows is two stages),
+//     six slots of 33 KB in flight, so the small stages at the narrow end of the triangle are
+//     pipelined six deep instead of one,
+//   * the consumers are driven by per-stage descriptors the producer leaves in shared memory
+//     (item, batch, panel, row segment); the column-side tiles are reduced across the 7
+//     consumer warps once per panel behind a named barrier,
+//   * stage columns padded to 516 doubles (= 8 mod 32 words): every fragment read of the
+//     three access patterns is exactly two shared-memory wavefronts.
+// The arithmetic is k_stream_fam_symt's, statement for statement.
+// ---------------------------------------------------------------------------
+#define RB_SYMP_THREADS 256        // 7 consumer warps + 1 producer warp (8 warps: 255 registers each)
+#define RB_SYMP_NW 7
+#define RB_SYMP_SLOTS 6
+#define RB_SYMP_ROWS 512           // rows per stage
+#define RB_SYMP_SLD (RB_SYMP_ROWS + 4)
+#define RB_SYMP_SLOT_DOUBLES (8 * RB_SYMP_SLD + 4 * 8 * 3)
+
+struct SympDesc {   // what a ring slot holds; item < 0: no more work
+  int item, b0, c, seg;
+};
+
+template <int MAXQ>
+__global__ void __launch_bounds__(RB_SYMP_THREADS, 1)
+k_stream_fam_symp(StreamArgs a, FamLists f) {
+  constexpr int KC = 8, CB = 2, NW = RB_SYMP_NW, NS = RB_SYMP_SLOTS, SLD = RB_SYMP_SLD;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ __align__(8) uint64_t full[NS], empty[NS];
+  __shared__ SympDesc s_desc[NS];
+  __shared__ __align__(16) double s_colp[2][NW][64];
+  const int ld = a.ld, M = a.M, nblk = a.ld >> 3;
+  double *ring = reinterpret_cast<double *>(smraw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int n_items = (*f.n_fam) * a.nsplit;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (wid == NW) {
+    // ================= producer warp ====================================================
+    int it = 0;
+    if (lane == 0) it = atomicAdd(f.work_counter, 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    int b = 0, c_off = 0, seg = 0;   // batch, column offset in the item's range, row segment
+    for (int q = 0;; ++q) {
+      const int slot = q % NS, round = q / NS;
+      if (round > 0) mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));   // consumers are done with it
+      double *st = ring + (size_t)slot * RB_SYMP_SLOT_DOUBLES;
+      if (it >= n_items) {   // terminal descriptor: every consumer warp sees it in order
+        if (lane == 0) {
+          s_desc[slot].item = -1;
+          mbar_arrive(&full[slot]);
+        }
+        break;
+      }
+      const int fam = it / a.nsplit, sp = it % a.nsplit;
+      const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);
+      const int c = c0 + c_off, ncols = min(KC, c1 - c);
+      const int cnt = f.cnt[fam], first = f.first[fam];
+      const int nbat = (cnt + CB - 1) / CB;
+      const int nv = min(CB, cnt - b * CB);
+      const int r_lo = c + RB_SYMP_ROWS * seg, r_hi = min(ld, r_lo + RB_SYMP_ROWS);
+      const bool last_seg = r_hi == ld;
+      const uint32_t bytes_v = (uint32_t)ncols * 32u, bytes_c = (uint32_t)(r_hi - r_lo) * 8u;
+      if (lane == 0) {
+        s_desc[slot].item = it; s_desc[slot].b0 = b * CB; s_desc[slot].c = c; s_desc[slot].seg = seg;
+        mbar_expect_tx(&full[slot], (uint32_t)ncols * bytes_c + (1 + nv) * bytes_v);
+        double *thin = st + (size_t)KC * SLD;
+        tma_load_1d(thin, a.G4prev + ((size_t)f.anc[fam] * ld + c) * 4, bytes_v, &full[slot]);
+        for (int s = 0; s < nv; ++s) {
+          const int ch = f.child[first + b * CB + s];
+          tma_load_1d(thin + 4 * KC * (1 + s), a.H4 + ((size_t)ch * ld + c) * 4, bytes_v, &full[slot]);
+        }
+      }
+      __syncwarp();
+      if (lane < ncols)   // rows [r_lo, r_hi) of column c + lane
+        tma_load_1d(st + (size_t)lane * SLD, a.P + (size_t)f.src[fam] * a.slab + (size_t)(c + lane) * ld + r_lo,
+                    bytes_c, &full[slot]);
+      // advance: segment -> panel -> batch -> item
+      if (!last_seg) {
+        ++seg;
+      } else {
+        seg = 0;
+        c_off += KC;
+        if (c0 + c_off >= c1) {
+          c_off = 0;
+          if (++b >= nbat) {
+            b = 0;
+            if (lane == 0) it = atomicAdd(f.work_counter, 1);
+            it = __shfl_sync(0xffffffffu, it, 0);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= consumer warps ======================================================
+  int cur_item = -1, cur_b0 = -1;
+  int fam = 0, sp = 0, c0 = 0, c1 = 0, nv = 0;
+  int child[CB] = {-1, -1};
+  double *Pd[CB] = {nullptr, nullptr};
+  const double *KSa = nullptr, *HrB = nullptr;
+  const int sB = g >> 2;
+  double acc[MAXQ][2];
+#pragma unroll
+  for (int qq = 0; qq < MAXQ; ++qq) acc[qq][0] = acc[qq][1] = 0.0;
+  double col0 = 0.0, col1 = 0.0;
+  int n_panel = 0;   // panels finished so far (parity selects the s_colp buffer)
+
+  auto flush_rows = [&]() {   // row-side slot of the batch that just ended
+    const int s = tg >> 1;
+    if (s < nv) {
+      const int ch = s == 0 ? child[0] : child[1];
+      double *out = a.PHp + ((size_t)ch * (2 * a.nsplit) + sp) * ld * 4;
+#pragma unroll
+      for (int qq = 0; qq < MAXQ; ++qq) {
+        const int j = wid + NW * qq;
+        if (j < nblk)
+          *reinterpret_cast<double2 *>(out + (size_t)(8 * j + g) * 4 + 2 * (tg & 1)) = make_double2(acc[qq][0], acc[qq][1]);
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) acc[qq][0] = acc[qq][1] = 0.0;
+  };
+
+  for (int q = 0;; ++q) {
+    const int slot = q % NS;
+    mbar_wait(&full[slot], (uint32_t)((q / NS) & 1));
+    const SympDesc d = s_desc[slot];
+    if (d.item < 0) break;
+    if (d.item != cur_item || d.b0 != cur_b0) {   // a new batch starts (uniform over the consumers)
+      if (cur_item >= 0) flush_rows();
+      cur_item = d.item; cur_b0 = d.b0;
+      fam = d.item / a.nsplit; sp = d.item % a.nsplit;
+      c0 = sp * a.cw; c1 = min(M, c0 + a.cw);
+      const int cnt = f.cnt[fam], first = f.first[fam];
+      nv = min(CB, cnt - d.b0);
+#pragma unroll
+      for (int s = 0; s < CB; ++s) {
+        child[s] = s < nv ? f.child[first + d.b0 + s] : -1;
+        Pd[s] = s < nv ? a.P + (size_t)a.dst_slot[child[s]] * a.slab : nullptr;
+      }
+      KSa = a.KS4prev + (size_t)f.anc[fam] * ld * 4;
+      HrB = sB < nv ? a.H4 + (size_t)(sB == 0 ? child[0] : child[1]) * ld * 4 + (g & 3) : nullptr;
+#pragma unroll
+      for (int s = 0; s < CB; ++s) {   // column-side slot: zero outside this item's columns
+        if (s < nv) {
+          double4 *oc = reinterpret_cast<double4 *>(a.PHp + ((size_t)child[s] * (2 * a.nsplit) + a.nsplit + sp) * ld * 4);
+          for (int r = tid; r < ld; r += NW * 32)
+            if (r < c0 || r >= c1) oc[r] = make_double4(0.0, 0.0, 0.0, 0.0);
+        }
+      }
+    }
+    const double *st = ring + (size_t)slot * RB_SYMP_SLOT_DOUBLES;
+    const double *thin = st + (size_t)KC * SLD;
+    const int c = d.c, ncols = min(KC, c1 - c), j0 = c >> 3;
+    const int r_lo = c + RB_SYMP_ROWS * d.seg, r_hi = min(ld, r_lo + RB_SYMP_ROWS);
+    const int jlo = r_lo >> 3, jhi = r_hi >> 3;
+    const bool last_seg = r_hi == ld;
+    const double gB = g < ncols ? thin[4 * g + tg] : 0.0;
+    double hB[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      hB[h] = (4 * h + tg < ncols && sB < nv) ? thin[4 * KC * (1 + sB) + 4 * (4 * h + tg) + (g & 3)] : 0.0;
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      const int j = wid + NW * qq;
+      if (j >= jlo && j < jhi) {
+        const int r = 8 * j + g, rs = r - r_lo;       // global row, row inside the stage
+        const bool diag = j == j0;
+        const double ksA = -KSa[(size_t)r * 4 + tg];
+        double t0 = st[(size_t)(2 * tg) * SLD + rs], t1 = st[(size_t)(2 * tg + 1) * SLD + rs];
+        dmma_m8n8k4(t0, t1, ksA, gB);
+#pragma unroll
+        for (int s = 0; s < CB; ++s) {
+          if (s < nv) {
+            if (2 * tg < ncols) Pd[s][(size_t)(c + 2 * tg) * ld + r] = t0;
+            if (2 * tg + 1 < ncols) Pd[s][(size_t)(c + 2 * tg + 1) * ld + r] = t1;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int u = 4 * h + tg;
+          double aR = st[(size_t)u * SLD + rs];
+          if (u >= ncols || (diag && g < u)) aR = 0.0;
+          dmma_m8n8k4(acc[qq][0], acc[qq][1], aR, hB[h]);
+          const int rho = 4 * h + tg;
+          double aC = st[(size_t)g * SLD + (8 * j - r_lo) + rho];
+          if (g >= ncols || (diag && rho <= g)) aC = 0.0;
+          const double bC = HrB != nullptr ? HrB[(size_t)(8 * j + rho) * 4] : 0.0;
+          dmma_m8n8k4(col0, col1, aC, bC);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);   // this warp has read everything it needs from the slot
+    if (last_seg) {   // the panel is complete: add the consumer warps' column-side tiles in fixed order
+      const int buf = n_panel & 1;
+      *reinterpret_cast<double2 *>(&s_colp[buf][wid][g * 8 + 2 * tg]) = make_double2(col0, col1);
+      col0 = col1 = 0.0;
+      named_barrier_sync(1, NW * 32);
+      if (tid < 64) {
+        const int u = tid >> 3, n = tid & 7, s = n >> 2;
+        if (u < ncols && s < nv) {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) t += s_colp[buf][w][tid];
+          const int ch = s == 0 ? child[0] : child[1];
+          a.PHp[(((size_t)ch * (2 * a.nsplit) + a.nsplit + sp) * ld + (c + u)) * 4 + (n & 3)] = t;
+        }
+      }
+      ++n_panel;
+    }
+  }
+  if (cur_item >= 0) flush_rows();
+}
+
 }  // namespace rb

@@ -3,6 +3,8 @@ only; k_stream_fam_sym in SIMT form, k_stream_fam_symt on the fp64 tensor cores)
 indices bit-exact, means / covariances / log-weights within 1e-8 (norm-wise for matrices).
 The reference never symmetrises P (src/particleFilter.m:198), so its two triangles differ by
 rounding; the tolerance absorbs that."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,9 +16,15 @@ from test_gpu_kernels import _problem, _rand_spd, _oracle_update
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[4, 5], ids=["simt", "dmma"])
+# 4 = k_stream_fam_sym (SIMT, shuffle reduction), 5 = k_stream_fam_symt (fp64 tensor cores): both
+# verified on a B200.  6 = k_stream_fam_symp (variant 5 with a producer warp and a six-slot ring) was
+# written after the round's GPU budget was spent and has NOT run yet: its cases are collected only
+# with RBSLAM_TEST_UNVERIFIED=1 so that the default suite contains verified kernels only.
+_VARIANTS = [(4, "simt"), (5, "dmma")] + ([(6, "dmma-pipelined")] if os.environ.get("RBSLAM_TEST_UNVERIFIED") else [])
+
+
+@pytest.fixture(params=[v for v, _ in _VARIANTS], ids=[n for _, n in _VARIANTS])
 def SYM(request):
-    """4 = k_stream_fam_sym (SIMT, shuffle reduction), 5 = k_stream_fam_symt (fp64 tensor cores)."""
     return request.param
 
 

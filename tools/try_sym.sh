@@ -1,5 +1,7 @@
 #!/bin/bash
-# symmetric streaming kernels (kalman_variant 4 = SIMT, 5 = DMMA): parity tests, then the C4 bench
+# symmetric streaming kernels (kalman_variant 4 = SIMT, 5 = DMMA, 6 = DMMA with producer warp + deep ring):
+# parity tests, then the C4 bench.  Variant 6 has not run on a GPU yet:
+#   RBSLAM_TEST_UNVERIFIED=1 SYM_K=pipelined tools/try_sym.sh 6 5 0
 mkdir -p gpurun_out
 timeout -s KILL 400 python -m pytest tests/test_gpu_symmetric.py -q -m gpu -k "${SYM_K:-dmma}" 2>&1 | tail -12 | cut -c1-250
 for v in "$@"; do
