@@ -85,7 +85,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -256,7 +256,8 @@ def run_cuda(args):
     M, d = ctx.M, ctx.d
     # ---- device-resident measurement ------------------------------------------------
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:          # one poller per job: rank 0 reports the clocks of its own GPU
+        sampler.start()
     ctx.filter_begin(*fargs, pr["dt"])
     ctx.sync()
     sampler.mark_load()
