@@ -713,7 +713,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
 template <int D, int R2>
 static int launch_stream_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   // default (KC=8 columns per stage, S=2 stages) measured best on C4; see profiles/tuning_r1.md
-  if (D == 3) {
+  if constexpr (D == 3) {   // the tuning configurations are instantiated for the C1/C4 family only
     switch (ctx->stream_cfg) {
       case 403: return launch_stream_cfg<D, R2, 4, 3>(ctx, a, resampled);
       case 404: return launch_stream_cfg<D, R2, 4, 4>(ctx, a, resampled);
@@ -813,7 +813,7 @@ static int launch_sym_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) 
 }
 template <int D, int R2>
 static int launch_sym_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
-  if (D == 3) {   // tuning knob RBSLAM_SYM_CFG="KC,S"
+  if constexpr (D == 3) {   // tuning knob RBSLAM_SYM_CFG="KC,S"
     switch (ctx->sym_cfg) {
       case 404: return launch_sym_cfg<D, R2, 4, 4>(ctx, a, resampled);
       case 406: return launch_sym_cfg<D, R2, 4, 6>(ctx, a, resampled);
