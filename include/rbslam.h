@@ -87,13 +87,18 @@ typedef struct {
   int32_t information_form;/* also carry ivec/Imat/halfLogDetP (information-form smoother) */
   int32_t keep_history;    /* 1: keep xn history for xn_traj / traj_sample outputs */
   int32_t rank, world;     /* particle sharding: this context owns N/world particles */
-  int32_t kalman_variant;  /* Kalman-update kernel: 0 = auto (shared-memory single pass when the
-                              slab fits one CTA, else the streaming pass with sibling fusion);
-                              2 = force the streaming pass; 3 = legacy three-kernel path (A/B
-                              baseline); 4 / 5 = symmetric streaming pass, lower triangle
-                              only, in SIMT form / on the fp64 tensor cores (experimental, filter
-                              only, parity-green but slower than 0 - see DESIGN.md section 8); 6 = variant 5
-                              with a producer warp and a deeper ring, not yet verified on a GPU */
+  int32_t kalman_variant;  /* Kalman-update kernel.
+                              0 = auto, valid for every entry point: shared-memory single pass when the
+                                  slab fits one CTA, else the streaming pass over full [ld x M] slabs with
+                                  sibling fusion;
+                             -1 = auto for contexts that only run the FILTER entry points (what the
+                                  particleFilter drop-ins pass): as 0, but large slabs are stored as packed
+                                  symmetric tiles (variant 7);
+                              2 = force the streaming pass over full slabs;
+                              3 = legacy three-kernel path (A/B baseline);
+                              7 = packed symmetric tile slabs streamed on the fp64 tensor cores: half the
+                                  memory and half the HBM traffic of 2; filter only, covariance form,
+                                  d <= 4, M <= 1080 (csrc/packed_kernels.cuh) */
 } rbslam_config;
 
 typedef struct {

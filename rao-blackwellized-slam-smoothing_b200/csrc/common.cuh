@@ -25,6 +25,7 @@ struct DevStatus {
   int not_pd_particle;
   int used_jitter;   // count of jitter retries (informational)
   int clamp_sample;  // count of u > wc(end) clamps (reference would index-error)
+  int peer_timeout;  // sharded filter: a peer never reached the barrier (it failed or died)
 };
 
 // ---------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 #include "kalman_kernels.cuh"
 #include "kalman_stream.cuh"
 #include "family_kernels.cuh"
+#include "packed_kernels.cuh"
 #include "engine_internal.h"
 
 using namespace rb;
@@ -86,7 +87,7 @@ __global__ void k_final_cov(int N, int M, int ld, size_t slab, const double *__r
                             const double *__restrict__ w, const int *__restrict__ iw_max,
                             const double *__restrict__ means, double *__restrict__ Pmax,
                             double *__restrict__ Pmean, const double *__restrict__ G4,
-                            const double *__restrict__ KS4, int sym) {
+                            const double *__restrict__ KS4, int layout) {
   const int c = blockIdx.x;
   const int im = *iw_max, il = N - 1;
   const double *Pm = P + (size_t)slot[im] * slab;
@@ -96,9 +97,11 @@ __global__ void k_final_cov(int N, int M, int ld, size_t slab, const double *__r
   const double wl = w[il];
   const double dc = xmean[c] - xll[c];
   for (int r = threadIdx.x; r < M; r += blockDim.x) {
-    // sym: only the lower triangle of a slab is valid -> element (r,c) lives at (max, min)
-    const int rr = sym ? max(r, c) : r, cc = sym ? min(r, c) : c;
-    double pm = Pm[rr + (size_t)cc * ld], pl = Pl[rr + (size_t)cc * ld];
+    // packed symmetric slabs store (r,c) of an upper block as its mirror image
+    int rr, cc;
+    slab_elem_rc(layout, r, c, rr, cc);
+    const size_t off = slab_elem(layout, ld, r, c);
+    double pm = Pm[off], pl = Pl[off];
     if (G4) {   // deferred downdate of the streaming path: P(r,c) -= KS(r,b) G(c,b)
       for (int b = 0; b < 4; ++b) {
         pm = fma(-KS4[((size_t)im * ld + rr) * 4 + b], G4[((size_t)im * ld + cc) * 4 + b], pm);
@@ -112,12 +115,11 @@ __global__ void k_final_cov(int N, int M, int ld, size_t slab, const double *__r
 
 // pack slabs into dense [M x M x cnt] logical order (read_particles)
 __global__ void k_pack_slabs(int M, int ld, size_t slab, const double *__restrict__ P,
-                             const int *__restrict__ slot, int i0, double *__restrict__ out, int sym) {
+                             const int *__restrict__ slot, int i0, double *__restrict__ out, int layout) {
   const int c = blockIdx.x, i = blockIdx.y;
   const double *src = P + (size_t)slot[i0 + i] * slab;
   double *dst = out + ((size_t)i * M + c) * M;
-  for (int r = threadIdx.x; r < M; r += blockDim.x)   // sym: mirror the valid lower triangle
-    dst[r] = sym ? src[max(r, c) + (size_t)min(r, c) * ld] : src[r + (size_t)c * ld];
+  for (int r = threadIdx.x; r < M; r += blockDim.x) dst[r] = src[slab_elem(layout, ld, r, c)];
 }
 __global__ void k_unpack_slabs(int M, int ld, size_t slab, double *__restrict__ P,
                                const int *__restrict__ slot, int i0, const double *__restrict__ in) {
@@ -182,11 +184,17 @@ int rb_check_status(rbslam_ctx *ctx) {
   CK(cudaMemcpyAsync(&st, ctx->d_status, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
+  if (st.peer_timeout)
+    return ctx->fail(RBSLAM_ECUDA, "sharded filter: a peer rank did not reach the barrier (it failed or exited)");
   if (st.not_pd) {
     char buf[256];
-    snprintf(buf, sizeof buf,
-             "innovation covariance not positive definite even with jitter (step %d, particle %d)",
-             st.not_pd_step, st.not_pd_particle);
+    if (st.not_pd_step < 0)
+      snprintf(buf, sizeof buf, "innovation covariance not positive definite even with jitter (reported by peer rank %d)",
+               -1 - st.not_pd_particle);
+    else
+      snprintf(buf, sizeof buf,
+               "innovation covariance not positive definite even with jitter (step %d, particle %d)",
+               st.not_pd_step, st.not_pd_particle);
     return ctx->fail(RBSLAM_ENOTPD, buf);
   }
   return RBSLAM_OK;
@@ -259,18 +267,26 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   // 1 = streaming pass with deferred downdate (kalman_stream.cuh), 2 = legacy 3-kernel path
   const bool small = kalman_small_smem(M, d) + 1024 <= ctx->smem_optin;
   const bool can_stream = d <= 4 && ctx->ld <= 4 * 2 * RB_STREAM_THREADS;
-  if (cfg->information_form && !can_stream)
+  if (cfg->information_form && (!can_stream || d > 3))
     return ctx->fail(RBSLAM_EARG, "information form needs d<=3 and M<=1536");
-  if (cfg->kalman_variant >= 4 && cfg->kalman_variant <= 6) {   // symmetric (lower-triangle) streaming pass, opt-in, filter only
-    if (!can_stream || d > 3 || ctx->ld > (cfg->kalman_variant >= 5 ? 1088 : 4 * RB_SYM_THREADS) || cfg->information_form)
-      return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5/6 need d<=3, M<=1152 (4) / M<=1088 (5, 6) and the covariance form");
-    if (getenv("RBSLAM_NO_FAM")) return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5/6 are family kernels (unset RBSLAM_NO_FAM)");
+  // packed symmetric tile slabs (packed_kernels.cuh): explicit (7), or chosen by the filter-only
+  // auto mode (-1) whenever the streaming path would be used
+  const bool pt_ok = d <= 4 && (ctx->ld % 8) == 0 && ctx->ld / 8 <= 135 && !cfg->information_form;
+  if (cfg->kalman_variant == 7 && !pt_ok)
+    return ctx->fail(RBSLAM_EARG, "kalman_variant 7 needs d<=4, ld a multiple of 8, M<=1080 and the covariance form");
+  if (cfg->kalman_variant >= 4 && cfg->kalman_variant <= 6)
+    return ctx->fail(RBSLAM_EARG, "kalman_variant 4/5/6 were removed (superseded by 7, packed symmetric slabs)");
+  if (cfg->kalman_variant == 7 || (cfg->kalman_variant == -1 && pt_ok && !small)) {
     ctx->kpath = 1;
-    ctx->sym = true;
-    ctx->sym_mma = cfg->kalman_variant >= 5;
-    ctx->sym_pipe = cfg->kalman_variant == 6;
-    if (const char *e = getenv("RBSLAM_SYM_FLAGS")) ctx->sym_flags = atoi(e);
-    if (const char *e = getenv("RBSLAM_SYM_CFG")) { int kc = 8, st = 2; if (sscanf(e, "%d,%d", &kc, &st) == 2) ctx->sym_cfg = kc * 100 + st; }
+    ctx->pt = true;
+    ctx->layout = RB_LAYOUT_PT;
+    ctx->slab = pt_slab_doubles(ctx->ld);
+    if (const char *e = getenv("RBSLAM_PT_CFG")) { int ts = 48, ns = 4; if (sscanf(e, "%d,%d", &ts, &ns) == 2) { ctx->pt_ts = ts; ctx->pt_ns = ns; } }
+    if (ctx->pt_ns < 2 || ctx->pt_ns > 8 || ctx->pt_ts < 1) return ctx->fail(RBSLAM_EARG, "RBSLAM_PT_CFG: need 2..8 slots");
+    if (const char *e = getenv("RBSLAM_PT_NW")) ctx->pt_nw = atoi(e) == 7 ? 7 : 15;
+    while (ctx->pt_ns > 2 && pt_smem_bytes(ctx->ld, ctx->pt_ts, ctx->pt_ns, ctx->pt_nw) + 2048 > ctx->smem_optin) --ctx->pt_ns;
+    if (pt_smem_bytes(ctx->ld, ctx->pt_ts, ctx->pt_ns, ctx->pt_nw) + 2048 > ctx->smem_optin)
+      return ctx->fail(RBSLAM_EARG, "packed streaming pass does not fit shared memory");
   } else if (small && cfg->kalman_variant != 2 && cfg->kalman_variant != 3 && !cfg->information_form) ctx->kpath = 0;
   else if (can_stream && cfg->kalman_variant != 3) ctx->kpath = 1;
   else if (d <= 4 && ctx->ld <= 2048) ctx->kpath = 2;
@@ -280,12 +296,23 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
     ctx->hs_p = (size_t)ctx->ld * 4; ctx->hs_a = 1; ctx->hs_c = 4;
     int ns = N >= 4096 ? 2 : std::max(1, std::min(8, (4 * 148 + N - 1) / N));
     if (const char *e = getenv("RBSLAM_NSPLIT")) ns = std::max(1, atoi(e));
-    if (const char *e = getenv("RBSLAM_STREAM_CFG")) { int kc = 4, st = 4; if (sscanf(e, "%d,%d", &kc, &st) == 2) ctx->stream_cfg = kc * 100 + st; }
     if (const char *e = getenv("RBSLAM_CTAS_PER_SM")) ctx->stream_ctas_per_sm = atoi(e);
     if (const char *e = getenv("RBSLAM_STREAM_HINTS")) ctx->stream_hints = atoi(e);
     int cw = ((M + ns - 1) / ns + 3) / 4 * 4;
-    if (ctx->sym_mma) cw = (cw + 7) / 8 * 8;   // 8-column MMA blocks
     ctx->nsplit = (M + cw - 1) / cw; ctx->cw = cw;
+    if (ctx->pt) {   // the nsplit items of a family stream panel ranges of (nearly) equal tile counts
+      const int nb = ctx->ld / 8;
+      ns = std::max(1, std::min(std::min(ns, RB_PT_MAXSPLIT), nb));
+      const size_t tot = pt_panel_off(nb, nb);
+      ctx->pt_psplit[0] = 0;
+      for (int sp = 1; sp < ns; ++sp) {
+        int p = ctx->pt_psplit[sp - 1] + 1;
+        while (p < nb - (ns - sp) && pt_panel_off(nb, p) < tot * sp / ns) ++p;
+        ctx->pt_psplit[sp] = p;
+      }
+      ctx->pt_psplit[ns] = nb;
+      ctx->nsplit = ns;
+    }
   } else {
     ctx->hs_p = (size_t)d * ctx->ldh; ctx->hs_a = ctx->ldh; ctx->hs_c = 1;
     ctx->nsplit = (M + 127) / 128; ctx->cw = (M + ctx->nsplit - 1) / ctx->nsplit;
@@ -331,8 +358,8 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
       RB_ALLOC(ctx->d_G4[b], (size_t)N * ctx->ld * 4);
       RB_ALLOC(ctx->d_KS4[b], (size_t)N * ctx->ld * 4);
     }
-    // the symmetric kernel keeps row-side and column-side partial sums in separate slots
-    RB_ALLOC(ctx->d_PHp, (size_t)N * ctx->nsplit * (ctx->sym ? 2 : 1) * ctx->ld * 4);
+    // the packed pass keeps one more partial slot (the column-side sums)
+    RB_ALLOC(ctx->d_PHp, (size_t)N * (ctx->nsplit + (ctx->pt ? 1 : 0)) * ctx->ld * 4);
     RB_ALLOC(ctx->d_fam, (size_t)17 * N + 8);   // + counters: n_fb, n_fa, work counters [2]
     ctx->use_fam = getenv("RBSLAM_NO_FAM") == nullptr;
   }
@@ -534,13 +561,22 @@ int rb_upload_inputs(rbslam_ctx *ctx, const rbslam_inputs *in, int K) {
     if ((rc = rb_h2d(ctx, ctx->d_Z, in->Z, sizeof(double) * ctx->nz * N * T * K))) return rc;
   }
   if (ctx->have_forced) {
+    for (size_t q = 0; q < (size_t)N * T * K; ++q) {   // used as indices on the device: check them here
+      if (q % ((size_t)N * T) < (size_t)N) continue;    // column t = 0 is unused
+      if (in->forced_ancestors[q] < 0 || in->forced_ancestors[q] >= N)
+        return ctx->fail(RBSLAM_EARG, "forced_ancestors out of range [0, N)");
+    }
     RB_ALLOC(ctx->d_forced, (size_t)N * T * K);
     if ((rc = rb_h2d(ctx, ctx->d_forced, in->forced_ancestors, sizeof(int) * (size_t)N * T * K))) return rc;
   }
   ctx->h_Uend.assign(K, 0.5);
   if (in->Uend) ctx->h_Uend.assign(in->Uend, in->Uend + K);
   ctx->h_forced_ak.clear();
-  if (in->forced_ak) ctx->h_forced_ak.assign(in->forced_ak, in->forced_ak + K);
+  if (in->forced_ak) {
+    for (int k = 0; k < K; ++k)
+      if (in->forced_ak[k] < 0 || in->forced_ak[k] >= N) return ctx->fail(RBSLAM_EARG, "forced_ak out of range [0, N)");
+    ctx->h_forced_ak.assign(in->forced_ak, in->forced_ak + K);
+  }
   return RBSLAM_OK;
 }
 
@@ -556,7 +592,8 @@ int rb_init_state(rbslam_ctx *ctx, bool info_form) {
   }
   k_fill_int_iota<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_slot[0], N);
   dim3 g(M, std::min(N, 4 * ctx->num_sms));
-  k_init_slabs<<<g, 128, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ctx->ld, M, N, ctx->d_P0, 0);
+  if (ctx->pt) k_init_slabs_pt<<<dim3(256, std::min(N, 4 * ctx->num_sms)), 64, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ctx->ld, M, N, ctx->d_P0);
+  else k_init_slabs<<<g, 128, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ctx->ld, M, N, ctx->d_P0, 0);
   const size_t tot = (size_t)M * N;
   k_init_xl<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_xl[0], M, N, ctx->d_x0lin, ctx->x0_cols);
   // xn(:, i) = x0_nonLin for all i -> history slot 0
@@ -629,11 +666,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
   sa.G4prev = ctx->d_G4[ctx->cg]; sa.KS4prev = ctx->d_KS4[ctx->cg]; sa.H4 = a.H; sa.PHp = ctx->d_PHp;
   const size_t smem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 8 * KC);
   auto kern = k_stream_pass<D, D, R2, KC, S>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
-    attr_done = true;
-  }
+  RB_OPTIN_SMEM(kern, ctx->smem_optin - 1024);
   if (smem > ctx->smem_optin - 1024) return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (ctx->smem_optin) / (smem + 2048)));
   if (ctx->stream_ctas_per_sm > 0) per_sm = ctx->stream_ctas_per_sm;
@@ -655,11 +688,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
     fb.cb = RB_CB; fb.kf = RB_KF;
     auto fkern = k_stream_fam<D, R2, KC, S, RB_CB>;
     const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 4 * KC * (1 + RB_CB));
-    static bool fattr_done = false;
-    if (!fattr_done) {
-      CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
-      fattr_done = true;
-    }
+    RB_OPTIN_SMEM(fkern, ctx->smem_optin - 1024);
     if (fsmem > ctx->smem_optin - 1024) return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
     const int fgrid = std::min(N * ctx->nsplit, ctx->num_sms);
     const int ngrp = ctx->item_group ? ctx->stream_groups : 1;   // no group tags: one pass over all families
@@ -712,18 +741,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
 }
 template <int D, int R2>
 static int launch_stream_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
-  // default (KC=8 columns per stage, S=2 stages) measured best on C4; see profiles/tuning_r1.md
-  if constexpr (D == 3) {   // the tuning configurations are instantiated for the C1/C4 family only
-    switch (ctx->stream_cfg) {
-      case 403: return launch_stream_cfg<D, R2, 4, 3>(ctx, a, resampled);
-      case 404: return launch_stream_cfg<D, R2, 4, 4>(ctx, a, resampled);
-      case 406: return launch_stream_cfg<D, R2, 4, 6>(ctx, a, resampled);
-      case 604: return launch_stream_cfg<D, R2, 6, 4>(ctx, a, resampled);
-      case 803: return launch_stream_cfg<D, R2, 8, 3>(ctx, a, resampled);
-      case 1202: return launch_stream_cfg<D, R2, 12, 2>(ctx, a, resampled);
-      default: break;
-    }
-  }
+  // KC = 8 columns per stage, S = 2 stages measured best on C4 (profiles/tuning_r1.md section 2)
   return launch_stream_cfg<D, R2, 8, 2>(ctx, a, resampled);
 }
 template <int D>
@@ -738,16 +756,16 @@ static int launch_stream(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   }
 }
 
-// symmetric streaming path (kalman_variant 4): lower triangle only, k_stream_fam_sym
-template <int D, int R2, int KC, int S>
-static int launch_sym_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
-  constexpr int CB = RB_SYM_CB;
+// packed symmetric slabs (kalman_variant 7): k_stream_fam_pt on the fp64 tensor cores
+template <int NW, int MAXQ>
+static int launch_pt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  constexpr int CB = RB_PT_CB;
   const int N = ctx->N, ld = ctx->ld;
-  StreamArgs sa;
-  sa.hints = ctx->sym_flags; sa.gk_by_particle = 0;
-  sa.M = ctx->M; sa.ld = ld; sa.cw = ctx->cw; sa.nsplit = ctx->nsplit; sa.slab = ctx->slab;
-  sa.P = ctx->d_P; sa.src_slot = a.src_slot; sa.dst_slot = a.dst_slot; sa.anc = a.ai;
-  sa.G4prev = ctx->d_G4[ctx->cg]; sa.KS4prev = ctx->d_KS4[ctx->cg]; sa.H4 = a.H; sa.PHp = ctx->d_PHp;
+  PtArgs pa;
+  pa.M = ctx->M; pa.ld = ld; pa.nb = ld / 8; pa.nsplit = ctx->nsplit; pa.ts = ctx->pt_ts; pa.ns = ctx->pt_ns;
+  for (int q = 0; q <= RB_PT_MAXSPLIT; ++q) pa.psplit[q] = ctx->pt_psplit[std::min(q, ctx->nsplit)];
+  pa.slab = ctx->slab; pa.P = ctx->d_P; pa.dst_slot = a.dst_slot;
+  pa.G4prev = ctx->d_G4[ctx->cg]; pa.KS4prev = ctx->d_KS4[ctx->cg]; pa.H4 = a.H; pa.PHp = ctx->d_PHp;
   int *fm = ctx->d_fam;
   FamBuildArgs fb;
   fb.n_items = N; fb.n_slabs = N; fb.n_items_dev = nullptr;
@@ -761,22 +779,9 @@ static int launch_sym_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) 
   fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
   fb.work_ctr = cnts + 2;
   fb.cb = CB; fb.kf = 2 * CB;
-  auto fkern = k_stream_fam_sym<D, R2, KC, S, CB>;
-  const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 4 * KC * (1 + CB));
-  static bool fattr_done = false;
-  if (!fattr_done) {
-    cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, fkern));
-    CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(ctx->smem_optin - fa.sharedSizeBytes)));
-    fattr_done = true;
-  }
-  {
-    cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, fkern));
-    if (fsmem + fa.sharedSizeBytes > ctx->smem_optin)
-      return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
-  }
+  auto fkern = k_stream_fam_pt<NW, MAXQ>;
+  const size_t fsmem = pt_smem_bytes(ld, ctx->pt_ts, ctx->pt_ns, NW);
+  RB_OPTIN_SMEM(fkern, ctx->smem_optin - 1024);
   const int fgrid = std::min(N * ctx->nsplit, ctx->num_sms);
   const int ngrp = ctx->item_group ? ctx->stream_groups : 1;
   for (int grp = 0; grp < ngrp; ++grp) {
@@ -789,125 +794,40 @@ static int launch_sym_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) 
     k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
     ctx->launches += 1;
     for (int phase = 0; phase < 2; ++phase) {
-      if (phase == 0 && !resampled) continue;
+      if (phase == 0 && !resampled) continue;   // surplus families exist only after resampling
       FamLists fl;
       const int *base = phase == 0 ? la : lb;
       fl.n_fam = cnts + (phase == 0 ? 1 : 0);
       fl.work_counter = cnts + 2 + phase;
       fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
       fl.child = base + 4 * (size_t)N;
-      fkern<<<fgrid, RB_SYM_THREADS, fsmem, ctx->stream>>>(sa, fl);
+      fkern<<<fgrid, 32 * (NW + 1), fsmem, ctx->stream>>>(pa, fl);
       ctx->launches += 1;
     }
   }
   Innov4Args ia;
-  ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = 2 * ctx->nsplit; ia.PHp = ctx->d_PHp; ia.H4 = a.H;
-  ia.xl_old = a.xl_old; ia.anc = a.ai; ia.xl_new = a.xl_new;
-  ia.G4new = ctx->d_G4[1 - ctx->cg]; ia.KS4new = ctx->d_KS4[1 - ctx->cg];
-  ia.y_t = a.y_t; ia.R = a.R; ia.jitter = a.jitter; ia.logw = a.logw; ia.status = a.status; ia.t = a.t;
-  k_innov4<D><<<N, 128, sizeof(double) * 4 * ld, ctx->stream>>>(ia);
-  ctx->launches += 1;
-  ctx->cg ^= 1;
-  ctx->pending = true;
-  return RBSLAM_OK;
-}
-template <int D, int R2>
-static int launch_sym_r(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
-  if constexpr (D == 3) {   // tuning knob RBSLAM_SYM_CFG="KC,S"
-    switch (ctx->sym_cfg) {
-      case 404: return launch_sym_cfg<D, R2, 4, 4>(ctx, a, resampled);
-      case 406: return launch_sym_cfg<D, R2, 4, 6>(ctx, a, resampled);
-      case 803: return launch_sym_cfg<D, R2, 8, 3>(ctx, a, resampled);
-      default: break;
-    }
-  }
-  return launch_sym_cfg<D, R2, 8, 2>(ctx, a, resampled);
-}
-template <int D>
-static int launch_sym(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
-  return ctx->ld / 2 <= RB_SYM_THREADS ? launch_sym_r<D, 1>(ctx, a, resampled) : launch_sym_r<D, 2>(ctx, a, resampled);
-}
-
-// symmetric pass on the fp64 tensor cores (kalman_variant 5): k_stream_fam_symt
-template <int D, int MAXQ, bool PIPE>
-static int launch_symt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
-  constexpr int KC = 8, S = 2, CB = 2;
-  const int N = ctx->N, ld = ctx->ld;
-  StreamArgs sa;
-  sa.hints = 0; sa.gk_by_particle = 0;
-  sa.M = ctx->M; sa.ld = ld; sa.cw = ctx->cw; sa.nsplit = ctx->nsplit; sa.slab = ctx->slab;
-  sa.P = ctx->d_P; sa.src_slot = a.src_slot; sa.dst_slot = a.dst_slot; sa.anc = a.ai;
-  sa.G4prev = ctx->d_G4[ctx->cg]; sa.KS4prev = ctx->d_KS4[ctx->cg]; sa.H4 = a.H; sa.PHp = ctx->d_PHp;
-  int *fm = ctx->d_fam;
-  FamBuildArgs fb;
-  fb.n_items = N; fb.n_slabs = N; fb.n_items_dev = nullptr;
-  fb.src_slot = a.src_slot; fb.dst_slot = a.dst_slot; fb.anc = a.ai;
-  fb.s_cnt = fm; fb.s_keeper = fm + N; fb.s_cursor = fm + 2 * (size_t)N; fb.s_first = fm + 3 * (size_t)N;
-  fb.s_fid = fm + 4 * (size_t)N; fb.s_xoff = fm + 5 * (size_t)N; fb.s_xfam = fm + 6 * (size_t)N;
-  int *lb = fm + 7 * (size_t)N, *la = fm + 12 * (size_t)N, *cnts = fm + 17 * (size_t)N;
-  fb.fb_src = lb; fb.fb_anc = lb + N; fb.fb_first = lb + 2 * (size_t)N; fb.fb_cnt = lb + 3 * (size_t)N;
-  fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
-  fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
-  fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
-  fb.work_ctr = cnts + 2;
-  fb.cb = CB; fb.kf = 2 * CB;
-  // PIPE: kalman_variant 6 (producer warp, six-slot ring of 8 x 512 stages), else variant 5
-  void (*fkern)(StreamArgs, FamLists);
-  if constexpr (PIPE) fkern = k_stream_fam_symp<MAXQ>; else fkern = k_stream_fam_symt<MAXQ>;
-  const size_t fsmem = PIPE ? sizeof(double) * (size_t)RB_SYMP_SLOTS * RB_SYMP_SLOT_DOUBLES
-                            : sizeof(double) * (size_t)S * ((size_t)KC * (ld + 2) + 4 * KC * (1 + CB));
-  const int fthreads = PIPE ? RB_SYMP_THREADS : RB_SYMT_THREADS;
-  cudaFuncAttributes fa;
-  CK(cudaFuncGetAttributes(&fa, fkern));
-  static bool fattr_done = false;
-  if (!fattr_done) {
-    CK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(ctx->smem_optin - fa.sharedSizeBytes)));
-    fattr_done = true;
-  }
-  if (fsmem + fa.sharedSizeBytes > ctx->smem_optin)
-    return ctx->fail(RBSLAM_EARG, "streaming stage ring does not fit shared memory");
-  const int fgrid = std::min(N * ctx->nsplit, ctx->num_sms);
-  const int ngrp = ctx->item_group ? ctx->stream_groups : 1;
-  for (int grp = 0; grp < ngrp; ++grp) {
-    if (grp > 0 && ctx->group_hook) {
-      int rch = ctx->group_hook(ctx, grp);
-      if (rch) return rch;
-    }
-    fb.item_group = ngrp > 1 ? ctx->item_group : nullptr;
-    fb.group = grp;
-    k_build_families<<<1, 1024, 0, ctx->stream>>>(fb);
-    ctx->launches += 1;
-    for (int phase = 0; phase < 2; ++phase) {
-      if (phase == 0 && !resampled) continue;
-      FamLists fl;
-      const int *base = phase == 0 ? la : lb;
-      fl.n_fam = cnts + (phase == 0 ? 1 : 0);
-      fl.work_counter = cnts + 2 + phase;
-      fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
-      fl.child = base + 4 * (size_t)N;
-      fkern<<<fgrid, fthreads, fsmem, ctx->stream>>>(sa, fl);
-      ctx->launches += 1;
-    }
-  }
-  Innov4Args ia;
-  ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = 2 * ctx->nsplit; ia.PHp = ctx->d_PHp; ia.H4 = a.H;
+  ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = ctx->nsplit + 1; ia.PHp = ctx->d_PHp; ia.H4 = a.H;
   ia.xl_old = a.xl_old; ia.anc = a.ai; ia.xl_new = a.xl_new;
   ia.G4new = ctx->d_G4[1 - ctx->cg]; ia.KS4new = ctx->d_KS4[1 - ctx->cg];
   ia.y_t = a.y_t; ia.R = a.R; ia.jitter = a.jitter; ia.logw = a.logw; ia.status = a.status; ia.t = a.t;
   ia.G4prev = ctx->d_G4[ctx->cg]; ia.KS4prev = ctx->d_KS4[ctx->cg];   // the products used the slab before its downdate
-  k_innov4<D><<<N, 128, sizeof(double) * 4 * ld, ctx->stream>>>(ia);
+  const size_t ism = sizeof(double) * 4 * ld;
+  switch (ctx->d) {
+    case 1: k_innov4<1><<<N, 128, ism, ctx->stream>>>(ia); break;
+    case 2: k_innov4<2><<<N, 128, ism, ctx->stream>>>(ia); break;
+    case 3: k_innov4<3><<<N, 128, ism, ctx->stream>>>(ia); break;
+    default: k_innov4<4><<<N, 128, ism, ctx->stream>>>(ia); break;
+  }
   ctx->launches += 1;
   ctx->cg ^= 1;
   ctx->pending = true;
   return RBSLAM_OK;
 }
-template <int D>
-static int launch_symt(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
-  // MAXQ = row blocks per consumer warp: 8 warps (variant 5) or 7 (variant 6) share ld / 8 blocks
-  if (ctx->sym_pipe)
-    return ctx->ld / 8 <= 72 ? launch_symt_q<D, 11, true>(ctx, a, resampled) : launch_symt_q<D, 20, true>(ctx, a, resampled);
-  return ctx->ld / 8 <= 72 ? launch_symt_q<D, 9, false>(ctx, a, resampled) : launch_symt_q<D, 17, false>(ctx, a, resampled);
+static int launch_pt(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
+  // MAXQ = row blocks per consumer warp: NW warps share ld / 8 blocks
+  const int nb = ctx->ld / 8;
+  if (ctx->pt_nw == 7) return nb <= 70 ? launch_pt_q<7, 10>(ctx, a, resampled) : launch_pt_q<7, 20>(ctx, a, resampled);
+  return nb <= 75 ? launch_pt_q<15, 5>(ctx, a, resampled) : launch_pt_q<15, 9>(ctx, a, resampled);
 }
 
 // apply the deferred downdate to every slab (before the state is read out as a whole)
@@ -916,6 +836,9 @@ int rb_flush_pending(rbslam_ctx *ctx) {
   const int N = ctx->N, M = ctx->M, ld = ctx->ld;
   dim3 g(std::min(M, 64), N);
   const double *G4 = ctx->d_G4[ctx->cg], *KS4 = ctx->d_KS4[ctx->cg];
+  if (ctx->pt) {
+    k_apply_pending_pt<<<dim3(std::min(ld / 8, 64), N), 256, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ld, ctx->d_slot[ctx->cs], G4, KS4);
+  } else
   switch (ctx->d) {
     case 1: k_apply_pending<1><<<g, 256, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ld, M, ctx->d_slot[ctx->cs], G4, KS4); break;
     case 2: k_apply_pending<2><<<g, 256, 0, ctx->stream>>>(ctx->d_P, ctx->slab, ld, M, ctx->d_slot[ctx->cs], G4, KS4); break;
@@ -959,21 +882,8 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled) {
                                                        ctx->d_counts + phase);
       ctx->launches += 1;
     }
-  } else if (ctx->kpath == 1 && ctx->sym_mma) {
-    int rc;
-    switch (d) {
-      case 1: rc = launch_symt<1>(ctx, a, resampled); break;
-      case 2: rc = launch_symt<2>(ctx, a, resampled); break;
-      default: rc = launch_symt<3>(ctx, a, resampled); break;
-    }
-    if (rc) return rc;
-  } else if (ctx->kpath == 1 && ctx->sym) {
-    int rc;
-    switch (d) {
-      case 1: rc = launch_sym<1>(ctx, a, resampled); break;
-      case 2: rc = launch_sym<2>(ctx, a, resampled); break;
-      default: rc = launch_sym<3>(ctx, a, resampled); break;
-    }
+  } else if (ctx->kpath == 1 && ctx->pt) {
+    int rc = launch_pt(ctx, a, resampled);
     if (rc) return rc;
   } else if (ctx->kpath == 1) {
     int rc;
@@ -1159,7 +1069,7 @@ extern "C" int rbslam_filter_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
                                             ctx->d_w, iw, means, Pmax, Pmean,
                                             (ctx->kpath == 1 && ctx->pending) ? ctx->d_G4[ctx->cg] : nullptr,
                                             (ctx->kpath == 1 && ctx->pending) ? ctx->d_KS4[ctx->cg] : nullptr,
-                                            ctx->sym ? 1 : 0);
+                                            ctx->layout);
     ctx->launches += 1;
   }
   CK(cudaGetLastError());
@@ -1234,7 +1144,7 @@ int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host) {
   for (int i0 = 0; i0 < N && !rc; i0 += chunk) {
     const int cnt = std::min(chunk, N - i0);
     k_pack_slabs<<<dim3(M, cnt), 128, 0, ctx->stream>>>(M, ctx->ld, ctx->slab, slabs, ctx->d_slot[ctx->cs], i0, tmp,
-                                                        (ctx->sym && slabs == ctx->d_P) ? 1 : 0);
+                                                        slabs == ctx->d_P ? ctx->layout : RB_LAYOUT_FULL);
     ctx->launches += 1;
     rc = rb_d2h(ctx, host + (size_t)i0 * per, tmp, per * cnt * 8);
   }
@@ -1245,6 +1155,7 @@ int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host) {
 extern "C" int rbslam_read_particles(rbslam_ctx *ctx, double *xn, double *xl, double *P, double *logw,
                                      double *w, int32_t *ai) {
   if (!ctx) return RBSLAM_EARG;
+  if (ctx->shard_ws) return ctx->fail(RBSLAM_EARG, "read_particles is not available on a sharded context (state lives on several GPUs)");
   CK(cudaSetDevice(ctx->cfg.device));
   const int N = ctx->N, M = ctx->M, n = ctx->n;
   const int tl = std::max(ctx->t - 1, 0) % ctx->T_hist;   // last completed step

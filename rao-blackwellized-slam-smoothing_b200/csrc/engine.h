@@ -42,13 +42,14 @@ struct rbslam_ctx {
   // sibling fusion (family_kernels.cuh): scratch [7][N], main/surplus family lists [2][5][N], counters
   int *d_fam = nullptr;
   bool use_fam = true;
-  bool sym = false;          // kalman_variant 4: only the lower triangle of every slab is streamed / valid
-  bool sym_mma = false;      // kalman_variant 5, 6: the symmetric pass on the fp64 tensor cores (k_stream_fam_symt)
-  bool sym_pipe = false;     // kalman_variant 6: producer-warp / deep-ring version (k_stream_fam_symp), unverified
-  int sym_flags = 0;         // RBSLAM_SYM_FLAGS: 2 = copy whole columns (diagnostic: full traffic, triangle arithmetic)
-  int sym_cfg = 802;         // RBSLAM_SYM_CFG="KC,S"
+  // kalman_variant 7: packed symmetric tile slabs (packed_kernels.cuh)
+  bool pt = false;
+  int layout = 0;            // RB_LAYOUT_FULL / _SYM / _PT: how element (r,c) of a slab is stored
+  int pt_ts = 48, pt_ns = 4; // tiles per stage, ring slots (RBSLAM_PT_CFG="TS,NS")
+  int pt_nw = 15;            // consumer warps per CTA: 15 (128 registers each) or 7 (255) (RBSLAM_PT_NW)
+  int pt_psplit[9] = {0};    // panel ranges of the nsplit items per family
   const int *item_group = nullptr;   // sharded engine: work group of each local item (see stream_groups)
-  int stream_cfg = 802, stream_ctas_per_sm = 0, stream_hints = 0;   // tuning knobs (env)
+  int stream_ctas_per_sm = 0, stream_hints = 0;   // tuning knobs (env)
   size_t hs_p = 0; int hs_a = 0, hs_c = 1;   // layout of d_H: H_i(a,c) at i*hs_p + a*hs_a + c*hs_c
   double *d_logw = nullptr, *d_w = nullptr, *d_wc = nullptr;
   double *d_Xhist = nullptr;     // [T_hist][N][n]

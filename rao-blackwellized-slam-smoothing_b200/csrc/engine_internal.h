@@ -30,7 +30,17 @@ static inline int dev_alloc(rbslam_ctx *c, T **p, size_t count) {
     }                                                          \
   } while (0)
 
-
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per DEVICE,
+// so the "already done" flag is kept per (call site = kernel instantiation, device ordinal).
+#define RB_OPTIN_SMEM(kern, bytes)                                                              \
+  do {                                                                                          \
+    static bool done__[64] = {false};                                                           \
+    const int dv__ = ctx->cfg.device & 63;                                                      \
+    if (!done__[dv__]) {                                                                        \
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      done__[dv__] = true;                                                                      \
+    }                                                                                           \
+  } while (0)
 
 int rb_h2d(rbslam_ctx *ctx, void *dst, const void *src, size_t bytes);
 int rb_d2h(rbslam_ctx *ctx, void *dst, const void *src, size_t bytes);

@@ -5,6 +5,7 @@
 #include <cstring>
 #include "engine_internal.h"
 #include "step_kernels.cuh"
+#include "packed_kernels.cuh"
 
 using namespace rb;
 
@@ -175,6 +176,7 @@ extern "C" int rbslam_op_kalman_update(rbslam_ctx *ctx, int32_t N, const double 
                                        const double *y_t, const double *R, double jitter, double *xl,
                                        double *P, double *logw) {
   if (!ctx || !y_t || !R || !xl || !P || !logw) return RBSLAM_EARG;
+  if (ctx->shard_ws) return ctx->fail(RBSLAM_EARG, "op_kalman_update is not available on a sharded context");
   if (N != ctx->N) return ctx->fail(RBSLAM_EARG, "op_kalman_update: N must equal the context's N");
   if (!H && !xn) return ctx->fail(RBSLAM_EARG, "op_kalman_update: need H or xn");
   CK(cudaSetDevice(ctx->cfg.device));
@@ -197,7 +199,8 @@ extern "C" int rbslam_op_kalman_update(rbslam_ctx *ctx, int32_t N, const double 
     for (int i0 = 0; i0 < N; i0 += chunk) {
       const int cnt = std::min(chunk, N - i0);
       if ((rc = rb_h2d(ctx, tmp, P + (size_t)i0 * per, per * cnt * 8))) return rc;
-      k_op_unpack<<<dim3(M, cnt), 128, 0, ctx->stream>>>(M, ctx->ld, ctx->slab, ctx->d_P + (size_t)i0 * ctx->slab, tmp);
+      if (ctx->pt) k_unpack_slabs_pt<<<dim3(ctx->ld / 8, cnt), 256, 0, ctx->stream>>>(M, ctx->ld, ctx->slab, ctx->d_P + (size_t)i0 * ctx->slab, tmp);
+      else k_op_unpack<<<dim3(M, cnt), 128, 0, ctx->stream>>>(M, ctx->ld, ctx->slab, ctx->d_P + (size_t)i0 * ctx->slab, tmp);
       CK(cudaStreamSynchronize(ctx->stream));
     }
   }

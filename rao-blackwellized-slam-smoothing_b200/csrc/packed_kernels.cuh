@@ -1,0 +1,370 @@
+// Packed symmetric covariance slabs and their streaming Kalman pass (kalman_variant 7).
+//
+// P_i and the downdate K SS K' (src/particleFilter.m:198) are symmetric, so half of a full
+// [ld x M] slab is redundant.  Layout "PT" (packed tiles) stores the lower block triangle only,
+// as 8x8 tiles:
+//
+//   nb = ld / 8 row blocks; panel p = the tiles (j, p), j = p .. nb-1, of block column p;
+//   panels follow each other, tiles inside a panel are ordered by j:
+//       tile index  tix(j, p) = p nb - p (p - 1) / 2 + (j - p),       64 doubles per tile
+//   -> a slab is ONE linear stream of nb (nb + 1) / 2 tiles (4.29 MB at M = 1027 instead of
+//   8.52 MB).  The diagonal tile (p, p) keeps all 64 entries (both triangles evolve as in the
+//   reference, which never symmetrises P); for j > p the tile holds P(8j.., 8p..) and stands
+//   for its mirror image as well.
+//   Inside a tile element (r, c) sits at  8 sigma(r) + (c ^ (r & 4)),  sigma = 0 1 3 2 4 5 7 6:
+//   the two fragment reads the tensor-core pass needs -- (row g, columns 2tg, 2tg+1) as one
+//   16-byte access and (rows 2tg, 2tg+1, column g) as two 8-byte accesses -- are both free of
+//   shared-memory bank conflicts, and the first one is also the layout of the store: a warp
+//   writes an updated tile as one contiguous 512-byte block.
+//
+// The pass (k_stream_fam_pt) is the sibling-fused, deferred-downdate pass of family_kernels.cuh
+// re-done on this layout:
+//   * data movement: a dedicated producer warp streams the slab as uniform stages of TS tiles
+//     (one exactly-sized cp.async.bulk each, whatever panel boundaries it crosses) into an
+//     NS-deep ring; full/empty mbarriers per slot, no block-wide barrier in the steady state;
+//   * arithmetic: mma.sync.m8n8k4.f64 per tile T (n = (sibling, measurement row) = 2 x 4):
+//       row side   PHrow(8j.., n) += T H_n(8p..)      2 DMMA, A operand = the loaded fragment
+//       col side   PHcol(8p.., n) += T' H_n(8j..)     2 DMMA, A operand = the transposed read
+//       downdate   T -= KS(8j.., :) G(8p.., :)'       1 DMMA, accumulator = the fragment
+//     and one 16-byte store per sibling.  The products use the tile BEFORE its pending
+//     downdate; k_innov4 completes them (Innov4Args::G4prev), exactly as kalman_variant 5 did;
+//   * warp w owns the row blocks j = w (mod NW): its row-side accumulators and its KS fragments
+//     stay in registers for the whole pass; per-batch operands (G of the ancestor, the
+//     siblings' H in fragment order) live in shared memory; the column-side tiles of the
+//     warps are added in fixed order once per panel behind a named barrier.
+// HBM traffic per particle-step: half of k_stream_fam's (4.3 MB read per pass over a family's slab,
+// 4.3 MB written per particle at M = 1027).
+#pragma once
+#include "family_kernels.cuh"
+
+namespace rb {
+
+enum { RB_LAYOUT_FULL = 0, RB_LAYOUT_SYM = 1, RB_LAYOUT_PT = 2 };
+
+__host__ __device__ __forceinline__ size_t pt_panel_off(int nb, int p) {   // first tile of panel p
+  return (size_t)p * nb - (size_t)p * (p - 1) / 2;
+}
+__host__ __device__ __forceinline__ int pt_pos(int r, int c) {             // inside a tile
+  return 8 * (r ^ ((r >> 1) & 1)) + (c ^ (r & 4));
+}
+__host__ __device__ __forceinline__ size_t pt_slab_doubles(int ld) {
+  const int nb = ld >> 3;
+  return (size_t)nb * (nb + 1) / 2 * 64;
+}
+// offset of the stored copy of element (r, c) in a slab of the given layout
+__host__ __device__ __forceinline__ size_t slab_elem(int layout, int ld, int r, int c) {
+  if (layout == RB_LAYOUT_FULL) return (size_t)r + (size_t)c * ld;
+  if (layout == RB_LAYOUT_SYM) return (size_t)(r > c ? r : c) + (size_t)(r > c ? c : r) * ld;
+  int bj = r >> 3, bp = c >> 3, rr = r & 7, cc = c & 7;
+  if (bj < bp) { int t = bj; bj = bp; bp = t; t = rr; rr = cc; cc = t; }
+  return (pt_panel_off(ld >> 3, bp) + (size_t)(bj - bp)) * 64 + pt_pos(rr, cc);
+}
+// (row, column) of the pending-downdate factors that belong to the stored copy of (r, c)
+__host__ __device__ __forceinline__ void slab_elem_rc(int layout, int r, int c, int &rs, int &cs) {
+  rs = r; cs = c;
+  if (layout == RB_LAYOUT_SYM && r < c) { rs = c; cs = r; }
+  if (layout == RB_LAYOUT_PT && (r >> 3) < (c >> 3)) { rs = c; cs = r; }
+}
+
+// ---------------------------------------------------------------------------
+// layout-aware helpers (initialisation, read-out)
+// ---------------------------------------------------------------------------
+// P[slot] = P0 for every slab; grid (tile chunk, particle chunk)
+__global__ void k_init_slabs_pt(double *__restrict__ P, size_t slab, int ld, int M, int N,
+                                const double *__restrict__ P0) {
+  const int nb = ld >> 3;
+  const int ntile = nb * (nb + 1) / 2;
+  for (int i = blockIdx.y; i < N; i += gridDim.y) {
+    double *dst = P + (size_t)i * slab;
+    for (int tl = blockIdx.x; tl < ntile; tl += gridDim.x) {
+      // invert tl -> (j, p): panels are short, a linear walk from an estimate is cheap
+      int p = (int)(((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * tl)) * 0.5);
+      while (p > 0 && pt_panel_off(nb, p) > (size_t)tl) --p;
+      while (pt_panel_off(nb, p + 1) <= (size_t)tl) ++p;
+      const int j = p + (tl - (int)pt_panel_off(nb, p));
+      for (int e = threadIdx.x; e < 64; e += blockDim.x) {
+        const int r = 8 * j + (e >> 3), c = 8 * p + (e & 7);
+        dst[(size_t)tl * 64 + pt_pos(e >> 3, e & 7)] = (r < M && c < M) ? P0[r + (size_t)c * M] : 0.0;
+      }
+    }
+  }
+}
+
+// dense [M x M x cnt] (logical order) -> packed slabs (rbslam_op_kalman_update)
+__global__ void k_unpack_slabs_pt(int M, int ld, size_t slab, double *__restrict__ P, const double *__restrict__ in) {
+  const int nb = ld >> 3, p = blockIdx.x, i = blockIdx.y;
+  double *dst = P + (size_t)i * slab + pt_panel_off(nb, p) * 64;
+  const double *src = in + (size_t)i * M * M;
+  for (int idx = threadIdx.x; idx < (nb - p) * 64; idx += blockDim.x) {
+    const int tl = idx >> 6, e = idx & 63;
+    const int r = 8 * (p + tl) + (e >> 3), c = 8 * p + (e & 7);
+    dst[(size_t)tl * 64 + pt_pos(e >> 3, e & 7)] = (r < M && c < M) ? src[r + (size_t)c * M] : 0.0;
+  }
+}
+
+// apply (and thereby clear) the pending downdate of every stored element: P -= KS G'
+__global__ void __launch_bounds__(256)
+k_apply_pending_pt(double *__restrict__ P, size_t slab, int ld, const int *__restrict__ slot,
+                   const double *__restrict__ G4, const double *__restrict__ KS4) {
+  const int nb = ld >> 3, i = blockIdx.y;
+  double *Pi = P + (size_t)slot[i] * slab;
+  const double *Gi = G4 + (size_t)i * ld * 4, *KSi = KS4 + (size_t)i * ld * 4;
+  for (int p = blockIdx.x; p < nb; p += gridDim.x) {
+    double *pan = Pi + pt_panel_off(nb, p) * 64;
+    for (int idx = threadIdx.x; idx < (nb - p) * 64; idx += blockDim.x) {
+      const int tl = idx >> 6, e = idx & 63;
+      const int r = 8 * (p + tl) + (e >> 3), c = 8 * p + (e & 7);
+      double v = pan[(size_t)tl * 64 + pt_pos(e >> 3, e & 7)];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v = fma(-KSi[(size_t)r * 4 + b], Gi[(size_t)c * 4 + b], v);
+      pan[(size_t)tl * 64 + pt_pos(e >> 3, e & 7)] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the streaming pass
+// ---------------------------------------------------------------------------
+#define RB_PT_CB 2                          // siblings per pass: n = 2 x 4 output columns
+#define RB_PT_MAXSPLIT 8
+
+struct PtArgs {
+  int M, ld, nb, nsplit;
+  int ts, ns;                     // tiles per stage, ring slots
+  int psplit[RB_PT_MAXSPLIT + 1]; // item sp streams the panels [psplit[sp], psplit[sp+1])
+  size_t slab;                    // doubles per slab
+  double *P;
+  const int *dst_slot;            // [N] slab of the particle
+  const double *G4prev;           // [N][ld][4] pending gain of the ancestor  (G(c,b))
+  const double *KS4prev;          // [N][ld][4] pending K*SS of the ancestor  (KS(r,b))
+  const double *H4;               // [N][ld][4] measurement Jacobian of the particle (H(a,c))
+  double *PHp;                    // [N][nsplit + 1][ld][4]: row-side partials per item, then the column side
+};
+
+struct PtDesc {   // what a ring slot holds; item < 0: no more work
+  int item, b0, t0, nt, p, j;
+};
+
+static inline size_t pt_smem_bytes(int ld, int ts, int ns, int nw) {
+  const int nb = ld >> 3;
+  return (size_t)ns * ts * 512 + (size_t)ld * 32 + (size_t)nb * 32 * 16 + (size_t)2 * nw * 64 * 8;
+}
+
+// NW consumer warps + one producer warp; NW + 1 is a multiple of 4 (registers are allocated to
+// warps in groups of four: 16 warps x 128 registers or 8 warps x 255)
+template <int NW, int MAXQ>
+__global__ void __launch_bounds__(32 * (NW + 1), 1)
+k_stream_fam_pt(PtArgs a, FamLists f) {
+  constexpr int CB = RB_PT_CB;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ __align__(8) uint64_t full[8], empty[8];
+  __shared__ PtDesc s_desc[8];
+  __shared__ int s_psplit[RB_PT_MAXSPLIT + 1];   // (a parameter array indexed at run time would live in local memory)
+  const int ld = a.ld, nb = a.nb, TS = a.ts, NS = a.ns;
+  double *ring = reinterpret_cast<double *>(smraw);                       // [NS][TS][64]
+  double *s_G = ring + (size_t)NS * TS * 64;                              // [ld][4] verbatim
+  double2 *s_bC = reinterpret_cast<double2 *>(s_G + (size_t)ld * 4);      // [nb][32] fragment order
+  double *s_colp = reinterpret_cast<double *>(s_bC + (size_t)nb * 32);    // [2][NW][64]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int n_items = (*f.n_fam) * a.nsplit;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    mbar_fence_init();
+#pragma unroll
+    for (int s = 0; s <= RB_PT_MAXSPLIT; ++s) s_psplit[s] = a.psplit[s];
+  }
+  __syncthreads();
+
+  if (wid == NW) {
+    // ================= producer warp: one lane walks item -> batch -> stage ==============
+    if (lane != 0) return;
+    int it = atomicAdd(f.work_counter, 1);
+    int b = 0;
+    bool fresh = true;         // (it, b) just changed: (re)start the tile walk
+    int t_cur = 0, t_end = 0, p = 0, j = 0;
+    int slot = 0, round = 0;
+    for (;;) {
+      if (round > 0) mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));   // consumers are done with it
+      if (it >= n_items) {     // terminal descriptor: every consumer warp sees it in order
+        s_desc[slot].item = -1;
+        mbar_arrive(&full[slot]);
+        break;
+      }
+      const int fam = it / a.nsplit, sp = it % a.nsplit;
+      if (fresh) {
+        p = s_psplit[sp]; j = p;
+        t_cur = (int)pt_panel_off(nb, p); t_end = (int)pt_panel_off(nb, s_psplit[sp + 1]);
+        fresh = false;
+      }
+      const int nt = min(TS, t_end - t_cur);
+      PtDesc d;
+      d.item = it; d.b0 = b * CB; d.t0 = t_cur; d.nt = nt; d.p = p; d.j = j;
+      s_desc[slot] = d;
+      mbar_expect_tx(&full[slot], (uint32_t)nt * 512u);
+      tma_load_1d(ring + (size_t)slot * TS * 64, a.P + (size_t)f.src[fam] * a.slab + (size_t)t_cur * 64,
+                  (uint32_t)nt * 512u, &full[slot]);
+      // advance (p, j) by nt tiles
+      t_cur += nt;
+      int left = nt;
+      while (left > 0) {
+        const int seg = min(left, nb - j);
+        left -= seg; j += seg;
+        if (j == nb) { ++p; j = p; }
+      }
+      if (t_cur >= t_end) {
+        fresh = true;
+        const int nbat = (f.cnt[fam] + CB - 1) / CB;
+        if (++b >= nbat) { b = 0; it = atomicAdd(f.work_counter, 1); }
+      }
+      if (++slot == NS) { slot = 0; ++round; }
+    }
+    return;
+  }
+
+  // ================= consumer warps ======================================================
+  // fragment offsets inside a tile: (row g, cols 2tg..2tg+1) and (rows 2tg, 2tg+1, col g)
+  const int offC = pt_pos(g, 2 * tg), offT0 = pt_pos(2 * tg, g), offT1 = pt_pos(2 * tg + 1, g);
+  int cur_item = -1, cur_b0 = -1, cur_fam = -1;
+  int sp = 0, nv = 0;
+  int child[CB] = {-1, -1};
+  double *Pd[CB] = {nullptr, nullptr};
+  double acc[MAXQ][2], ksA[MAXQ];
+#pragma unroll
+  for (int qq = 0; qq < MAXQ; ++qq) { acc[qq][0] = acc[qq][1] = 0.0; ksA[qq] = 0.0; }
+  double col0 = 0.0, col1 = 0.0, gB = 0.0, hB0 = 0.0, hB1 = 0.0;
+  int n_panel = 0;   // panels finished so far (parity selects the s_colp buffer)
+  int cur_p = -1;    // panel whose gB / hB are loaded
+
+  auto flush_rows = [&]() {   // row-side slot of the batch that just ended: lane holds PHrow(8j+g, n = 2tg, 2tg+1)
+    const int s = tg >> 1;
+    if (s < nv) {
+      const int ch = s == 0 ? child[0] : child[1];
+      double *out = a.PHp + ((size_t)ch * (a.nsplit + 1) + sp) * ld * 4;
+#pragma unroll
+      for (int qq = 0; qq < MAXQ; ++qq) {
+        const int jj = wid + NW * qq;
+        if (jj < nb)
+          *reinterpret_cast<double2 *>(out + (size_t)(8 * jj + g) * 4 + 2 * (tg & 1)) = make_double2(acc[qq][0], acc[qq][1]);
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) acc[qq][0] = acc[qq][1] = 0.0;
+  };
+
+  int slot = 0, round = 0;
+  for (;;) {
+    mbar_wait(&full[slot], (uint32_t)(round & 1));
+    const PtDesc d = s_desc[slot];
+    if (d.item < 0) break;
+    if (d.item != cur_item || d.b0 != cur_b0) {   // a new batch starts (uniform over the consumers)
+      if (cur_item >= 0) flush_rows();
+      const int fam = d.item / a.nsplit;
+      sp = d.item % a.nsplit;
+      const int cnt = f.cnt[fam], first = f.first[fam];
+      nv = min(CB, cnt - d.b0);
+#pragma unroll
+      for (int s = 0; s < CB; ++s) {
+        child[s] = s < nv ? f.child[first + d.b0 + s] : -1;
+        Pd[s] = s < nv ? a.P + (size_t)a.dst_slot[child[s]] * a.slab : nullptr;
+      }
+      // every consumer is past the last panel barrier of the previous batch: the operand
+      // arrays in shared memory may be rewritten
+      if (fam != cur_fam || d.item != cur_item) {
+        const double *KSa = a.KS4prev + (size_t)f.anc[fam] * ld * 4;
+#pragma unroll
+        for (int qq = 0; qq < MAXQ; ++qq) {
+          const int jj = wid + NW * qq;
+          ksA[qq] = jj < nb ? -KSa[(size_t)jj * 32 + lane] : 0.0;   // -KS(8jj + g, tg)
+        }
+        if (fam != cur_fam) {
+          const double2 *Ga = reinterpret_cast<const double2 *>(a.G4prev + (size_t)f.anc[fam] * ld * 4);
+          double2 *sg = reinterpret_cast<double2 *>(s_G);
+          for (int idx = tid; idx < ld * 2; idx += NW * 32) sg[idx] = Ga[idx];
+        }
+      }
+      {   // siblings' H in fragment order: s_bC[j][lane] = H_s(b, 8j + 2tg + {0, 1}), n = g = 4s + b
+        const double *H0 = a.H4 + (size_t)child[0] * ld * 4;
+        const double *H1 = nv > 1 ? a.H4 + (size_t)child[1] * ld * 4 : nullptr;
+        for (int idx = tid; idx < nb * 32; idx += NW * 32) {
+          const int l2 = idx & 31, jb = idx >> 5, g2 = l2 >> 2, t2 = l2 & 3;
+          const double *Hs = (g2 >> 2) == 0 ? H0 : H1;
+          double2 v = make_double2(0.0, 0.0);
+          if (Hs != nullptr) {
+            const size_t o = (size_t)(8 * jb + 2 * t2) * 4 + (g2 & 3);
+            v = make_double2(Hs[o], Hs[o + 4]);
+          }
+          s_bC[idx] = v;
+        }
+      }
+      cur_item = d.item; cur_b0 = d.b0; cur_fam = fam; cur_p = -1;
+      named_barrier_sync(1, NW * 32);
+    }
+    const double *st = ring + (size_t)slot * TS * 64;
+    int t = 0, p = d.p, j = d.j;
+    while (t < d.nt) {
+      const int seg = min(d.nt - t, nb - j), jend = j + seg;
+      if (p != cur_p) {   // operands of the panel: G(8p + g, tg) and the siblings' H at columns 8p..
+        gB = s_G[(size_t)p * 32 + lane];
+        const double2 hv = s_bC[(size_t)p * 32 + lane];
+        hB0 = hv.x; hB1 = hv.y;
+        cur_p = p;
+      }
+      const double *tb = st + (long long)(t - j) * 64;       // tile (jj, p) of this stage at tb + jj * 64
+      const size_t gt = (size_t)(d.t0 + t - j) * 64 + offC;  // same, in the slab
+#pragma unroll
+      for (int qq = 0; qq < MAXQ; ++qq) {
+        const int jj = wid + NW * qq;
+        if (jj >= j && jj < jend) {
+          const double *tp = tb + (size_t)jj * 64;
+          double2 tv = *reinterpret_cast<const double2 *>(tp + offC);
+          dmma_m8n8k4(acc[qq][0], acc[qq][1], tv.x, hB0);      // row side, tile before its downdate
+          dmma_m8n8k4(acc[qq][0], acc[qq][1], tv.y, hB1);
+          if (jj != p) {                                       // column side: strictly lower tiles
+            const double a0 = tp[offT0], a1 = tp[offT1];
+            const double2 xv = s_bC[(size_t)jj * 32 + lane];
+            dmma_m8n8k4(col0, col1, a0, xv.x);
+            dmma_m8n8k4(col0, col1, a1, xv.y);
+          }
+          dmma_m8n8k4(tv.x, tv.y, ksA[qq], gB);                // the ancestor's pending downdate
+#pragma unroll
+          for (int s = 0; s < CB; ++s)
+            if (s < nv) *reinterpret_cast<double2 *>(Pd[s] + gt + (size_t)jj * 64) = tv;
+        }
+      }
+      t += seg;
+      if (jend == nb) {   // the panel is complete: add the consumer warps' column-side tiles in fixed order
+        const int buf = n_panel & 1;
+        *reinterpret_cast<double2 *>(s_colp + ((size_t)(buf * NW + wid) * 64 + g * 8 + 2 * tg)) = make_double2(col0, col1);
+        col0 = col1 = 0.0;
+        if (t >= d.nt) {   // last use of the slot by this warp: release it before the barrier
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+        named_barrier_sync(1, NW * 32);
+        if (tid < 64) {
+          const int u = tid >> 3, n = tid & 7, s = n >> 2;
+          if (s < nv) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sum += s_colp[(size_t)(buf * NW + w) * 64 + tid];
+            const int ch = s == 0 ? child[0] : child[1];
+            a.PHp[(((size_t)ch * (a.nsplit + 1) + a.nsplit) * ld + (8 * p + u)) * 4 + (n & 3)] = sum;
+          }
+        }
+        ++n_panel;
+        ++p; j = p;
+        if (t >= d.nt) goto released;
+      } else {
+        j = jend;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);   // this warp has read everything it needs from the slot
+  released:
+    if (++slot == NS) { slot = 0; ++round; }
+  }
+  if (cur_item >= 0) flush_rows();
+}
+
+}  // namespace rb

@@ -24,6 +24,7 @@
 #include "engine_internal.h"
 #include "step_kernels.cuh"
 #include "shard_plan.cuh"
+#include "packed_kernels.cuh"
 
 using namespace rb;
 
@@ -186,18 +187,29 @@ __global__ void k_logw_scatter(int Nloc, int world, const int *__restrict__ glob
 }
 
 // barrier across the GPUs of the node: flags live in every rank's memory, mapped by all
-__global__ void k_peer_barrier(int world, int rank, unsigned long long epoch, PeerTable pt) {
+// A rank that fails (not-PD error, CUDA error, host exception) never arrives: the spin is bounded
+// (~20 s of SM clock) and a time-out is reported through the status word instead of hanging the
+// stream.  Slots 16.. of the flags page carry every rank's not-PD flag so that all ranks, rank 0
+// in particular, see a failure that happened on any shard.
+#define RB_BARRIER_SPIN_CYCLES 40000000000ll
+__global__ void k_peer_barrier(int world, int rank, unsigned long long epoch, PeerTable pt, DevStatus *status) {
   const int r = threadIdx.x;
   if (r >= world) return;
+  const unsigned long long bad = status->not_pd ? 1ull : 0ull;
+  unsigned long long *rflags = static_cast<unsigned long long *>(pt.p[SH_FLAGS][r]);
+  if (bad) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(rflags + 16 + rank), "l"(bad) : "memory");
   __threadfence_system();
-  unsigned long long *remote = static_cast<unsigned long long *>(pt.p[SH_FLAGS][r]) + rank;
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
-  const unsigned long long *mine = static_cast<const unsigned long long *>(pt.p[SH_FLAGS][rank]) + r;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(rflags + rank), "l"(epoch) : "memory");
+  const unsigned long long *mine = static_cast<const unsigned long long *>(pt.p[SH_FLAGS][rank]);
   unsigned long long v;
+  const long long t0 = clock64();
   do {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + r) : "memory");
+    if (v < epoch && clock64() - t0 > RB_BARRIER_SPIN_CYCLES) { status->peer_timeout = 1; break; }
   } while (v < epoch);
   __threadfence_system();
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + 16 + r) : "memory");
+  if (v && !status->not_pd) { status->not_pd = 1; status->not_pd_step = -1; status->not_pd_particle = -1 - r; }
 }
 
 __global__ void k_final_means_sharded(int gN, int M, const int *__restrict__ owner,
@@ -219,13 +231,15 @@ __global__ void k_final_cov_sharded(int M, int ld, const double *__restrict__ Pm
                                     const double *__restrict__ G4m, const double *__restrict__ KS4m,
                                     const double *__restrict__ G4l, const double *__restrict__ KS4l,
                                     const double *__restrict__ xll, double wl, const double *__restrict__ means,
-                                    double *__restrict__ Pmax, double *__restrict__ Pmean, int sym) {
+                                    double *__restrict__ Pmax, double *__restrict__ Pmean, int layout) {
   const int c = blockIdx.x;
   const double *xmean = means + M;
   const double dc = xmean[c] - xll[c];
   for (int r = threadIdx.x; r < M; r += blockDim.x) {
-    const int rr = sym ? max(r, c) : r, cc = sym ? min(r, c) : c;   // sym: lower triangle only
-    double pm = Pm[rr + (size_t)cc * ld], pl = Pl[rr + (size_t)cc * ld];
+    int rr, cc;   // packed symmetric slabs store (r,c) of an upper block as its mirror image
+    slab_elem_rc(layout, r, c, rr, cc);
+    const size_t off = slab_elem(layout, ld, r, c);
+    double pm = Pm[off], pl = Pl[off];
     for (int b = 0; b < 4; ++b) {
       pm = fma(-KS4m[(size_t)rr * 4 + b], G4m[(size_t)cc * 4 + b], pm);
       pl = fma(-KS4l[(size_t)rr * 4 + b], G4l[(size_t)cc * 4 + b], pl);
@@ -301,7 +315,7 @@ extern "C" int rbslam_ipc_count(void) { return SH_COUNT; }
 static int peer_barrier(rbslam_ctx *ctx) {
   ShardWs *s = sh_of(ctx);
   ++s->epoch;
-  k_peer_barrier<<<1, 32, 0, ctx->stream>>>(s->world, s->rank, s->epoch, s->peers);
+  k_peer_barrier<<<1, 32, 0, ctx->stream>>>(s->world, s->rank, s->epoch, s->peers, ctx->d_status);
   ctx->launches += 1;
   CK(cudaGetLastError());
   return RBSLAM_OK;
@@ -345,6 +359,7 @@ int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
   s->migrated = 0;
   ctx->running = true;
   ctx->t = 0;
+  CK(cudaMemsetAsync(s->flags + 16, 0, 16 * sizeof(unsigned long long), ctx->stream));   // peers' failure flags of an earlier run
   if ((rc = peer_barrier(ctx))) return rc;   // nobody starts before everybody is initialised
   return RBSLAM_OK;
 }
@@ -553,7 +568,7 @@ int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
     k_final_cov_sharded<<<M, 128, 0, ctx->stream>>>(M, ld, at(SH_P, im, ctx->slab), at(SH_P, gN - 1, ctx->slab),
                                                     at(gsel, im, t4), at(ksel, im, t4), at(gsel, gN - 1, t4),
                                                     at(ksel, gN - 1, t4), at(xsel, gN - 1, M), wl, means, Pmax, Pmean,
-                                                    ctx->sym ? 1 : 0);
+                                                    ctx->layout);
     ctx->launches += 1;
     CK(cudaGetLastError());
     if (out->traj_max && (rc = rb_d2h(ctx, out->traj_max, s->traj_max, sizeof(double) * n * T))) return rc;

@@ -424,7 +424,7 @@ static int info_kalman_phase_d(rbslam_ctx *ctx, const double *y_t_dev, const dou
 #define RB_INFO_LAUNCH(R2V, DA)                                                                         \
       {                                                                                                \
         auto kern = k_stream_pass<D, DA, R2V, 8, 2>;                                                   \
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024))); \
+        RB_OPTIN_SMEM(kern, ctx->smem_optin - 1024);                                                   \
         kern<<<grid, RB_STREAM_THREADS, smem, ctx->stream>>>(sa, list, cnt, nullptr);                       \
       }
       switch (R2) { case 1: RB_INFO_LAUNCH(1, D) break; case 2: RB_INFO_LAUNCH(2, D) break;
@@ -485,12 +485,8 @@ int rb_info_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, const double *y
 static int launch_gemm(rbslam_ctx *ctx, bool ta, const GemmArgs &g, int batch) {
   dim3 grid((g.m + 127) / 128, (g.n + 63) / 64, batch);
   const size_t smem = sizeof(double) * 32 * (RB_LDA + RB_LDB);
-  static bool attr = false;
-  if (!attr) {
-    CK(cudaFuncSetAttribute(k_dgemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_dgemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  RB_OPTIN_SMEM(k_dgemm<true>, smem);
+  RB_OPTIN_SMEM(k_dgemm<false>, smem);
   if (ta) k_dgemm<true><<<grid, 256, smem, ctx->stream>>>(g);
   else k_dgemm<false><<<grid, 256, smem, ctx->stream>>>(g);
   ctx->launches += 1;
@@ -503,9 +499,9 @@ static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
   if (!nt) {
     nt = 128;
     if (const char *e = getenv("RBSLAM_CHOL_THREADS")) nt = atoi(e) == 256 ? 256 : 128;
-    CK(cudaFuncSetAttribute(k_chol_solve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_solve_smem(128)));
-    CK(cudaFuncSetAttribute(k_chol_solve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_solve_smem(256)));
   }
+  RB_OPTIN_SMEM(k_chol_solve<128>, chol_solve_smem(128));
+  RB_OPTIN_SMEM(k_chol_solve<256>, chol_solve_smem(256));
   if (nt == 256) k_chol_solve<256><<<batch, 256, chol_solve_smem(256), ctx->stream>>>(c);
   else k_chol_solve<128><<<batch, 128, chol_solve_smem(128), ctx->stream>>>(c);
   ctx->launches += 1;
@@ -621,8 +617,9 @@ static int ancestor_weights_info(rbslam_ctx *ctx, int t, bool use_default_dyn) {
 extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N_K, int32_t form,
                                    rbslam_smoother_outputs *out) {
   if (!ctx || !in || !out || N_K < 1 || (form != 0 && form != 1)) return RBSLAM_EARG;
+  if (ctx->shard_ws) return ctx->fail(RBSLAM_EARG, "rbslam_smoother_run: this context is a filter shard (world > 1)");
   if (!ctx->cfg.keep_history) return ctx->fail(RBSLAM_EARG, "the smoother needs keep_history=1");
-  if (ctx->sym) return ctx->fail(RBSLAM_EARG, "kalman_variant 4 (symmetric storage) is filter-only");
+  if (ctx->pt) return ctx->fail(RBSLAM_EARG, "packed symmetric slabs (kalman_variant 7 / -1) are filter-only: create the context with kalman_variant 0");
   const bool sparse = ctx->mc.family == FAM_SPARSE_VISUAL2D;
   if (form == 1 && sparse)
     return ctx->fail(RBSLAM_EARG, "This code has only been implemented for dense features");   // :77-80

@@ -430,6 +430,10 @@ k_normalize(int N, int n, const double *__restrict__ logw, double *__restrict__ 
       const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
       if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
     }
+    // every weight NaN (chol failed even with jitter: the status word reports it): no comparison
+    // succeeded.  MATLAB's max returns index 1 for an all-NaN vector; never leave an out-of-range
+    // index behind for the kernels that gather with iw_max
+    if (bidx < 0 || bidx >= N) bidx = 0;
     if (lane == 0) { s_idx[0] = bidx; if (iw_max_out) *iw_max_out = bidx; }
   }
   __syncthreads();

@@ -418,6 +418,7 @@ def particleFilter(dynModel, measModel, odometry, y, x0_nonLin, x0_lin, P0_lin, 
     mode, seed, streams = _as_streams(rng)
     yy = np.asarray(y, dtype=np.float64)
     T = yy.shape[0]
+    ctx_kw.setdefault("kalman_variant", -1)   # filter only: packed symmetric slabs where they apply
     with Context(model, N_P, T, device=device, rng_mode=mode, seed=seed, **ctx_kw) as ctx:
         if makePlots is not None:
             def _cb(k, t, ctx=ctx):

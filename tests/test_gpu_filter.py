@@ -60,6 +60,7 @@ def _compare(o, ref, taps, T, tol=TOL):
     ("radio", 64, {"traj": "square_3D", "m": 60}),
     ("mag", 24, {"m": 64, "T": 24}),                     # small-M kernel
     ("mag", 16, {"m": 253, "T": 12}),                    # streaming kernels (M=256)
+    ("mag", 40, {"m": 1024, "T": 5}),                    # C4 slab size: k_stream_fam<3,3,8,2,3>, real families
     ("sparse", 40, {"T": 60}),                           # C3 shape: M=40, d=20 with NaNs
 ])
 def test_filter_teacher_forced(rbslam_lib, fam, N, kw):
@@ -156,4 +157,43 @@ def test_filter_c1_shape(rbslam_lib, N, m, T):
     ref, taps = _run_oracle(om, pr, N, st)
     with rb.Context(gm, N, T, rng_mode=0) as ctx:
         o = ctx.filter_run(*_args(pr), pr["dt"], streams=st, taps=True)
+    _compare(o, ref, taps, T)
+
+
+@pytest.mark.parametrize("variant", [2, 7], ids=["full", "packed"])
+def test_filter_heavy_families(rbslam_lib, variant):
+    """Forced ancestors with one ancestor taking most offspring (families far above the 4 / 6
+    siblings a main family holds -> surplus families, several batches, copies landing in many
+    dead slabs) next to singletons and childless particles."""
+    rb = rbslam_lib
+    N = 32
+    pr, om, gm = _setup(rb, "mag", N, m=253, T=6)
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(8), 1, T, N, om.nz)
+    rng = np.random.default_rng(4)
+    forced = np.zeros((1, T, N), dtype=np.int32)
+    for t in range(1, T):
+        heavy = int(rng.integers(0, N))
+        a = rng.integers(0, N, N)
+        a[rng.permutation(N)[:19]] = heavy          # 19+ offspring of one ancestor
+        a[rng.permutation(N)[:7]] = (heavy + 5) % N  # and a 7-sibling family
+        forced[0, t] = a
+    ref, taps = _run_oracle(om, pr, N, st, forced=forced[0])
+    with rb.Context(gm, N, T, rng_mode=0, kalman_variant=variant) as ctx:
+        o = ctx.filter_run(*_args(pr), pr["dt"], streams=st, forced_ancestors=forced, taps=True)
+    _compare(o, ref, taps, T)
+
+
+@pytest.mark.parametrize("variant", [2, 7], ids=["full", "packed"])
+def test_filter_long_horizon_deferred_downdate(rbslam_lib, variant):
+    """T = 600 teacher-forced steps at N = 8, M = 256: the pending (G, KS) pair rides through
+    every resampling for the whole run; the drift against the oracle stays inside 1e-8."""
+    rb = rbslam_lib
+    N, T = 8, 600
+    pr, om, gm = _setup(rb, "mag", N, m=253, T=T)
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(12), 1, T, N, om.nz)
+    ref, taps = _run_oracle(om, pr, N, st)
+    forced = np.stack([tp["ai"] for tp in taps])[None].astype(np.int32)
+    with rb.Context(gm, N, T, rng_mode=0, kalman_variant=variant) as ctx:
+        o = ctx.filter_run(*_args(pr), pr["dt"], streams=st, forced_ancestors=forced, taps=True)
     _compare(o, ref, taps, T)
