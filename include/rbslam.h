@@ -231,6 +231,23 @@ RBSLAM_API int rbslam_op_dyn_logweight(rbslam_ctx *ctx, int32_t N, const double 
                             const double *dx, double dt, const double *Q, int32_t use_default,
                             double *logwDyn);
 
+/* Measurement part of the ancestor weights of the reference trajectory (logwMeas) for N particles,
+   through the kernels the smoother sweeps use (K6: batched fp64 GEMM + Cholesky; K7: batched M x M
+   Cholesky), at any size:
+     form 0, covariance form (src/particleSmoother.m:187-229, dense families):
+        A = P [M x M x N], v = xl [M x N], S = D [ne x M] stacked future Jacobians (time-major, d rows per
+        step), r = stacked future measurements [ne], R [d x d];  q2, hld unused (may be NULL)
+        logwMeas_i = -sum(log(diag(cS))) - 1/2 v'v - ne/2 log(2 pi),  cS = chol(D P_i D' + kron(I, R)),
+        v = cS \ (r - D xl_i); jitter as src/particleSmoother.m:70, 222-225
+     form 1, information form (src/particleSmootherInformationForm.m:225-236):
+        A = Imat [M x M x N], v = ivec [M x N], S = ImatAddt [M x M], r = ivecAddt [M], q2 [N] = ivec_i' P_i ivec_i,
+        hld [N] = halfLogDetP;  ne, R unused;  jitter < 0 reproduces quirk Q7 (no retry: failure is an error)
+        logwMeas_i = -1/2 q2_i - hld_i - sum(log(diag(cI))) + 1/2 |cI \ (ivec_i + ivecAddt)|^2,
+        cI = chol(Imat_i + ImatAddt) */
+RBSLAM_API int rbslam_op_ancestor_weights(rbslam_ctx *ctx, int32_t form, int32_t N, int32_t ne, const double *A,
+                               const double *v, const double *S, const double *r, const double *R,
+                               const double *q2, const double *hld, double jitter, double *logwMeas);
+
 /* ---- multi-GPU sharding (one process per GPU) --------------------------- */
 /* Host-only planner: given the ancestors of all N new particles and the owner
    rank of every old particle, assign new particles to ranks so that offspring

@@ -825,3 +825,93 @@ extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int
   if (out->AI && (rc = rb_d2h(ctx, out->AI, w->AI, sizeof(double) * (size_t)N_K * T * N))) return rc;
   return rb_check_status(ctx);
 }
+
+// ---------------------------------------------------------------------------
+// kernel-level entry point: the measurement part of the ancestor weights for N particles,
+// host buffers in and out.  Runs exactly the kernels of the sweeps (k_future_resid, k_dgemm x2,
+// k_chol_solve for form 0; k_chol_solve on Imat_i + ImatAddt for form 1) at any size, so K6 / K7
+// can be compared with the oracle's per-particle formulas at the C1 / C5 shapes where a whole
+// smoother run is out of the oracle's reach.
+// ---------------------------------------------------------------------------
+__global__ void k_aw_combine(int N, int form, double ne, const double *__restrict__ sumlog,
+                             const double *__restrict__ vtv, const double *__restrict__ q2,
+                             const double *__restrict__ hld, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (form == 0) out[i] = -sumlog[i] - 0.5 * vtv[i] - ne / 2.0 * RB_LOG2PI;         // src/particleSmoother.m:229
+  else out[i] = -0.5 * q2[i] - hld[i] - sumlog[i] + 0.5 * vtv[i];                    // ...InformationForm.m:234-236
+}
+
+extern "C" int rbslam_op_ancestor_weights(rbslam_ctx *ctx, int32_t form, int32_t N, int32_t ne, const double *A,
+                                          const double *v, const double *S, const double *r, const double *R,
+                                          const double *q2, const double *hld, double jitter, double *logwMeas) {
+  if (!ctx || !A || !v || !S || !r || !logwMeas || N < 1 || (form != 0 && form != 1)) return RBSLAM_EARG;
+  if (form == 0 && (ne < 1 || !R)) return ctx->fail(RBSLAM_EARG, "op_ancestor_weights form 0: need ne >= 1 and R");
+  if (form == 1 && (!q2 || !hld)) return ctx->fail(RBSLAM_EARG, "op_ancestor_weights form 1: need q2 and halfLogDetP");
+  if (form == 0 && ctx->mc.family == FAM_SPARSE_VISUAL2D)
+    return ctx->fail(RBSLAM_EARG, "op_ancestor_weights: dense families only (the sparse family re-linearises per particle)");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int M = ctx->M, d = ctx->d;
+  const int n = form == 0 ? ne : M;          // order of the matrix that is factored
+  if (form == 0 && ne % d) return ctx->fail(RBSLAM_EARG, "op_ancestor_weights form 0: ne must be a multiple of d");
+  int rc;
+  struct Buf { void *p = nullptr; ~Buf() { if (p) cudaFree(p); } };
+  Buf bA, bv, bS, br, bR, bW, bSS, bL, be, bsl, bvv, bq, bh, bo;
+  auto alloc = [&](Buf &b, size_t bytes) -> int {
+    if (cudaMalloc(&b.p, bytes ? bytes : 8) != cudaSuccess) { cudaGetLastError(); return ctx->fail(RBSLAM_ECUDA, "op_ancestor_weights: out of device memory"); }
+    return RBSLAM_OK;
+  };
+  const size_t MM = (size_t)M * M, ldl = chol_ldl(n);
+  if ((rc = alloc(bA, MM * N * 8)) || (rc = alloc(bv, (size_t)M * N * 8)) || (rc = alloc(bsl, (size_t)N * 8)) ||
+      (rc = alloc(bvv, (size_t)N * 8)) || (rc = alloc(bo, (size_t)N * 8)) || (rc = alloc(bL, ldl * n * N * 8)))
+    return rc;
+  if ((rc = rb_h2d(ctx, bA.p, A, MM * N * 8)) || (rc = rb_h2d(ctx, bv.p, v, (size_t)M * N * 8))) return rc;
+  CholArgs c{};
+  c.n = n; c.L = (double *)bL.p; c.ldl = (int)ldl; c.strideL = ldl * n; c.jitter = jitter;
+  c.sum_log_diag = (double *)bsl.p; c.vtv = (double *)bvv.p; c.status = ctx->d_status; c.t = 0;
+  CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(DevStatus), ctx->stream));
+  if (form == 0) {
+    // S = D [ne x M] (MATLAB layout) -> Dt [M x ne]; r = stacked future measurements
+    std::vector<double> Dt((size_t)M * ne);
+    for (int j = 0; j < ne; ++j)
+      for (int cidx = 0; cidx < M; ++cidx) Dt[cidx + (size_t)j * M] = S[j + (size_t)cidx * ne];
+    if ((rc = alloc(bS, Dt.size() * 8)) || (rc = alloc(br, (size_t)ne * 8)) || (rc = alloc(bR, (size_t)d * d * 8)) ||
+        (rc = alloc(bW, (size_t)M * ne * N * 8)) || (rc = alloc(bSS, (size_t)ne * ne * N * 8)) ||
+        (rc = alloc(be, (size_t)ne * N * 8)))
+      return rc;
+    if ((rc = rb_h2d(ctx, bS.p, Dt.data(), Dt.size() * 8)) || (rc = rb_h2d(ctx, br.p, r, (size_t)ne * 8)) ||
+        (rc = rb_h2d(ctx, bR.p, R, (size_t)d * d * 8)))
+      return rc;
+    k_future_resid<<<dim3((ne + 3) / 4, N), 128, 0, ctx->stream>>>(M, ne, (const double *)bS.p, M, (const double *)br.p,
+                                                                  (const double *)bv.p, 0, (double *)be.p, ne);
+    ctx->launches += 1;
+    GemmArgs g1{};   // W = P_i * D'
+    g1.m = M; g1.n = ne; g1.k = M; g1.A = (const double *)bA.p; g1.lda = M; g1.strideA = MM; g1.slotA = nullptr;
+    g1.B = (const double *)bS.p; g1.ldb = M; g1.strideB = 0;
+    g1.C = (double *)bW.p; g1.ldc = M; g1.strideC = (size_t)M * ne; g1.Rblk = nullptr; g1.d = 1;
+    GemmArgs g2{};   // SS = D * W + kron(I, R)
+    g2.m = ne; g2.n = ne; g2.k = M; g2.A = (const double *)bS.p; g2.lda = M; g2.strideA = 0; g2.slotA = nullptr;
+    g2.B = (const double *)bW.p; g2.ldb = M; g2.strideB = (size_t)M * ne;
+    g2.C = (double *)bSS.p; g2.ldc = ne; g2.strideC = (size_t)ne * ne; g2.Rblk = (const double *)bR.p; g2.d = d;
+    if ((rc = launch_gemm(ctx, false, g1, N)) || (rc = launch_gemm(ctx, true, g2, N))) return rc;
+    c.A1 = (const double *)bSS.p; c.lda1 = ne; c.strideA1 = (size_t)ne * ne; c.slot1 = nullptr; c.A2 = nullptr; c.lda2 = 0;
+    c.rhs = (const double *)be.p; c.stride_rhs = ne; c.rhs2 = nullptr;
+  } else {
+    // A = Imat [M x M x N], v = ivec [M x N], S = ImatAddt [M x M], r = ivecAddt [M]
+    if ((rc = alloc(bS, MM * 8)) || (rc = alloc(br, (size_t)M * 8)) || (rc = alloc(bq, (size_t)N * 8)) ||
+        (rc = alloc(bh, (size_t)N * 8)))
+      return rc;
+    if ((rc = rb_h2d(ctx, bS.p, S, MM * 8)) || (rc = rb_h2d(ctx, br.p, r, (size_t)M * 8)) ||
+        (rc = rb_h2d(ctx, bq.p, q2, (size_t)N * 8)) || (rc = rb_h2d(ctx, bh.p, hld, (size_t)N * 8)))
+      return rc;
+    c.A1 = (const double *)bA.p; c.lda1 = M; c.strideA1 = MM; c.slot1 = nullptr; c.A2 = (const double *)bS.p; c.lda2 = M;
+    c.rhs = (const double *)bv.p; c.stride_rhs = M; c.rhs2 = (const double *)br.p;
+  }
+  if ((rc = launch_chol(ctx, c, N))) return rc;
+  k_aw_combine<<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, form, (double)ne, (const double *)bsl.p, (const double *)bvv.p,
+                                                         (const double *)bq.p, (const double *)bh.p, (double *)bo.p);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if ((rc = rb_d2h(ctx, logwMeas, bo.p, (size_t)N * 8))) return rc;
+  return rb_check_status(ctx);
+}

@@ -375,6 +375,26 @@ class Context:
                                                    _capi.dptr(xl), _capi.dptr(P), _capi.dptr(logw)))
         return xl, P, logw
 
+    def op_ancestor_weights(self, form, A, v, S, r, R=None, q2=None, hld=None, jitter=1e-2):
+        """logwMeas [N] of the reference trajectory's ancestor weights (rbslam_op_ancestor_weights):
+        form 0: A = P [M x M x N], v = xl [M x N], S = D [ne x M], r = y_future [ne], R;
+        form 1: A = Imat, v = ivec, S = ImatAddt [M x M], r = ivecAddt [M], q2, hld [N]."""
+        A = _capi.fcol(A)
+        v = _capi.fcol(v)
+        S = _capi.fcol(np.atleast_2d(S))
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        N = v.shape[1]
+        ne = S.shape[0] if form == 0 else 0
+        Rc = None if R is None else _capi.fcol(np.atleast_2d(R))
+        q2c = None if q2 is None else np.ascontiguousarray(q2, dtype=np.float64)
+        hc = None if hld is None else np.ascontiguousarray(hld, dtype=np.float64)
+        out = np.zeros(N)
+        self._ck(self._lib.rbslam_op_ancestor_weights(self._h, int(form), N, ne, _capi.dptr(A), _capi.dptr(v),
+                                                      _capi.dptr(S), _capi.dptr(r), _capi.dptr(Rc),
+                                                      _capi.dptr(q2c), _capi.dptr(hc), float(jitter),
+                                                      _capi.dptr(out)))
+        return out
+
     def op_dyn_logweight(self, xnk_t, xn, dx, dt, Q, use_default=False):
         xn = _capi.fcol(xn)
         N = xn.shape[1]

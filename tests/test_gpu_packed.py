@@ -40,7 +40,7 @@ def test_packed_kalman_update(rbslam_lib, fam, m):
         assert abs(logw[i] - lr) <= 1e-8 * max(1.0, abs(lr))
 
 
-@pytest.mark.parametrize("cfg", ["48,4", "7,3", "200,2"])
+@pytest.mark.parametrize("cfg", ["48,4", "7,3", "100,2"])
 def test_packed_stage_shapes(rbslam_lib, cfg, monkeypatch):
     """Stage size / ring depth do not change results: stages that end inside a panel, stages
     that span many of the short panels at the narrow end, a ring of two."""

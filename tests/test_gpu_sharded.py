@@ -62,13 +62,13 @@ def _worker(rank, world, port, N, m, T, seed, q, overlap=False, variant=2):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("variant", [2, 7], ids=["full", "packed"])
-@pytest.mark.parametrize("overlap", [False, True], ids=["barrier-first", "overlap"])
-@pytest.mark.parametrize("world,N,m,T", [(2, 32, 64, 12), (2, 64, 253, 8), (4, 64, 64, 8)])
+@pytest.mark.parametrize("world,N,m,T,overlap,variant", [
+    (2, 32, 64, 12, False, 2), (2, 64, 253, 8, False, 2), (4, 64, 64, 8, False, 2),
+    (2, 32, 64, 12, True, 2), (2, 64, 253, 8, True, 2), (4, 64, 64, 8, True, 2),
+    (2, 32, 64, 12, False, 7), (2, 64, 253, 8, False, 7),        # packed symmetric slabs
+])
 def test_sharded_filter_matches_single_gpu_and_oracle(rbslam_lib, world, N, m, T, overlap, variant):
     rb = rbslam_lib
-    if variant == 7 and (overlap or world == 4):
-        pytest.skip("packed slabs: covered by the barrier-first 2-rank cases")
     import torch.multiprocessing as mp
     import oracle
     seed = 77

@@ -140,3 +140,85 @@ def test_smoother_dropin_signatures(rbslam_lib):
     assert rb.particleSmootherInformationForm(gm2.dynModel, gm2.measModel, None, pr2["odometry"], pr2["y"],
                                               pr2["x0_nonLin"], pr2["x0_lin"], pr2["P0_lin"], pr2["Q"],
                                               pr2["R"], 6, 2, pr2["dt"], True) is None
+
+
+# ---------------------------------------------------------------------------
+# K6 / K7 alone at the BASELINE shapes (rbslam_op_ancestor_weights): the oracle's per-particle
+# formulas for 8 particles; a whole smoother run at these sizes is out of the oracle's reach.
+# ---------------------------------------------------------------------------
+def _c1_state(rb, m, T, N, seed):
+    """A plausible mid-run particle state at the C1 / C5 slab size: N particles after a few
+    filter steps of the oracle (different poses -> different P_i, xl_i, Imat_i, ivec_i)."""
+    pr = rb.synth.dense_mag_problem(N_T=T, m=m, seed=seed, m_sim=300)
+    om = oracle.DenseMag3D(pr["NN"], pr["L"])
+    rng = np.random.default_rng(seed)
+    M = m + 3
+    xn = np.repeat(pr["x0_nonLin"][:, None], N, axis=1) + 0.3 * rng.standard_normal((7, N))
+    P = np.repeat(pr["P0_lin"][None], N, axis=0).copy()
+    xl = np.zeros((M, N))
+    Imat = np.repeat(np.diag(1.0 / np.diag(pr["P0_lin"]))[None], N, axis=0).copy()
+    ivec = np.zeros((M, N))
+    Ri = np.linalg.inv(pr["R"])
+    for t in range(4):                       # four Kalman updates at perturbed poses
+        xs = xn + 0.05 * t
+        H = om.measModel(xs)
+        for i in range(N):
+            S = H[i] @ P[i] @ H[i].T + pr["R"]
+            K = P[i] @ H[i].T @ np.linalg.inv(S)
+            xl[:, i] += K @ (pr["y"][t] - H[i] @ xl[:, i])
+            P[i] = P[i] - K @ S @ K.T
+            Imat[i] += H[i].T @ Ri @ H[i]
+            ivec[:, i] += H[i].T @ Ri @ pr["y"][t]
+    return pr, om, P, xl, Imat, ivec
+
+
+def test_ancestor_weights_cov_c1_size(rbslam_lib):
+    """K6 at the C1 shape: M = 515, the full future system of T = 192 steps (d tau = 576)."""
+    rb = rbslam_lib
+    N, m, T = 8, 512, 193
+    pr, om, P, xl, _, _ = _c1_state(rb, m, T, N, seed=21)
+    gm = rb.models.from_problem(pr)
+    rng = np.random.default_rng(2)
+    xnk = np.repeat(pr["x0_nonLin"][:, None], T - 1, axis=1) + 0.2 * rng.standard_normal((7, T - 1))
+    D = om.measModel(xnk).reshape(-1, m + 3)            # stacked future Jacobians, time-major, d rows per step
+    yfut = pr["y"][1:T].reshape(-1)
+    ne = D.shape[0]
+    assert ne == 576
+    RR = np.kron(np.eye(T - 1), pr["R"])
+    ref = np.zeros(N)
+    for i in range(N):                                  # src/particleSmoother.m:191-229
+        SS = D @ P[i] @ D.T + RR
+        e = yfut - D @ xl[:, i]
+        cS = np.linalg.cholesky(SS)
+        v = np.linalg.solve(cS, e)
+        ref[i] = -np.sum(np.log(np.diag(cS))) - 0.5 * (v @ v) - ne / 2 * np.log(2 * np.pi)
+    with rb.Context(gm, N, 4) as ctx:
+        got = ctx.op_ancestor_weights(0, P.transpose(1, 2, 0), xl, D, yfut, R=pr["R"], jitter=1e-2)
+    assert np.all(np.abs(got - ref) <= 1e-8 * np.maximum(1.0, np.abs(ref))), (got, ref)
+
+
+def test_ancestor_weights_info_c5_size(rbslam_lib):
+    """K7 at the C1 / C5 shape: batched 515 x 515 Cholesky of Imat_i + ImatAddt, forward solve,
+    quadratic forms (src/particleSmootherInformationForm.m:225-236)."""
+    rb = rbslam_lib
+    N, m = 8, 512
+    pr, om, P, xl, Imat, ivec = _c1_state(rb, m, 40, N, seed=22)
+    gm = rb.models.from_problem(pr)
+    rng = np.random.default_rng(3)
+    M = m + 3
+    xnk = np.repeat(pr["x0_nonLin"][:, None], 30, axis=1) + 0.2 * rng.standard_normal((7, 30))
+    Hk = om.measModel(xnk)
+    Ri = np.linalg.inv(pr["R"])
+    ImatAddt = sum(Hk[j].T @ Ri @ Hk[j] for j in range(30))
+    ivecAddt = sum(Hk[j].T @ Ri @ pr["y"][5 + j] for j in range(30))
+    q2 = np.array([ivec[:, i] @ P[i] @ ivec[:, i] for i in range(N)])
+    hld = np.array([0.5 * np.linalg.slogdet(P[i])[1] for i in range(N)])
+    ref = np.zeros(N)
+    for i in range(N):
+        cI = np.linalg.cholesky(Imat[i] + ImatAddt)
+        vI = np.linalg.solve(cI, ivec[:, i] + ivecAddt)
+        ref[i] = -0.5 * q2[i] - hld[i] - np.sum(np.log(np.diag(cI))) + 0.5 * (vI @ vI)
+    with rb.Context(gm, N, 4, information_form=True) as ctx:
+        got = ctx.op_ancestor_weights(1, Imat.transpose(1, 2, 0), ivec, ImatAddt, ivecAddt, q2=q2, hld=hld,
+                                      jitter=-1.0)
+    assert np.all(np.abs(got - ref) <= 1e-8 * np.maximum(1.0, np.abs(ref))), (got, ref)
