@@ -37,17 +37,22 @@ WORKLOAD = "C4 synthetic 3D dense-mag scale-up (BASELINE.json configs[3])"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=120)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--particles", type=int, default=10000, help="N_P per GPU (C4: 10^4)")
     ap.add_argument("--basis", type=int, default=1024, help="m eigenfunctions (C4: 1024)")
-    ap.add_argument("--variant", type=int, default=0, help="kalman kernel variant (0=auto)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1: weak = --particles per GPU (default), strong = --particles in total")
+    ap.add_argument("--variant", type=int, default=-1,
+                    help="kalman kernel variant (-1 = filter-only auto: packed symmetric slabs; 0/2 = full slabs)")
+    ap.add_argument("--scaling", default="both", choices=["both", "weak", "strong"],
+                    help="N>1: strong = --particles in total (the configuration BASELINE.json names; the "
+                         "line's value), weak = --particles per GPU; both (default) measures the two and "
+                         "reports the strong one as value and the weak one under 'weak'")
+    ap.add_argument("--e2e-steps", type=int, default=200, help="T of the end-to-end rbslam_filter_run call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-smoother", action="store_true", help="skip the smoother block (N=1 only)")
     ap.add_argument("--cpu-sample-particles", type=int, default=64)
-    ap.add_argument("--cpu-sample-steps", type=int, default=20)
+    ap.add_argument("--cpu-sample-steps", type=int, default=12)
     return ap.parse_args()
 
 
@@ -150,19 +155,6 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(M, n_particles):
-    """DRAM bytes of one step's Kalman-update launches, scaled from the committed ncu capture
-    (profiles/traffic.json: measured bytes per particle-step at this M), or None."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            per = json.load(open(p)).get("per_particle_step_bytes", {}).get(str(M))
-            return per * n_particles if per else None
-        except Exception:
-            pass
-    return None
-
-
 def cpu_baseline(pr, m, n_particles, n_steps):
     """Oracle port timed on the host cores, bounded sample of the same workload."""
     import oracle
@@ -210,6 +202,72 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def traffic_entry(M, variant):
+    """Measured DRAM bytes per particle-step of the Kalman-update launches for the kernel that
+    ran (profiles/traffic.json, one ncu --set full capture per kernel), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    key = "packed" if variant in (-1, 7) else "full"
+    try:
+        return json.load(open(p))[key]["per_particle_step_bytes"].get(str(M))
+    except Exception:
+        return None
+
+
+def fp64_peak():
+    p = os.path.join(ROOT, "profiles", "fp64_peaks_r1.json")
+    try:
+        return float(json.load(open(p))["fp64_dmma_m8n8k4_tflops"]), "measured (profiles/fp64_peaks_r1.json, tools/fp64_peak.cu)"
+    except Exception:
+        return 37.0, "fallback"
+
+
+def smoother_block(rbslam, device):
+    """Second half of BASELINE.json's metric: smoother seconds per run.
+    C1 = the reference's dense-mag example (N_P = 100, m = 512 -> M = 515, T = 192,
+    run_dense3D_magfield.m:85,124; N_K = 10, slam-dense-mag/main.m:26) in both forms, whole runs;
+    C5 = BASELINE.json configs[4] (information form, N = 4096, M = 515, T = 5000) on a stated T-slice:
+    sweep 2 of an N_K = 2 run, ms per step of the slice times 5000."""
+    out = {}
+    pr = rbslam.synth.dense_mag_problem(N_T=192, m=512, seed=1, n_laps=3, m_sim=2000)
+    gm = rbslam.models.from_problem(pr)
+    a = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
+    NK = 10
+    for form, name in ((0, "c1_cov"), (1, "c1_info")):
+        with rbslam.Context(gm, 100, 192, device=device, rng_mode=1, seed=1, information_form=(form == 1)) as ctx:
+            ctx.smoother_run(*a, pr["dt"], 2, form)          # warm-up: every kernel of both kinds of sweep
+            t0 = time.perf_counter()
+            ctx.smoother_run(*a, pr["dt"], NK, form)
+            out[name + "_s_per_run"] = time.perf_counter() - t0
+    out["c1"] = "N_P=100, M=515, T=192, N_K=%d, dense-mag, device Philox stream; wall time of one rbslam_smoother_run call from host buffers" % NK
+    Ts, N5 = 24, 4096
+    pr = rbslam.synth.dense_mag_problem(N_T=Ts, m=512, seed=1, n_laps=3, m_sim=2000)
+    gm = rbslam.models.from_problem(pr)
+    a = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
+    with rbslam.Context(gm, N5, Ts, device=device, rng_mode=1, seed=1, information_form=True) as ctx:
+        ctx.smoother_run(*a, pr["dt"], 1, 1)
+        t0 = time.perf_counter()
+        ctx.smoother_run(*a, pr["dt"], 1, 1)
+        t_filter = time.perf_counter() - t0
+        ctx.phase_timing(True)
+        t0 = time.perf_counter()
+        ctx.smoother_run(*a, pr["dt"], 2, 1)
+        t_two = time.perf_counter() - t0
+        ph = ctx.phase_times()
+    M = gm.M
+    ms_step = 1e3 * (t_two - t_filter) / Ts          # a sweep with ancestor weights
+    anc_ms = ph["ancestor"] / (Ts - 1)
+    flops = N5 * (M ** 3 / 3.0 + 4.0 * M * M)         # SURVEY 8(d): chol + solve + quadratic form
+    peak, src = fp64_peak()
+    out.update({
+        "c5_ms_per_step": ms_step, "c5_s_per_sweep": ms_step * 5000 / 1e3,
+        "c5": "information form, N=4096, M=515: sweep 2 of an N_K=2 run on a T=%d slice, extrapolated to T=5000; one GPU" % Ts,
+        "c5_ancestor_ms_per_step": anc_ms,
+        "fp64_tflops": flops / (anc_ms / 1e3) / 1e12, "fp64_peak_tflops": peak, "fp64_peak_source": src,
+        "fp64_frac": flops / (anc_ms / 1e3) / 1e12 / peak,
+        "fp64_kernel": "k_chol_solve (K7: batched 515 x 515 Cholesky + solve), M^3/3 + 4 M^2 flop per particle-step"})
+    return out
+
+
 def run_cuda(args):
     import rbslam
     from rbslam import _capi
@@ -228,7 +286,7 @@ def run_cuda(args):
     K, W = args.steps, max(args.warmup, 3)
     N, m = args.particles, args.basis
     # step 0 has no resampling (src/particleFilter.m:103) and is always part of the warm-up
-    T = 1 + W + K
+    T = max(1 + W + K, args.e2e_steps)
     pr, T = make_problem(m, T)
     gm = rbslam.models.from_problem(pr)
     fargs = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
@@ -240,105 +298,145 @@ def run_cuda(args):
             torch.cuda.synchronize()
             dist.barrier()
 
-    if world > 1:
-        # ONE filter sharded over the GPUs (peer-memory data path, csrc/sharded.cu)
-        from rbslam.dist import ShardedFilter
-        gN = N * world if args.scaling == "weak" else N
-        if gN % world:
-            raise SystemExit("--particles must be divisible by the number of GPUs")
-        ctx = ShardedFilter(gm, gN, T, rank=rank, world=world, device=local_rank, seed=seed,
-                            kalman_variant=args.variant)
-    else:
-        gN = N
-        ctx = rbslam.Context(gm, N, T, device=local_rank, rng_mode=_capi.RNG_PHILOX, seed=seed,
-                             keep_history=True, kalman_variant=args.variant)
-    n_loc = gN // world
-    M, d = ctx.M, ctx.d
-    # ---- device-resident measurement ------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:          # one poller per job: rank 0 reports the clocks of its own GPU
-        sampler.start()
-    ctx.filter_begin(*fargs, pr["dt"])
-    ctx.sync()
-    sampler.mark_load()
-    for _ in range(1 + W):
-        ctx.filter_step()
-    ctx.sync()
-    c0 = ctx.counters()
-    barrier()
-    sampler.mark()
-    ctx.phase_timing(True)
-    ctx.event_record(0)
-    for _ in range(K):
-        ctx.filter_step()
-    ctx.event_record(1)
-    ms = ctx.event_elapsed_ms(0, 1)
-    ctx.sync()
-    clocks = sampler.stop()
-    phases = ctx.phase_times()
-    ctx.phase_timing(False)
-    c1 = ctx.counters()
-    barrier()
-    launches = c1["kernel_launches"] - c0["kernel_launches"]
-    ctx.filter_end(T=None)
-    # ---- end to end through the public C-ABI call, host buffers -----------------------
-    ctx.sync()
-    barrier()
-    cA = ctx.counters()
-    t0 = time.perf_counter()
-    ctx.filter_run(*fargs, pr["dt"], want_xn_traj=False)
-    e2e_s = time.perf_counter() - t0
-    cB = ctx.counters()
-    ctx.close()
-
-    if dist is not None:
+    def reduce_max(vals):
+        if dist is None:
+            return vals
         import torch
-        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t.tolist()
-        e2e_s = e2e_ms / 1e3
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt)
-        launches = int(lt.item())
+        return t.tolist()
+
+    def measure(gN, with_e2e):
+        """K timed steps of ONE filter with gN particles in total (sharded over the ranks)."""
+        if world > 1:
+            from rbslam.dist import ShardedFilter
+            ctx = ShardedFilter(gm, gN, T, rank=rank, world=world, device=local_rank, seed=seed,
+                                kalman_variant=args.variant)
+        else:
+            ctx = rbslam.Context(gm, gN, T, device=local_rank, rng_mode=_capi.RNG_PHILOX, seed=seed,
+                                 keep_history=True, kalman_variant=args.variant)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:          # one poller per job: rank 0 reports the clocks of its own GPU
+            sampler.start()
+        ctx.filter_begin(*fargs, pr["dt"])
+        ctx.sync()
+        sampler.mark_load()
+        for _ in range(1 + W):
+            ctx.filter_step()
+        ctx.sync()
+        c0 = ctx.counters()
+        barrier()
+        sampler.mark()
+        ctx.phase_timing(True)
+        ctx.event_record(0)
+        for _ in range(K):
+            ctx.filter_step()
+        ctx.event_record(1)
+        ms = ctx.event_elapsed_ms(0, 1)
+        ctx.sync()
+        clocks = sampler.stop()
+        phases = ctx.phase_times()
+        ctx.phase_timing(False)
+        c1 = ctx.counters()
+        barrier()
+        res = {"launches": c1["kernel_launches"] - c0["kernel_launches"], "clocks": clocks,
+               "phases": phases, "M": ctx.M, "d": ctx.d, "ld": ctx.ld}
+        ctx.filter_end(T=None)
+        ctx.sync()
+        e2e_s = 0.0
+        if with_e2e:
+            # end to end through the public C-ABI call, host buffers in and out.  Stopping the clock
+            # poller above leaves the GPU idle for up to 2 s and its clocks drop; a few untimed steps
+            # bring it back to the state the timed region ran in
+            ctx.filter_begin(*fargs, pr["dt"])
+            for _ in range(4):
+                ctx.filter_step()
+            ctx.sync()
+            barrier()
+            cA = ctx.counters()
+            t0 = time.perf_counter()
+            ctx.filter_run(*fargs, pr["dt"], want_xn_traj=False)
+            e2e_s = time.perf_counter() - t0
+            cB = ctx.counters()
+            res["h2d"] = (cB["h2d_bytes"] - cA["h2d_bytes"]) / T
+            res["d2h"] = (cB["d2h_bytes"] - cA["d2h_bytes"]) / T
+        ctx.close()
+        ms, e2e_ms = reduce_max([ms, e2e_s * 1e3])
+        res["ms"], res["e2e_s"] = ms, e2e_ms / 1e3
+        if dist is not None:
+            import torch
+            lt = torch.tensor([res["launches"]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(lt)
+            res["launches"] = int(lt.item())
+        return res
+
+    if world > 1 and N % world:
+        raise SystemExit("--particles must be divisible by the number of GPUs")
+    scaling = "weak" if world == 1 else ("strong" if args.scaling == "both" else args.scaling)
+    gN = N * world if (world > 1 and scaling == "weak") else N
+    r = measure(gN, True)
+    weak = None
+    if world > 1 and args.scaling == "both":
+        weak = measure(N * world, False)
+
     if rank == 0:
-        total_particles = gN
-        value = total_particles * K / (ms / 1e3)
-        bytes_alg_step = n_loc * (16.0 * M * M + 8.0 * M * (2 * d + 2))   # per GPU
-        kal_ms = phases["kalman"] / K
+        n_loc = gN // world
+        M, d = r["M"], r["d"]
+        packed = args.variant in (-1, 7)
+        slab_bytes = (r["ld"] // 8) * (r["ld"] // 8 + 1) // 2 * 512 if packed else r["ld"] * M * 8
+        value = gN * K / (r["ms"] / 1e3)
+        bytes_alg_step = n_loc * (16.0 * M * M + 8.0 * M * (2 * d + 2))   # per GPU, SURVEY 8(d)
+        kal_ms = r["phases"]["kalman"] / K
         peak, peak_src = measured_peak()
         achieved = bytes_alg_step / (kal_ms / 1e3) / 1e9 if kal_ms > 0 else None
+        per = traffic_entry(M, args.variant)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+            "ms_per_step": r["ms"] / K, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "N_particles_total": gN, "N_particles_per_gpu": n_loc, "m_basis": m,
                        "M_linear_states": M, "d_meas": d,
-                       "state_bytes_per_gpu": n_loc * ctx.ld * M * 8,
+                       "kalman_variant": args.variant,
+                       "slab_layout": "packed symmetric 8x8 tiles (lower block triangle)" if packed
+                                      else "full column-major [ld x M]",
+                       "state_bytes_per_gpu": n_loc * slab_bytes,
                        "parallelism": ("one filter, particles sharded %d per GPU; peer-memory "
                                        "all-gather of log-weights + migration of surplus slabs" % n_loc)
                        if world > 1 else "single",
                        "l2": "inputs (%.1f GB of covariance slabs per GPU per step) far larger than L2"
-                             % (n_loc * ctx.ld * M * 8 / 1e9),
+                             % (n_loc * slab_bytes / 1e9),
                        "rng": "device Philox4x32-10"},
-            "clocks": clocks,
-            "e2e": {"value": total_particles * T / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": (cB["h2d_bytes"] - cA["h2d_bytes"]) / T,
-                    "d2h_bytes_per_step": (cB["d2h_bytes"] - cA["d2h_bytes"]) / T,
+            "clocks": r["clocks"],
+            "e2e": {"value": gN * T / r["e2e_s"], "unit": UNIT,
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "what": "rbslam_filter_run from host buffers: upload, init of %d slabs, %d steps, "
                             "final extraction, download" % (n_loc, T)},
-            "gpu_launches": launches,
+            "gpu_launches": r["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(M, n_loc),
+                         "frac": achieved / peak if achieved else None,
+                         "traffic": per * n_loc if per else None,
                          "kernel": "Kalman update phase (gather + log-weight + rank-%d downdate)" % d,
                          "algorithmic_bytes_per_launch": bytes_alg_step,
+                         "achieved_on_traffic": (per * n_loc / (kal_ms / 1e3) / 1e9) if (per and kal_ms > 0) else None,
+                         "note": "achieved = SURVEY 8(d) algorithmic bytes (full slab read + written) / kernel time; "
+                                 "the packed kernel moves about half of them, so frac reads above 1; "
+                                 "achieved_on_traffic uses the ncu-measured DRAM bytes of this kernel",
                          "kernel_ms_per_step": kal_ms, "peak_source": peak_src,
                          # the sharded step times its migration planner in the slot the
                          # single-GPU information-form filter uses for its own phase
                          "phases_ms_per_step": {("plan" if (k == "info" and world > 1) else k): v / K
-                                                for k, v in phases.items() if v > 0}},
+                                                for k, v in r["phases"].items() if v > 0}},
         }
+        if weak is not None:
+            line["weak"] = {"value": N * world * K / (weak["ms"] / 1e3), "unit": UNIT,
+                            "N_particles_total": N * world, "N_particles_per_gpu": N,
+                            "ms_per_step": weak["ms"] / K,
+                            "phases_ms_per_step": {("plan" if k == "info" else k): v / K
+                                                   for k, v in weak["phases"].items() if v > 0}}
+        if world == 1 and not args.no_smoother:
+            line["smoother"] = smoother_block(rbslam, local_rank)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(pr, m, args.cpu_sample_particles,
                                                 args.cpu_sample_steps)

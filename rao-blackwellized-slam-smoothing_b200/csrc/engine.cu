@@ -271,7 +271,7 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
     return ctx->fail(RBSLAM_EARG, "information form needs d<=3 and M<=1536");
   // packed symmetric tile slabs (packed_kernels.cuh): explicit (7), or chosen by the filter-only
   // auto mode (-1) whenever the streaming path would be used
-  const bool pt_ok = d <= 4 && (ctx->ld % 8) == 0 && ctx->ld / 8 <= 135 && !cfg->information_form;
+  const bool pt_ok = d <= 4 && (ctx->ld % 8) == 0 && ctx->ld / 8 <= 140 && !cfg->information_form;
   if (cfg->kalman_variant == 7 && !pt_ok)
     return ctx->fail(RBSLAM_EARG, "kalman_variant 7 needs d<=4, ld a multiple of 8, M<=1080 and the covariance form");
   if (cfg->kalman_variant >= 4 && cfg->kalman_variant <= 6)
@@ -283,7 +283,6 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
     ctx->slab = pt_slab_doubles(ctx->ld);
     if (const char *e = getenv("RBSLAM_PT_CFG")) { int ts = 48, ns = 4; if (sscanf(e, "%d,%d", &ts, &ns) == 2) { ctx->pt_ts = ts; ctx->pt_ns = ns; } }
     if (ctx->pt_ns < 2 || ctx->pt_ns > 8 || ctx->pt_ts < 1) return ctx->fail(RBSLAM_EARG, "RBSLAM_PT_CFG: need 2..8 slots");
-    if (const char *e = getenv("RBSLAM_PT_NW")) ctx->pt_nw = atoi(e) == 7 ? 7 : 15;
     while (ctx->pt_ns > 2 && pt_smem_bytes(ctx->ld, ctx->pt_ts, ctx->pt_ns, ctx->pt_nw) + 2048 > ctx->smem_optin) --ctx->pt_ns;
     if (pt_smem_bytes(ctx->ld, ctx->pt_ts, ctx->pt_ns, ctx->pt_nw) + 2048 > ctx->smem_optin)
       return ctx->fail(RBSLAM_EARG, "packed streaming pass does not fit shared memory");
@@ -801,7 +800,7 @@ static int launch_pt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
       fl.work_counter = cnts + 2 + phase;
       fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
       fl.child = base + 4 * (size_t)N;
-      fkern<<<fgrid, 32 * (NW + 1), fsmem, ctx->stream>>>(pa, fl);
+      fkern<<<fgrid, 32 * (NW + 2), fsmem, ctx->stream>>>(pa, fl);
       ctx->launches += 1;
     }
   }
@@ -826,8 +825,7 @@ static int launch_pt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
 static int launch_pt(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   // MAXQ = row blocks per consumer warp: NW warps share ld / 8 blocks
   const int nb = ctx->ld / 8;
-  if (ctx->pt_nw == 7) return nb <= 70 ? launch_pt_q<7, 10>(ctx, a, resampled) : launch_pt_q<7, 20>(ctx, a, resampled);
-  return nb <= 75 ? launch_pt_q<15, 5>(ctx, a, resampled) : launch_pt_q<15, 9>(ctx, a, resampled);
+  return nb <= 70 ? launch_pt_q<14, 5>(ctx, a, resampled) : launch_pt_q<14, 10>(ctx, a, resampled);
 }
 
 // apply the deferred downdate to every slab (before the state is read out as a whole)

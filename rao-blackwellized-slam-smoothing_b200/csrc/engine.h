@@ -45,8 +45,8 @@ struct rbslam_ctx {
   // kalman_variant 7: packed symmetric tile slabs (packed_kernels.cuh)
   bool pt = false;
   int layout = 0;            // RB_LAYOUT_FULL / _SYM / _PT: how element (r,c) of a slab is stored
-  int pt_ts = 48, pt_ns = 4; // tiles per stage, ring slots (RBSLAM_PT_CFG="TS,NS")
-  int pt_nw = 15;            // consumer warps per CTA: 15 (128 registers each) or 7 (255) (RBSLAM_PT_NW)
+  int pt_ts = 84, pt_ns = 3; // tiles per stage, ring slots (RBSLAM_PT_CFG="TS,NS")
+  int pt_nw = 14;            // consumer warps per CTA (+ reducer + producer = 16 warps x 128 registers)
   int pt_psplit[9] = {0};    // panel ranges of the nsplit items per family
   const int *item_group = nullptr;   // sharded engine: work group of each local item (see stream_groups)
   int stream_ctas_per_sm = 0, stream_hints = 0;   // tuning knobs (env)

@@ -29,9 +29,10 @@
 //     and one 16-byte store per sibling.  The products use the tile BEFORE its pending
 //     downdate; k_innov4 completes them (Innov4Args::G4prev), exactly as kalman_variant 5 did;
 //   * warp w owns the row blocks j = w (mod NW): its row-side accumulators and its KS fragments
-//     stay in registers for the whole pass; per-batch operands (G of the ancestor, the
-//     siblings' H in fragment order) live in shared memory; the column-side tiles of the
-//     warps are added in fixed order once per panel behind a named barrier.
+//     stay in registers for the whole pass; the siblings' H live in shared memory in fragment
+//     order, G of the ancestor is prefetched one panel ahead; the column-side tiles of the
+//     consumer warps go through a small ring of buffers to a reducer warp that adds them in
+//     fixed order (deterministic) - the consumers never wait for each other inside a batch.
 // HBM traffic per particle-step: half of k_stream_fam's (4.3 MB read per pass over a family's slab,
 // 4.3 MB written per particle at M = 1027).
 #pragma once
@@ -127,6 +128,7 @@ k_apply_pending_pt(double *__restrict__ P, size_t slab, int ld, const int *__res
 // ---------------------------------------------------------------------------
 #define RB_PT_CB 2                          // siblings per pass: n = 2 x 4 output columns
 #define RB_PT_MAXSPLIT 8
+#define RB_PT_NBUF 4                        // column-side partial tiles in flight (panels)
 
 struct PtArgs {
   int M, ld, nb, nsplit;
@@ -144,39 +146,43 @@ struct PtArgs {
 struct PtDesc {   // what a ring slot holds; item < 0: no more work
   int item, b0, t0, nt, p, j;
 };
+struct PtColDesc {   // what a column-side buffer holds: panel p of the batch (ch0, ch1); p < 0: no more work
+  int p, ch0, ch1;
+};
 
 static inline size_t pt_smem_bytes(int ld, int ts, int ns, int nw) {
   const int nb = ld >> 3;
-  return (size_t)ns * ts * 512 + (size_t)ld * 32 + (size_t)nb * 32 * 16 + (size_t)2 * nw * 64 * 8;
+  return (size_t)ns * ts * 512 + (size_t)nb * 32 * 16 + (size_t)RB_PT_NBUF * nw * 64 * 8;
 }
 
-// NW consumer warps + one producer warp; NW + 1 is a multiple of 4 (registers are allocated to
-// warps in groups of four: 16 warps x 128 registers or 8 warps x 255)
+// Warp roles: NW consumer warps, one reducer warp (NW), one producer warp (NW + 1).  NW + 2 is a
+// multiple of 4 (registers are allocated to warps in groups of four: 16 warps x 128 registers).
 template <int NW, int MAXQ>
-__global__ void __launch_bounds__(32 * (NW + 1), 1)
+__global__ void __launch_bounds__(32 * (NW + 2), 1)
 k_stream_fam_pt(PtArgs a, FamLists f) {
-  constexpr int CB = RB_PT_CB;
+  constexpr int CB = RB_PT_CB, NBUF = RB_PT_NBUF;
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ __align__(8) uint64_t full[8], empty[8];
+  __shared__ __align__(8) uint64_t full[8], empty[8], colfull[NBUF], colfree[NBUF];
   __shared__ PtDesc s_desc[8];
+  __shared__ PtColDesc s_cdesc[NBUF];
   __shared__ int s_psplit[RB_PT_MAXSPLIT + 1];   // (a parameter array indexed at run time would live in local memory)
   const int ld = a.ld, nb = a.nb, TS = a.ts, NS = a.ns;
-  double *ring = reinterpret_cast<double *>(smraw);                       // [NS][TS][64]
-  double *s_G = ring + (size_t)NS * TS * 64;                              // [ld][4] verbatim
-  double2 *s_bC = reinterpret_cast<double2 *>(s_G + (size_t)ld * 4);      // [nb][32] fragment order
-  double *s_colp = reinterpret_cast<double *>(s_bC + (size_t)nb * 32);    // [2][NW][64]
+  double *ring = reinterpret_cast<double *>(smraw);                             // [NS][TS][64]
+  double2 *s_bC = reinterpret_cast<double2 *>(ring + (size_t)NS * TS * 64);     // [nb][32] fragment order
+  double *s_colp = reinterpret_cast<double *>(s_bC + (size_t)nb * 32);          // [NBUF][NW][64]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int n_items = (*f.n_fam) * a.nsplit;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    for (int s = 0; s < NBUF; ++s) { mbar_init(&colfull[s], NW); mbar_init(&colfree[s], 1); }
     mbar_fence_init();
 #pragma unroll
     for (int s = 0; s <= RB_PT_MAXSPLIT; ++s) s_psplit[s] = a.psplit[s];
   }
   __syncthreads();
 
-  if (wid == NW) {
+  if (wid == NW + 1) {
     // ================= producer warp: one lane walks item -> batch -> stage ==============
     if (lane != 0) return;
     int it = atomicAdd(f.work_counter, 1);
@@ -222,18 +228,42 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
     return;
   }
 
+  if (wid == NW) {
+    // ================= reducer warp: adds the consumers' column-side tiles, panel by panel, in
+    // fixed warp order (deterministic), and stores PHcol(8p.., n) of both siblings ==========
+    const int col_slot = a.nsplit;
+    for (int n = 0;; ++n) {
+      const int buf = n % NBUF;
+      mbar_wait(&colfull[buf], (uint32_t)((n / NBUF) & 1));
+      const PtColDesc cd = s_cdesc[buf];
+      if (cd.p < 0) break;
+      const double2 *part = reinterpret_cast<const double2 *>(s_colp + (size_t)buf * NW * 64) + lane;
+      double2 sum = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { const double2 v = part[w * 32]; sum.x += v.x; sum.y += v.y; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&colfree[buf]);
+      // lane holds PHcol(8p + g, n = 2tg, 2tg + 1): sibling tg >> 1, entries 2 (tg & 1), +1
+      const int ch = (tg >> 1) == 0 ? cd.ch0 : cd.ch1;
+      if (ch >= 0)
+        *reinterpret_cast<double2 *>(a.PHp + (((size_t)ch * (a.nsplit + 1) + col_slot) * ld + (8 * cd.p + g)) * 4 + 2 * (tg & 1)) = sum;
+    }
+    return;
+  }
+
   // ================= consumer warps ======================================================
   // fragment offsets inside a tile: (row g, cols 2tg..2tg+1) and (rows 2tg, 2tg+1, col g)
   const int offC = pt_pos(g, 2 * tg), offT0 = pt_pos(2 * tg, g), offT1 = pt_pos(2 * tg + 1, g);
-  int cur_item = -1, cur_b0 = -1, cur_fam = -1;
+  int cur_item = -1, cur_b0 = -1;
   int sp = 0, nv = 0;
   int child[CB] = {-1, -1};
   double *Pd[CB] = {nullptr, nullptr};
+  const double *Ga = nullptr;   // pending gain of the family's ancestor, [ld][4]: G(8p + g, tg) at Ga[32 p + lane]
   double acc[MAXQ][2], ksA[MAXQ];
 #pragma unroll
   for (int qq = 0; qq < MAXQ; ++qq) { acc[qq][0] = acc[qq][1] = 0.0; ksA[qq] = 0.0; }
-  double col0 = 0.0, col1 = 0.0, gB = 0.0, hB0 = 0.0, hB1 = 0.0;
-  int n_panel = 0;   // panels finished so far (parity selects the s_colp buffer)
+  double col0 = 0.0, col1 = 0.0, gB = 0.0, gB_next = 0.0, hB0 = 0.0, hB1 = 0.0;
+  int n_panel = 0;   // panels finished so far by this warp (selects the column-side buffer)
   int cur_p = -1;    // panel whose gB / hB are loaded
 
   auto flush_rows = [&]() {   // row-side slot of the batch that just ended: lane holds PHrow(8j+g, n = 2tg, 2tg+1)
@@ -250,6 +280,17 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
     }
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq) acc[qq][0] = acc[qq][1] = 0.0;
+  };
+  // hand this warp's column-side tile of panel p to the reducer (p < 0: end of work)
+  auto post_col = [&](int p) {
+    const int buf = n_panel % NBUF;
+    if (n_panel >= NBUF) mbar_wait(&colfree[buf], (uint32_t)((n_panel / NBUF - 1) & 1));
+    *reinterpret_cast<double2 *>(s_colp + ((size_t)(buf * NW + wid) * 64 + 2 * lane)) = make_double2(col0, col1);
+    if (wid == 0 && lane == 0) { PtColDesc cd; cd.p = p; cd.ch0 = child[0]; cd.ch1 = child[1]; s_cdesc[buf] = cd; }
+    col0 = col1 = 0.0;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&colfull[buf]);
+    ++n_panel;
   };
 
   int slot = 0, round = 0;
@@ -268,21 +309,16 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
         child[s] = s < nv ? f.child[first + d.b0 + s] : -1;
         Pd[s] = s < nv ? a.P + (size_t)a.dst_slot[child[s]] * a.slab : nullptr;
       }
-      // every consumer is past the last panel barrier of the previous batch: the operand
-      // arrays in shared memory may be rewritten
-      if (fam != cur_fam || d.item != cur_item) {
+      if (d.item != cur_item) {   // KS fragments of the family's ancestor: registers for the whole item
         const double *KSa = a.KS4prev + (size_t)f.anc[fam] * ld * 4;
+        Ga = a.G4prev + (size_t)f.anc[fam] * ld * 4;
 #pragma unroll
         for (int qq = 0; qq < MAXQ; ++qq) {
           const int jj = wid + NW * qq;
           ksA[qq] = jj < nb ? -KSa[(size_t)jj * 32 + lane] : 0.0;   // -KS(8jj + g, tg)
         }
-        if (fam != cur_fam) {
-          const double2 *Ga = reinterpret_cast<const double2 *>(a.G4prev + (size_t)f.anc[fam] * ld * 4);
-          double2 *sg = reinterpret_cast<double2 *>(s_G);
-          for (int idx = tid; idx < ld * 2; idx += NW * 32) sg[idx] = Ga[idx];
-        }
       }
+      named_barrier_sync(1, NW * 32);   // every consumer is done with the previous batch's operands
       {   // siblings' H in fragment order: s_bC[j][lane] = H_s(b, 8j + 2tg + {0, 1}), n = g = 4s + b
         const double *H0 = a.H4 + (size_t)child[0] * ld * 4;
         const double *H1 = nv > 1 ? a.H4 + (size_t)child[1] * ld * 4 : nullptr;
@@ -297,25 +333,30 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
           s_bC[idx] = v;
         }
       }
-      cur_item = d.item; cur_b0 = d.b0; cur_fam = fam; cur_p = -1;
+      cur_item = d.item; cur_b0 = d.b0; cur_p = -1;
+      gB_next = Ga[(size_t)d.p * 32 + lane];
       named_barrier_sync(1, NW * 32);
     }
     const double *st = ring + (size_t)slot * TS * 64;
     int t = 0, p = d.p, j = d.j;
     while (t < d.nt) {
       const int seg = min(d.nt - t, nb - j), jend = j + seg;
-      if (p != cur_p) {   // operands of the panel: G(8p + g, tg) and the siblings' H at columns 8p..
-        gB = s_G[(size_t)p * 32 + lane];
+      if (p != cur_p) {   // operands of the panel: G(8p + g, tg) (prefetched one panel ahead) and the siblings' H at columns 8p..
+        gB = gB_next;
+        if (p + 1 < nb) gB_next = Ga[(size_t)(p + 1) * 32 + lane];
         const double2 hv = s_bC[(size_t)p * 32 + lane];
         hB0 = hv.x; hB1 = hv.y;
         cur_p = p;
       }
       const double *tb = st + (long long)(t - j) * 64;       // tile (jj, p) of this stage at tb + jj * 64
       const size_t gt = (size_t)(d.t0 + t - j) * 64 + offC;  // same, in the slab
+      // this warp's row blocks in [j, jend): jj = wid + NW qq, qq in [qlo, qhi)
+      const int qlo = j > wid ? (j - wid + NW - 1) / NW : 0;
+      const int qhi = jend > wid ? (jend - wid + NW - 1) / NW : 0;
 #pragma unroll
       for (int qq = 0; qq < MAXQ; ++qq) {
-        const int jj = wid + NW * qq;
-        if (jj >= j && jj < jend) {
+        if (qq >= qlo && qq < qhi) {
+          const int jj = wid + NW * qq;
           const double *tp = tb + (size_t)jj * 64;
           double2 tv = *reinterpret_cast<const double2 *>(tp + offC);
           dmma_m8n8k4(acc[qq][0], acc[qq][1], tv.x, hB0);      // row side, tile before its downdate
@@ -333,38 +374,19 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
         }
       }
       t += seg;
-      if (jend == nb) {   // the panel is complete: add the consumer warps' column-side tiles in fixed order
-        const int buf = n_panel & 1;
-        *reinterpret_cast<double2 *>(s_colp + ((size_t)(buf * NW + wid) * 64 + g * 8 + 2 * tg)) = make_double2(col0, col1);
-        col0 = col1 = 0.0;
-        if (t >= d.nt) {   // last use of the slot by this warp: release it before the barrier
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[slot]);
-        }
-        named_barrier_sync(1, NW * 32);
-        if (tid < 64) {
-          const int u = tid >> 3, n = tid & 7, s = n >> 2;
-          if (s < nv) {
-            double sum = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) sum += s_colp[(size_t)(buf * NW + w) * 64 + tid];
-            const int ch = s == 0 ? child[0] : child[1];
-            a.PHp[(((size_t)ch * (a.nsplit + 1) + a.nsplit) * ld + (8 * p + u)) * 4 + (n & 3)] = sum;
-          }
-        }
-        ++n_panel;
+      if (jend == nb) {   // the panel is complete
+        post_col(p);
         ++p; j = p;
-        if (t >= d.nt) goto released;
       } else {
         j = jend;
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[slot]);   // this warp has read everything it needs from the slot
-  released:
     if (++slot == NS) { slot = 0; ++round; }
   }
   if (cur_item >= 0) flush_rows();
+  post_col(-1);   // terminal marker for the reducer
 }
 
 }  // namespace rb
