@@ -148,6 +148,10 @@ typedef struct {
   int32_t *ak;             /* [N_K] sampled trajectory index per sweep, 0-based */
 } rbslam_smoother_outputs;
 
+/* called after every time step t = 0..T-1 (the filter's makePlots hook, src/particleFilter.m:215-217) and,
+   by rbslam_smoother_run, once more per sweep with t == T when the sweep's outputs XNK(:,:,sweep),
+   XLK(:,sweep), PK(:,:,sweep) have been written (the smoother's makePlots hook and progress line,
+   src/particleSmoother.m:359-365) */
 typedef void (*rbslam_step_fn)(void *user, int32_t sweep, int32_t t);
 
 /* ---- life cycle --------------------------------------------------------- */
@@ -179,6 +183,13 @@ RBSLAM_API int rbslam_sync(rbslam_ctx *ctx);                     /* wait for enq
    xn [n x N], xl [M x N], P [M x M x N], logw [N], w [N], ai [N] */
 RBSLAM_API int rbslam_read_particles(rbslam_ctx *ctx, double *xn, double *xl, double *P, double *logw,
                           double *w, int32_t *ai);
+/* the trajectory outputs as the reference holds them when it calls makePlots at step t
+   (src/particleFilter.m:92-97,215-217): traj_max, traj_mean [n x T] and yhattraj [d x T] (predicted
+   measurement of the highest-weight particle; recorded while a step callback is registered) with NaN in
+   the columns of steps not yet run, xn_traj [n x N x T] (genealogy of the current particles) with zero
+   pages.  Any pointer may be NULL. */
+RBSLAM_API int rbslam_read_trajectories(rbslam_ctx *ctx, double *traj_max, double *traj_mean, double *yhattraj,
+                             double *xn_traj);
 /* information-form extras: ivec [M x N], Imat [M x M x N], halfLogDetP [N] */
 RBSLAM_API int rbslam_read_information(rbslam_ctx *ctx, double *ivec, double *Imat, double *halfLogDetP);
 /* counters since context creation: kernels launched by this library, bytes copied */

@@ -145,7 +145,23 @@ __global__ void k_trace(int N, int n, int T, const double *__restrict__ X, const
   }
 }
 
-// transpose taps [T][N] -> MATLAB [N x T] is the same memory; nothing to do.
+// yhattraj(:,t) = predicted measurement of the highest-weight particle (src/particleFilter.m:200-203):
+// dense families yhat = H_i * xl_i with the mean BEFORE the update, sparse family the model's yhat.
+// Only evaluated when a step callback (the makePlots hook) is registered.
+__global__ void k_yhat_max(int M, int d, const int *__restrict__ iw_max, const double *__restrict__ H, size_t hs_p,
+                           int hs_a, int hs_c, const double *__restrict__ xl_old, const int *__restrict__ anc,
+                           const double *__restrict__ yhat_model, double *__restrict__ out) {
+  const int i = *iw_max;
+  const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (a >= d) return;
+  if (yhat_model) { if (lane == 0) out[a] = yhat_model[a + (size_t)i * d]; return; }
+  const double *x = xl_old + (size_t)(anc ? anc[i] : i) * M;
+  const double *Hi = H + (size_t)i * hs_p + (size_t)a * hs_a;
+  double acc = 0.0;
+  for (int c = lane; c < M; c += 32) acc = fma(Hi[(size_t)c * hs_c], x[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[a] = acc;
+}
 
 // ---------------------------------------------------------------------------
 // helpers
@@ -271,7 +287,7 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
     return ctx->fail(RBSLAM_EARG, "information form needs d<=3 and M<=1536");
   // packed symmetric tile slabs (packed_kernels.cuh): explicit (7), or chosen by the filter-only
   // auto mode (-1) whenever the streaming path would be used
-  const bool pt_ok = d <= 4 && (ctx->ld % 8) == 0 && ctx->ld / 8 <= 140 && !cfg->information_form;
+  const bool pt_ok = d <= 4 && (ctx->ld % 8) == 0 && ctx->ld / 8 <= 135 && !cfg->information_form;
   if (cfg->kalman_variant == 7 && !pt_ok)
     return ctx->fail(RBSLAM_EARG, "kalman_variant 7 needs d<=4, ld a multiple of 8, M<=1080 and the covariance form");
   if (cfg->kalman_variant >= 4 && cfg->kalman_variant <= 6)
@@ -422,7 +438,7 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
                   ctx->d_counts, ctx->d_H, ctx->d_yhat, ctx->d_PHpart, ctx->d_G, ctx->d_KS,
                   ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_PHp, ctx->d_fam,
                   ctx->d_logw, ctx->d_w, ctx->d_wc, ctx->d_Xhist, ctx->d_Ahist, ctx->d_traj_max,
-                  ctx->d_traj_mean, ctx->d_iwmax, ctx->d_status, ctx->d_scratch};
+                  ctx->d_traj_mean, ctx->d_iwmax, ctx->d_status, ctx->d_scratch, ctx->d_yhattraj};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (auto e : ctx->ph_events) cudaEventDestroy(e);
   for (auto &e : ctx->user_events) if (e) cudaEventDestroy(e);
@@ -800,7 +816,7 @@ static int launch_pt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
       fl.work_counter = cnts + 2 + phase;
       fl.src = base; fl.anc = base + N; fl.first = base + 2 * (size_t)N; fl.cnt = base + 3 * (size_t)N;
       fl.child = base + 4 * (size_t)N;
-      fkern<<<fgrid, 32 * (NW + 2), fsmem, ctx->stream>>>(pa, fl);
+      fkern<<<fgrid, 32 * (NW + 1), fsmem, ctx->stream>>>(pa, fl);
       ctx->launches += 1;
     }
   }
@@ -825,7 +841,7 @@ static int launch_pt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
 static int launch_pt(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   // MAXQ = row blocks per consumer warp: NW warps share ld / 8 blocks
   const int nb = ctx->ld / 8;
-  return nb <= 70 ? launch_pt_q<14, 5>(ctx, a, resampled) : launch_pt_q<14, 10>(ctx, a, resampled);
+  return nb <= 75 ? launch_pt_q<15, 5>(ctx, a, resampled) : launch_pt_q<15, 9>(ctx, a, resampled);
 }
 
 // apply the deferred downdate to every slab (before the state is read out as a whole)
@@ -1014,6 +1030,15 @@ static int filter_step_impl(rbslam_ctx *ctx) {
   rb_phase_end(ctx);
   ctx->t += 1;
   if (ctx->step_fn) {
+    if (!ctx->d_yhattraj) {
+      RB_ALLOC(ctx->d_yhattraj, (size_t)ctx->T * ctx->d);
+    }
+    const bool sparse = ctx->mc.family == FAM_SPARSE_VISUAL2D;
+    k_yhat_max<<<1, 32 * ctx->d, 0, ctx->stream>>>(
+        ctx->M, ctx->d, ctx->d_iwmax + t, ctx->d_H, ctx->hs_p, ctx->hs_a, ctx->hs_c, ctx->d_xl[1 - ctx->cx],
+        resampled ? ctx->d_Ahist + (size_t)(t % ctx->T_hist) * N : nullptr, sparse ? ctx->d_yhat : nullptr,
+        ctx->d_yhattraj + (size_t)t * ctx->d);
+    ctx->launches += 1;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->step_fn(ctx->step_user, ctx->sweep, t);
   }
@@ -1164,6 +1189,45 @@ extern "C" int rbslam_read_particles(rbslam_ctx *ctx, double *xn, double *xl, do
   if (logw && (rc = rb_d2h(ctx, logw, ctx->d_logw, sizeof(double) * N))) return rc;
   if (w && (rc = rb_d2h(ctx, w, ctx->d_w, sizeof(double) * N))) return rc;
   if (ai && (rc = rb_d2h(ctx, ai, ctx->d_Ahist + (size_t)tl * N, sizeof(int) * N))) return rc;
+  return RBSLAM_OK;
+}
+
+// the trajectory outputs as the reference holds them when it calls makePlots at step t
+// (src/particleFilter.m:92-97, 215-217): columns / pages of steps not yet run are NaN (traj_max,
+// traj_mean, yhattraj) or zero (xn_traj)
+extern "C" int rbslam_read_trajectories(rbslam_ctx *ctx, double *traj_max, double *traj_mean, double *yhattraj,
+                                        double *xn_traj) {
+  if (!ctx) return RBSLAM_EARG;
+  if (ctx->shard_ws) return ctx->fail(RBSLAM_EARG, "read_trajectories is not available on a sharded context");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int N = ctx->N, n = ctx->n, d = ctx->d, T = ctx->run_T, t = ctx->t;   // t steps are complete
+  if (T < 1 || t < 1 || t > T) return ctx->fail(RBSLAM_EARG, "read_trajectories: no completed step");
+  int rc;
+  const double nanv = nan("");
+  if (traj_max) {
+    for (size_t q = (size_t)n * t; q < (size_t)n * T; ++q) traj_max[q] = nanv;
+    if ((rc = rb_d2h(ctx, traj_max, ctx->d_traj_max, sizeof(double) * n * t))) return rc;
+  }
+  if (traj_mean) {
+    for (size_t q = (size_t)n * t; q < (size_t)n * T; ++q) traj_mean[q] = nanv;
+    if ((rc = rb_d2h(ctx, traj_mean, ctx->d_traj_mean, sizeof(double) * n * t))) return rc;
+  }
+  if (yhattraj) {
+    if (!ctx->d_yhattraj) return ctx->fail(RBSLAM_EARG, "yhattraj is recorded only while a step callback is registered");
+    for (size_t q = (size_t)d * t; q < (size_t)d * T; ++q) yhattraj[q] = nanv;
+    if ((rc = rb_d2h(ctx, yhattraj, ctx->d_yhattraj, sizeof(double) * d * t))) return rc;
+  }
+  if (xn_traj) {
+    if (!ctx->cfg.keep_history) return ctx->fail(RBSLAM_EARG, "xn_traj needs keep_history=1");
+    for (size_t q = (size_t)n * N * t; q < (size_t)n * N * T; ++q) xn_traj[q] = 0.0;
+    double *tmp = nullptr;
+    RB_ALLOC(tmp, (size_t)n * N * t);
+    k_trace<<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, n, t, ctx->d_Xhist, ctx->d_Ahist, nullptr, tmp);
+    ctx->launches += 1;
+    rc = rb_d2h(ctx, xn_traj, tmp, sizeof(double) * n * N * t);
+    cudaFree(tmp);
+    if (rc) return rc;
+  }
   return RBSLAM_OK;
 }
 

@@ -46,7 +46,7 @@ struct rbslam_ctx {
   bool pt = false;
   int layout = 0;            // RB_LAYOUT_FULL / _SYM / _PT: how element (r,c) of a slab is stored
   int pt_ts = 84, pt_ns = 3; // tiles per stage, ring slots (RBSLAM_PT_CFG="TS,NS")
-  int pt_nw = 14;            // consumer warps per CTA (+ reducer + producer = 16 warps x 128 registers)
+  int pt_nw = 15;            // consumer warps per CTA (+ the service warp = 16 warps x 128 registers)
   int pt_psplit[9] = {0};    // panel ranges of the nsplit items per family
   const int *item_group = nullptr;   // sharded engine: work group of each local item (see stream_groups)
   int stream_ctas_per_sm = 0, stream_hints = 0;   // tuning knobs (env)
@@ -57,6 +57,7 @@ struct rbslam_ctx {
   int T_hist = 2;
   double *d_traj_max = nullptr, *d_traj_mean = nullptr;   // [T][n]
   int *d_iwmax = nullptr;        // [T]
+  double *d_yhattraj = nullptr;  // [T][d] predicted measurement of the highest-weight particle (makePlots tap)
   double *d_logw_hist = nullptr, *d_w_hist = nullptr;     // [T][N] optional taps
   rb::DevStatus *d_status = nullptr;
   double *d_scratch = nullptr;   // misc outputs (xl_mean, P_mean, ...)

@@ -146,6 +146,11 @@ struct PtArgs {
 struct PtDesc {   // what a ring slot holds; item < 0: no more work
   int item, b0, t0, nt, p, j;
 };
+struct PtBatch {     // state of the batch the consumers work on (uniform over the CTA)
+  int item, b0, sp, ch0, ch1;
+  double *Pd0, *Pd1;
+  const double *Ga;    // pending gain of the family's ancestor, [ld][4]: G(8p + g, tg) at Ga[32 p + lane]
+};
 struct PtColDesc {   // what a column-side buffer holds: panel p of the batch (ch0, ch1); p < 0: no more work
   int p, ch0, ch1;
 };
@@ -155,16 +160,17 @@ static inline size_t pt_smem_bytes(int ld, int ts, int ns, int nw) {
   return (size_t)ns * ts * 512 + (size_t)nb * 32 * 16 + (size_t)RB_PT_NBUF * nw * 64 * 8;
 }
 
-// Warp roles: NW consumer warps, one reducer warp (NW), one producer warp (NW + 1).  NW + 2 is a
-// multiple of 4 (registers are allocated to warps in groups of four: 16 warps x 128 registers).
+// Warp roles: NW consumer warps and one service warp (lane 0 = producer, lanes 1..31 = reducer).
+// NW + 1 is a multiple of 4 (registers are allocated to warps in groups of four: 16 warps x 128).
 template <int NW, int MAXQ>
-__global__ void __launch_bounds__(32 * (NW + 2), 1)
+__global__ void __launch_bounds__(32 * (NW + 1), 1)
 k_stream_fam_pt(PtArgs a, FamLists f) {
   constexpr int CB = RB_PT_CB, NBUF = RB_PT_NBUF;
   extern __shared__ __align__(128) unsigned char smraw[];
   __shared__ __align__(8) uint64_t full[8], empty[8], colfull[NBUF], colfree[NBUF];
   __shared__ PtDesc s_desc[8];
   __shared__ PtColDesc s_cdesc[NBUF];
+  __shared__ PtBatch s_bat;
   __shared__ int s_psplit[RB_PT_MAXSPLIT + 1];   // (a parameter array indexed at run time would live in local memory)
   const int ld = a.ld, nb = a.nb, TS = a.ts, NS = a.ns;
   double *ring = reinterpret_cast<double *>(smraw);                             // [NS][TS][64]
@@ -179,12 +185,12 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
     mbar_fence_init();
 #pragma unroll
     for (int s = 0; s <= RB_PT_MAXSPLIT; ++s) s_psplit[s] = a.psplit[s];
+    s_bat.item = -1; s_bat.b0 = -1; s_bat.ch0 = s_bat.ch1 = -1;
   }
   __syncthreads();
 
-  if (wid == NW + 1) {
-    // ================= producer warp: one lane walks item -> batch -> stage ==============
-    if (lane != 0) return;
+  if (wid == NW && lane == 0) {
+    // ================= producer: one lane walks item -> batch -> stage ===================
     int it = atomicAdd(f.work_counter, 1);
     int b = 0;
     bool fresh = true;         // (it, b) just changed: (re)start the tile walk
@@ -229,36 +235,40 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
   }
 
   if (wid == NW) {
-    // ================= reducer warp: adds the consumers' column-side tiles, panel by panel, in
-    // fixed warp order (deterministic), and stores PHcol(8p.., n) of both siblings ==========
+    // ================= reducer (lanes 1..31 of the producer's warp; the two roles only ever wait
+    // on mbarriers, independent thread scheduling interleaves them): adds the consumers'
+    // column-side tiles, panel by panel, in fixed warp order (deterministic), and stores
+    // PHcol(8p.., n) of both siblings ========================================================
+    constexpr unsigned RMASK = 0xfffffffeu;
     const int col_slot = a.nsplit;
     for (int n = 0;; ++n) {
       const int buf = n % NBUF;
       mbar_wait(&colfull[buf], (uint32_t)((n / NBUF) & 1));
       const PtColDesc cd = s_cdesc[buf];
       if (cd.p < 0) break;
-      const double2 *part = reinterpret_cast<const double2 *>(s_colp + (size_t)buf * NW * 64) + lane;
-      double2 sum = make_double2(0.0, 0.0);
+      for (int e = lane - 1; e < 32; e += 31) {   // fragment slot e = 4 g' + tg' holds PHcol(8p + g', n = 2tg', 2tg' + 1)
+        const double2 *part = reinterpret_cast<const double2 *>(s_colp + (size_t)buf * NW * 64) + e;
+        double2 sum = make_double2(0.0, 0.0);
 #pragma unroll
-      for (int w = 0; w < NW; ++w) { const double2 v = part[w * 32]; sum.x += v.x; sum.y += v.y; }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&colfree[buf]);
-      // lane holds PHcol(8p + g, n = 2tg, 2tg + 1): sibling tg >> 1, entries 2 (tg & 1), +1
-      const int ch = (tg >> 1) == 0 ? cd.ch0 : cd.ch1;
-      if (ch >= 0)
-        *reinterpret_cast<double2 *>(a.PHp + (((size_t)ch * (a.nsplit + 1) + col_slot) * ld + (8 * cd.p + g)) * 4 + 2 * (tg & 1)) = sum;
+        for (int w = 0; w < NW; ++w) { const double2 v = part[w * 32]; sum.x += v.x; sum.y += v.y; }
+        const int ge = e >> 2, te = e & 3;
+        const int ch = (te >> 1) == 0 ? cd.ch0 : cd.ch1;   // sibling te >> 1, entries 2 (te & 1), +1
+        if (ch >= 0)
+          *reinterpret_cast<double2 *>(a.PHp + (((size_t)ch * (a.nsplit + 1) + col_slot) * ld + (8 * cd.p + ge)) * 4 + 2 * (te & 1)) = sum;
+      }
+      __syncwarp(RMASK);
+      if (lane == 1) mbar_arrive(&colfree[buf]);
     }
     return;
   }
 
   // ================= consumer warps ======================================================
+  // Everything that is uniform over the CTA for the length of a batch lives in shared memory
+  // (s_bat), not in registers: the register file is needed for the MAXQ row-block accumulators
+  // and KS fragments, and a spilled scalar costs an L2 round trip in this kernel (the L1 is a
+  // few KB next to a 220 KB shared-memory carve-out).
   // fragment offsets inside a tile: (row g, cols 2tg..2tg+1) and (rows 2tg, 2tg+1, col g)
   const int offC = pt_pos(g, 2 * tg), offT0 = pt_pos(2 * tg, g), offT1 = pt_pos(2 * tg + 1, g);
-  int cur_item = -1, cur_b0 = -1;
-  int sp = 0, nv = 0;
-  int child[CB] = {-1, -1};
-  double *Pd[CB] = {nullptr, nullptr};
-  const double *Ga = nullptr;   // pending gain of the family's ancestor, [ld][4]: G(8p + g, tg) at Ga[32 p + lane]
   double acc[MAXQ][2], ksA[MAXQ];
 #pragma unroll
   for (int qq = 0; qq < MAXQ; ++qq) { acc[qq][0] = acc[qq][1] = 0.0; ksA[qq] = 0.0; }
@@ -267,10 +277,9 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
   int cur_p = -1;    // panel whose gB / hB are loaded
 
   auto flush_rows = [&]() {   // row-side slot of the batch that just ended: lane holds PHrow(8j+g, n = 2tg, 2tg+1)
-    const int s = tg >> 1;
-    if (s < nv) {
-      const int ch = s == 0 ? child[0] : child[1];
-      double *out = a.PHp + ((size_t)ch * (a.nsplit + 1) + sp) * ld * 4;
+    const int ch = (tg >> 1) == 0 ? s_bat.ch0 : s_bat.ch1;
+    if (ch >= 0) {
+      double *out = a.PHp + ((size_t)ch * (a.nsplit + 1) + s_bat.sp) * ld * 4;
 #pragma unroll
       for (int qq = 0; qq < MAXQ; ++qq) {
         const int jj = wid + NW * qq;
@@ -286,7 +295,7 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
     const int buf = n_panel % NBUF;
     if (n_panel >= NBUF) mbar_wait(&colfree[buf], (uint32_t)((n_panel / NBUF - 1) & 1));
     *reinterpret_cast<double2 *>(s_colp + ((size_t)(buf * NW + wid) * 64 + 2 * lane)) = make_double2(col0, col1);
-    if (wid == 0 && lane == 0) { PtColDesc cd; cd.p = p; cd.ch0 = child[0]; cd.ch1 = child[1]; s_cdesc[buf] = cd; }
+    if (wid == 0 && lane == 0) { PtColDesc cd; cd.p = p; cd.ch0 = s_bat.ch0; cd.ch1 = s_bat.ch1; s_cdesc[buf] = cd; }
     col0 = col1 = 0.0;
     __syncwarp();
     if (lane == 0) mbar_arrive(&colfull[buf]);
@@ -296,32 +305,34 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
   int slot = 0, round = 0;
   for (;;) {
     mbar_wait(&full[slot], (uint32_t)(round & 1));
-    const PtDesc d = s_desc[slot];
-    if (d.item < 0) break;
-    if (d.item != cur_item || d.b0 != cur_b0) {   // a new batch starts (uniform over the consumers)
-      if (cur_item >= 0) flush_rows();
-      const int fam = d.item / a.nsplit;
-      sp = d.item % a.nsplit;
-      const int cnt = f.cnt[fam], first = f.first[fam];
-      nv = min(CB, cnt - d.b0);
-#pragma unroll
-      for (int s = 0; s < CB; ++s) {
-        child[s] = s < nv ? f.child[first + d.b0 + s] : -1;
-        Pd[s] = s < nv ? a.P + (size_t)a.dst_slot[child[s]] * a.slab : nullptr;
-      }
-      if (d.item != cur_item) {   // KS fragments of the family's ancestor: registers for the whole item
+    const int d_item = s_desc[slot].item;
+    if (d_item < 0) break;
+    if (d_item != s_bat.item || s_desc[slot].b0 != s_bat.b0) {   // a new batch starts (uniform over the consumers)
+      if (s_bat.item >= 0) flush_rows();
+      const int fam = d_item / a.nsplit, b0 = s_desc[slot].b0;
+      const int first = f.first[fam], nv = min(CB, f.cnt[fam] - b0);
+      const int ch0 = f.child[first + b0], ch1 = nv > 1 ? f.child[first + b0 + 1] : -1;
+      const double *Ga = a.G4prev + (size_t)f.anc[fam] * ld * 4;
+      if (d_item != s_bat.item) {   // KS fragments of the family's ancestor: registers for the whole item
         const double *KSa = a.KS4prev + (size_t)f.anc[fam] * ld * 4;
-        Ga = a.G4prev + (size_t)f.anc[fam] * ld * 4;
 #pragma unroll
         for (int qq = 0; qq < MAXQ; ++qq) {
           const int jj = wid + NW * qq;
           ksA[qq] = jj < nb ? -KSa[(size_t)jj * 32 + lane] : 0.0;   // -KS(8jj + g, tg)
         }
       }
-      named_barrier_sync(1, NW * 32);   // every consumer is done with the previous batch's operands
+      named_barrier_sync(1, NW * 32);   // every consumer is done with the previous batch (operands, s_bat)
+      if (tid == 0) {
+        PtBatch nbt;
+        nbt.item = d_item; nbt.b0 = b0; nbt.sp = d_item % a.nsplit; nbt.ch0 = ch0; nbt.ch1 = ch1;
+        nbt.Pd0 = a.P + (size_t)a.dst_slot[ch0] * a.slab;
+        nbt.Pd1 = ch1 >= 0 ? a.P + (size_t)a.dst_slot[ch1] * a.slab : nullptr;
+        nbt.Ga = Ga;
+        s_bat = nbt;
+      }
       {   // siblings' H in fragment order: s_bC[j][lane] = H_s(b, 8j + 2tg + {0, 1}), n = g = 4s + b
-        const double *H0 = a.H4 + (size_t)child[0] * ld * 4;
-        const double *H1 = nv > 1 ? a.H4 + (size_t)child[1] * ld * 4 : nullptr;
+        const double *H0 = a.H4 + (size_t)ch0 * ld * 4;
+        const double *H1 = ch1 >= 0 ? a.H4 + (size_t)ch1 * ld * 4 : nullptr;
         for (int idx = tid; idx < nb * 32; idx += NW * 32) {
           const int l2 = idx & 31, jb = idx >> 5, g2 = l2 >> 2, t2 = l2 & 3;
           const double *Hs = (g2 >> 2) == 0 ? H0 : H1;
@@ -333,23 +344,25 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
           s_bC[idx] = v;
         }
       }
-      cur_item = d.item; cur_b0 = d.b0; cur_p = -1;
-      gB_next = Ga[(size_t)d.p * 32 + lane];
+      cur_p = -1;
+      gB_next = Ga[(size_t)s_desc[slot].p * 32 + lane];
       named_barrier_sync(1, NW * 32);
     }
     const double *st = ring + (size_t)slot * TS * 64;
-    int t = 0, p = d.p, j = d.j;
-    while (t < d.nt) {
-      const int seg = min(d.nt - t, nb - j), jend = j + seg;
+    const int d_nt = s_desc[slot].nt;
+    int t = 0, p = s_desc[slot].p, j = s_desc[slot].j;
+    while (t < d_nt) {
+      const int seg = min(d_nt - t, nb - j), jend = j + seg;
       if (p != cur_p) {   // operands of the panel: G(8p + g, tg) (prefetched one panel ahead) and the siblings' H at columns 8p..
         gB = gB_next;
-        if (p + 1 < nb) gB_next = Ga[(size_t)(p + 1) * 32 + lane];
+        if (p + 1 < nb) gB_next = s_bat.Ga[(size_t)(p + 1) * 32 + lane];
         const double2 hv = s_bC[(size_t)p * 32 + lane];
         hB0 = hv.x; hB1 = hv.y;
         cur_p = p;
       }
-      const double *tb = st + (long long)(t - j) * 64;       // tile (jj, p) of this stage at tb + jj * 64
-      const size_t gt = (size_t)(d.t0 + t - j) * 64 + offC;  // same, in the slab
+      const double *tb = st + (long long)(t - j) * 64 + offC;                    // fragment of tile (jj, p) at tb + jj * 64
+      const size_t gt = (size_t)(s_desc[slot].t0 + t - j) * 64 + offC;           // same, in the slab
+      double *const P0 = s_bat.Pd0 + gt, *const P1 = s_bat.Pd1 ? s_bat.Pd1 + gt : nullptr;
       // this warp's row blocks in [j, jend): jj = wid + NW qq, qq in [qlo, qhi)
       const int qlo = j > wid ? (j - wid + NW - 1) / NW : 0;
       const int qhi = jend > wid ? (jend - wid + NW - 1) / NW : 0;
@@ -358,19 +371,18 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
         if (qq >= qlo && qq < qhi) {
           const int jj = wid + NW * qq;
           const double *tp = tb + (size_t)jj * 64;
-          double2 tv = *reinterpret_cast<const double2 *>(tp + offC);
+          double2 tv = *reinterpret_cast<const double2 *>(tp);
           dmma_m8n8k4(acc[qq][0], acc[qq][1], tv.x, hB0);      // row side, tile before its downdate
           dmma_m8n8k4(acc[qq][0], acc[qq][1], tv.y, hB1);
           if (jj != p) {                                       // column side: strictly lower tiles
-            const double a0 = tp[offT0], a1 = tp[offT1];
+            const double a0 = tp[offT0 - offC], a1 = tp[offT1 - offC];
             const double2 xv = s_bC[(size_t)jj * 32 + lane];
             dmma_m8n8k4(col0, col1, a0, xv.x);
             dmma_m8n8k4(col0, col1, a1, xv.y);
           }
           dmma_m8n8k4(tv.x, tv.y, ksA[qq], gB);                // the ancestor's pending downdate
-#pragma unroll
-          for (int s = 0; s < CB; ++s)
-            if (s < nv) *reinterpret_cast<double2 *>(Pd[s] + gt + (size_t)jj * 64) = tv;
+          *reinterpret_cast<double2 *>(P0 + (size_t)jj * 64) = tv;
+          if (P1 != nullptr) *reinterpret_cast<double2 *>(P1 + (size_t)jj * 64) = tv;
         }
       }
       t += seg;
@@ -385,7 +397,7 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
     if (lane == 0) mbar_arrive(&empty[slot]);   // this warp has read everything it needs from the slot
     if (++slot == NS) { slot = 0; ++round; }
   }
-  if (cur_item >= 0) flush_rows();
+  if (s_bat.item >= 0) flush_rows();
   post_col(-1);   // terminal marker for the reducer
 }
 

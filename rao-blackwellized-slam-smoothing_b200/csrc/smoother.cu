@@ -819,7 +819,9 @@ extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int
       if ((rc = rb_d2h(ctx, out->PK + (size_t)k * M * M, tmp, sizeof(double) * M * M))) return rc;
     }
     ctx->running = false;
-    // src/particleSmoother.m:365 prints "Particle smoother iteration k/N_K done."; hosts print it
+    // sweep k is complete and its outputs are written: t == T tells the host's callback so
+    // (src/particleSmoother.m:359-365: makePlots(xnk,xlk,k,XNK,XLK,PK), then the progress line)
+    if (ctx->step_fn) ctx->step_fn(ctx->step_user, k, T);
   }
   if (out->ak) for (int k = 0; k < N_K; ++k) out->ak[k] = h_ak[k];
   if (out->AI && (rc = rb_d2h(ctx, out->AI, w->AI, sizeof(double) * (size_t)N_K * T * N))) return rc;

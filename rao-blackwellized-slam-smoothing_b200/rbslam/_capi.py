@@ -79,6 +79,7 @@ SYMBOLS = {
     "rbslam_sync": (C.c_int, [_ctx]),
     "rbslam_read_particles": (C.c_int, [_ctx, c_double_p, c_double_p, c_double_p, c_double_p,
                                         c_double_p, c_int32_p]),
+    "rbslam_read_trajectories": (C.c_int, [_ctx, c_double_p, c_double_p, c_double_p, c_double_p]),
     "rbslam_read_information": (C.c_int, [_ctx, c_double_p, c_double_p, c_double_p]),
     "rbslam_counters": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),

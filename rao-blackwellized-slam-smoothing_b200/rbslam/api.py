@@ -194,6 +194,7 @@ class Context:
         inp, keep, T = self._inputs(odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams,
                                     forced_ancestors=forced_ancestors)
         out, o = self._filter_outputs(T, want_xn_traj, taps)
+        self._run_T = T
         self._ck(self._lib.rbslam_filter_run(self._h, C.byref(inp), C.byref(out)))
         return o
 
@@ -229,6 +230,17 @@ class Context:
                                                  _capi.iptr(ai)))
         return dict(xn=xn, xl=xl, P=Pm, logw=logw, w=w, ai=ai)
 
+    def read_trajectories(self, xn_traj=True):
+        """traj_max, traj_mean, yhattraj, xn_traj as the reference holds them at the current step
+        (NaN / zero beyond it): the trajectory arguments of the filter's makePlots hook."""
+        n, N, d, T = self.n, self.N, self.d, self._run_T
+        tm, tmean = np.zeros((n, T), order="F"), np.zeros((n, T), order="F")
+        yh = np.zeros((d, T), order="F")
+        xt = np.zeros((n, N, T), order="F") if xn_traj else None
+        self._ck(self._lib.rbslam_read_trajectories(self._h, _capi.dptr(tm), _capi.dptr(tmean), _capi.dptr(yh),
+                                                    _capi.dptr(xt)))
+        return dict(traj_max=tm, traj_mean=tmean, yhattraj=yh, xn_traj=xt)
+
     def read_information(self):
         N, M = self.N, self.M
         ivec = np.zeros((M, N), order="F")
@@ -260,6 +272,7 @@ class Context:
         out.XNK, out.XLK, out.PK = _capi.dptr(o["XNK"]), _capi.dptr(o["XLK"]), _capi.dptr(o["PK"])
         out.ak = _capi.iptr(o["ak"])
         out.AI = _capi.dptr(o.get("AI"))
+        self._smoother_out = o
         self._ck(self._lib.rbslam_smoother_run(self._h, C.byref(inp), N_K, form, C.byref(out)))
         return o
 
@@ -441,9 +454,14 @@ def particleFilter(dynModel, measModel, odometry, y, x0_nonLin, x0_lin, P0_lin, 
     ctx_kw.setdefault("kalman_variant", -1)   # filter only: packed symmetric slabs where they apply
     with Context(model, N_P, T, device=device, rng_mode=mode, seed=seed, **ctx_kw) as ctx:
         if makePlots is not None:
+            # makePlots(xn,xl(:,iw_max),P(:,:,iw_max),traj_max,yhattraj,xn_traj,traj_mean,xl,P)
+            # (src/particleFilter.m:215-217), every step
             def _cb(k, t, ctx=ctx):
                 st = ctx.read_particles()
-                makePlots(t, st)
+                tr = ctx.read_trajectories()
+                im = int(np.argmax(st["w"]))
+                makePlots(st["xn"], st["xl"][:, im], st["P"][:, :, im], tr["traj_max"], tr["yhattraj"],
+                          tr["xn_traj"], tr["traj_mean"], st["xl"], st["P"])
             ctx.set_step_callback(_cb)
         o = ctx.filter_run(odometry, yy, x0_nonLin, x0_lin, P0_lin, Q, R, dt, streams)
     return (o["traj_max"], o["traj_mean"], o["xl_max"], o["xl_mean"], o["P_max"], o["P_mean"],
@@ -466,10 +484,15 @@ def _smoother(form, dynModel, measModel, dynResNorm, odometry, y, x0_nonLin, x0_
     T = yy.shape[0]
     with Context(model, N_P, T, device=device, rng_mode=mode, seed=seed,
                  information_form=(form == 1), **ctx_kw) as ctx:
+        def _cb(k, t, ctx=ctx):
+            if t != T:
+                return
+            o = ctx._smoother_out       # filled sweep by sweep by the library
+            if makePlots is not None:   # makePlots(xnk,xlk,k,XNK,XLK,PK), src/particleSmoother.m:359-361
+                makePlots(o["XNK"][:, :, k], o["XLK"][:, k], k, o["XNK"], o["XLK"], o["PK"])   # k 0-based here, 1-based in MATLAB
+            print("Particle smoother iteration %i/%i done." % (k + 1, N_K))   # :365
+        ctx.set_step_callback(_cb)
         o = ctx.smoother_run(odometry, yy, x0_nonLin, x0_lin, P0_lin, Q, R, dt, N_K, form, streams)
-    if makePlots is not None:
-        for k in range(N_K):
-            makePlots(o["XNK"][:, :, k], o["XLK"][:, k], k, o["XNK"], o["XLK"], o["PK"])
     return o["XNK"], o["XLK"], o["PK"]
 
 

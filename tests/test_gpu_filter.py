@@ -197,3 +197,34 @@ def test_filter_long_horizon_deferred_downdate(rbslam_lib, variant):
     with rb.Context(gm, N, T, rng_mode=0, kalman_variant=variant) as ctx:
         o = ctx.filter_run(*_args(pr), pr["dt"], streams=st, forced_ancestors=forced, taps=True)
     _compare(o, ref, taps, T)
+
+
+@pytest.mark.parametrize("fam,N,kw", [("radio", 20, {"m": 40}), ("mag", 12, {"m": 253, "T": 6}),
+                                      ("sparse", 16, {"T": 12})])
+def test_particlefilter_makeplots_hook(rbslam_lib, fam, N, kw):
+    """The drop-in forwards makePlots every step with the reference's nine arguments
+    (src/particleFilter.m:215-217): xn, xl(:,iw_max), P(:,:,iw_max), traj_max, yhattraj, xn_traj,
+    traj_mean, xl, P -- NaN / zero in the columns of steps not yet run, as in the reference."""
+    rb = rbslam_lib
+    pr, om, gm = _setup(rb, fam, N, **kw)
+    T = min(pr["y"].shape[0], 8)
+    pr = dict(pr, y=pr["y"][:T], odometry=pr["odometry"][:T])
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(2), 1, T, N, om.nz)
+    want, got = [], []
+
+    def keep(dst):
+        def f(xn, xl_max, P_max, traj_max, yhattraj, xn_traj, traj_mean, xl, P):
+            dst.append([np.array(v, dtype=np.float64).copy() for v in
+                        (xn, xl_max, P_max, traj_max, yhattraj, xn_traj, traj_mean, xl, P)])
+        return f
+    oracle.particleFilter(om, *_args(pr), N, pr["dt"], st, makePlots=keep(want))
+    rb.particleFilter(gm.dynModel, gm.measModel, pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"],
+                      pr["P0_lin"], pr["Q"], pr["R"], N, pr["dt"], bool(gm.sparse), keep(got), rng=st)
+    assert len(got) == len(want) == T
+    names = ["xn", "xl_max", "P_max", "traj_max", "yhattraj", "xn_traj", "traj_mean", "xl", "P"]
+    for t in range(T):
+        for k, a, b in zip(names, got[t], want[t]):
+            if k == "P":
+                b = b.transpose(1, 2, 0)            # the oracle keeps P as [N, M, M]
+            assert np.array_equal(np.isnan(a), np.isnan(b)), (t, k)
+            assert_close_norm(np.nan_to_num(a), np.nan_to_num(b), 1e-7 if k == "traj_mean" else TOL, "%s@%d" % (k, t))

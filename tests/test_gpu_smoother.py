@@ -222,3 +222,28 @@ def test_ancestor_weights_info_c5_size(rbslam_lib):
         got = ctx.op_ancestor_weights(1, Imat.transpose(1, 2, 0), ivec, ImatAddt, ivecAddt, q2=q2, hld=hld,
                                       jitter=-1.0)
     assert np.all(np.abs(got - ref) <= 1e-8 * np.maximum(1.0, np.abs(ref))), (got, ref)
+
+
+def test_particlesmoother_makeplots_and_progress(rbslam_lib, capsys):
+    """The smoother drop-in calls makePlots(xnk,xlk,k,XNK,XLK,PK) and prints the progress line once
+    per sweep, when that sweep's outputs exist (src/particleSmoother.m:359-365)."""
+    rb = rbslam_lib
+    N, K = 10, 3
+    pr, om, gm = _setup(rb, "radio", N, m=40)
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(4), K, T, N, om.nz)
+    want, got = [], []
+    oracle.particleSmoother(om, *_args(pr), N, K, pr["dt"], st,
+                            makePlots=lambda xnk, xlk, k, XNK, XLK, PK: want.append((xnk.copy(), xlk.copy(), k, XNK.copy())))
+    XNK, XLK, PK = rb.particleSmoother(gm.dynModel, gm.measModel, gm.dynResNorm, pr["odometry"], pr["y"],
+                                       pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"], N, K,
+                                       pr["dt"], False,
+                                       lambda xnk, xlk, k, XNK, XLK, PK: got.append((xnk.copy(), xlk.copy(), k, XNK.copy())),
+                                       rng=st)
+    assert [g[2] for g in got] == [w[2] for w in want] == list(range(K))
+    for g, w in zip(got, want):
+        assert_close_norm(g[0], w[0], 1e-8, "xnk")
+        assert_close_norm(g[1], w[1], 1e-8, "xlk")
+        assert_close_norm(g[3][:, :, :g[2] + 1], w[3][:, :, :w[2] + 1], 1e-8, "XNK so far")
+    out = capsys.readouterr().out
+    assert out.count("Particle smoother iteration") == K and "iteration %d/%d done." % (K, K) in out
