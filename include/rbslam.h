@@ -158,6 +158,17 @@ typedef void (*rbslam_step_fn)(void *user, int32_t sweep, int32_t t);
 RBSLAM_API int rbslam_version(void);
 RBSLAM_API int rbslam_device_count(void);
 RBSLAM_API int rbslam_create(rbslam_ctx **out, const rbslam_config *cfg);
+/* ONE filter whose particles are sharded over several GPUs of the box, driven from ONE host process --
+   what a MATLAB caller (a single process, src/particleFilter.m:1-3 called from one interpreter thread)
+   needs to use the whole machine.  devices[n_devices]: CUDA ordinals (they may repeat: shards then
+   share a GPU); cfg->N is the global particle count (divisible by n_devices); cfg->device/rank/world
+   are ignored; rng_mode PHILOX, keep_history = 1, dense model on the streaming path.  The returned
+   leader context drives every shard through rbslam_filter_begin/step/end/run, rbslam_sync,
+   rbslam_counters; rbslam_destroy(leader) destroys the group.  The shards are the contexts of the
+   one-process-per-GPU mode below with their peer tables wired by plain device pointers
+   (cudaDeviceEnablePeerAccess); the step never synchronises with the host. */
+RBSLAM_API int rbslam_create_group(rbslam_ctx **out, const rbslam_config *cfg, const int32_t *devices,
+                        int32_t n_devices);
 RBSLAM_API void rbslam_destroy(rbslam_ctx *ctx);
 RBSLAM_API const char *rbslam_last_error(const rbslam_ctx *ctx); /* ctx may be NULL: last create error */
 /* derived sizes: n, d, M, nz, nw, n_odo, ld (in that order) */
@@ -258,6 +269,19 @@ RBSLAM_API int rbslam_op_dyn_logweight(rbslam_ctx *ctx, int32_t N, const double 
 RBSLAM_API int rbslam_op_ancestor_weights(rbslam_ctx *ctx, int32_t form, int32_t N, int32_t ne, const double *A,
                                const double *v, const double *S, const double *r, const double *R,
                                const double *q2, const double *hld, double jitter, double *logwMeas);
+
+/* ---- EKF baseline of the dense magnetic-field example ---------------------- */
+/* examples/slam-dense-mag/ekf_dense.m:37-102 with the closures dynModel_ekf / measModel_ekf of
+   run_dense3D_magfield.m:281-316, run on the device for a dense-mag context (its basis NN, L is used;
+   N and T of the context are irrelevant).  State x = [pos(3); orientation deviation(3); map(M)],
+   ns = M + 6; x0 [ns], q0 [4] (linearisation point), P0 [ns x ns]; odometry [odo_rows x 7]; y [T x 3];
+   Q [6 x 6 x Q_pages]; R [3 x 3]; dt [dt_len]; LL [2 x 3] = the domain bounds measModel_ekf hands to
+   JacobianPhi3D.  Outputs (any may be NULL): xf_traj [ns x T], qnb_traj [4 x T], Pf_last [ns x ns]
+   (= Pf_traj(:,:,T)), Pf_traj [ns x ns x T] (the reference keeps all of them: 8.5 MB each at M = 1027). */
+RBSLAM_API int rbslam_ekf_run(rbslam_ctx *ctx, int32_t T, const double *odometry, int32_t odo_rows, const double *y,
+                   const double *x0, const double *q0, const double *P0, const double *Q, int32_t Q_pages,
+                   const double *R, const double *dt, int32_t dt_len, const double *LL, double *xf_traj,
+                   double *qnb_traj, double *Pf_last, double *Pf_traj);
 
 /* ---- multi-GPU sharding (one process per GPU) --------------------------- */
 /* Host-only planner: given the ancestors of all N new particles and the owner

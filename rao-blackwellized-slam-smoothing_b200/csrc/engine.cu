@@ -310,6 +310,7 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
   if (ctx->kpath == 1) {
     ctx->hs_p = (size_t)ctx->ld * 4; ctx->hs_a = 1; ctx->hs_c = 4;
     int ns = N >= 4096 ? 2 : std::max(1, std::min(8, (4 * 148 + N - 1) / N));
+    if (ctx->pt && N >= 5000) ns = 1;   // > 20 waves of families per launch: whole-slab items balance well enough
     if (const char *e = getenv("RBSLAM_NSPLIT")) ns = std::max(1, atoi(e));
     if (const char *e = getenv("RBSLAM_CTAS_PER_SM")) ctx->stream_ctas_per_sm = atoi(e);
     if (const char *e = getenv("RBSLAM_STREAM_HINTS")) ctx->stream_hints = atoi(e);
@@ -419,6 +420,58 @@ extern "C" int rbslam_create(rbslam_ctx **out, const rbslam_config *cfg) {
   return RBSLAM_OK;
 }
 
+// ---------------------------------------------------------------------------
+// ONE filter sharded over several GPUs, driven from ONE host process (SURVEY 8(b) "Threading": a
+// MATLAB caller has a single process).  The shards are ordinary sharded contexts (sharded.cu);
+// their peer tables hold plain device pointers instead of CUDA-IPC mappings, and the host thread
+// enqueues every shard's step in turn -- the step itself never synchronises with the host, the
+// shards meet in the peer-memory barriers on the devices.
+// ---------------------------------------------------------------------------
+extern "C" int rbslam_create_group(rbslam_ctx **out, const rbslam_config *cfg, const int32_t *devices, int32_t n_devices) {
+  if (!out || !cfg || !devices) { g_create_error = "null argument"; return RBSLAM_EARG; }
+  *out = nullptr;
+  if (n_devices < 1 || n_devices > 8) { g_create_error = "1..8 devices"; return RBSLAM_EARG; }
+  if (n_devices == 1) {
+    rbslam_config c1 = *cfg;
+    c1.device = devices[0]; c1.rank = 0; c1.world = 1;
+    return rbslam_create(out, &c1);
+  }
+  if (cfg->rng_mode != RBSLAM_RNG_PHILOX || !cfg->keep_history) {
+    g_create_error = "a device group runs the sharded filter: rng_mode PHILOX and keep_history=1";
+    return RBSLAM_EARG;
+  }
+  std::vector<rbslam_ctx *> sh;
+  int rc = RBSLAM_OK;
+  for (int r = 0; r < n_devices && rc == RBSLAM_OK; ++r) {
+    rbslam_config c = *cfg;
+    c.device = devices[r]; c.rank = r; c.world = n_devices;
+    rbslam_ctx *ctx = nullptr;
+    rc = rbslam_create(&ctx, &c);
+    if (rc == RBSLAM_OK) sh.push_back(ctx);
+  }
+  for (int r = 0; r < (int)sh.size() && rc == RBSLAM_OK; ++r)
+    for (int p = 0; p < (int)sh.size() && rc == RBSLAM_OK; ++p) {
+      if (p == r) continue;
+      if (devices[p] != devices[r]) {
+        cudaSetDevice(devices[r]);
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, devices[r], devices[p]);
+        cudaError_t e = can ? cudaDeviceEnablePeerAccess(devices[p], 0) : cudaErrorPeerAccessUnsupported;
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        if (e != cudaSuccess) { g_create_error = "devices of the group cannot access each other's memory"; rc = RBSLAM_ECUDA; break; }
+      }
+      rc = rb_shard_wire(sh[r], sh[p]);
+    }
+  if (rc != RBSLAM_OK) {
+    for (rbslam_ctx *c : sh) rbslam_destroy(c);
+    return rc;
+  }
+  for (size_t r = 1; r < sh.size(); ++r) sh[r]->group_member = true;
+  sh[0]->group = sh;
+  *out = sh[0];
+  return RBSLAM_OK;
+}
+
 static void free_run_inputs(rbslam_ctx *ctx) {
   void **ptrs[] = {(void **)&ctx->d_odo, (void **)&ctx->d_y, (void **)&ctx->d_Q, (void **)&ctx->d_R,
                    (void **)&ctx->d_P0, (void **)&ctx->d_x0lin, (void **)&ctx->d_U, (void **)&ctx->d_Z,
@@ -428,6 +481,12 @@ static void free_run_inputs(rbslam_ctx *ctx) {
 
 extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
   if (!ctx) return;
+  if (!ctx->group.empty()) {   // group leader: the other shards go first
+    std::vector<rbslam_ctx *> members(ctx->group.begin() + 1, ctx->group.end());
+    ctx->group.clear();
+    for (rbslam_ctx *m : members) { m->group_member = false; rbslam_destroy(m); }
+  }
+  if (ctx->cfg.device >= 0) cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_run_inputs(ctx);
   rb_smoother_free(ctx);
@@ -466,6 +525,14 @@ extern "C" void *rbslam_stream(rbslam_ctx *ctx) { return ctx ? (void *)ctx->stre
 
 extern "C" int rbslam_sync(rbslam_ctx *ctx) {
   if (!ctx) return RBSLAM_EARG;
+  for (size_t r = 1; r < ctx->group.size(); ++r) {
+    rbslam_ctx *m = ctx->group[r];
+    cudaSetDevice(m->cfg.device);
+    if (cudaStreamSynchronize(m->stream) != cudaSuccess) return ctx->fail(RBSLAM_ECUDA, "group shard failed");
+    int rcm = rb_check_status(m);
+    if (rcm) return ctx->fail(rcm, m->err);
+  }
+  CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));
   return rb_check_status(ctx);
 }
@@ -475,6 +542,11 @@ extern "C" int rbslam_counters(rbslam_ctx *ctx, int64_t *kl, int64_t *h2d, int64
   if (kl) *kl = ctx->launches;
   if (h2d) *h2d = ctx->h2d;
   if (d2h) *d2h = ctx->d2h;
+  for (size_t r = 1; r < ctx->group.size(); ++r) {   // group leader: the whole group's work
+    if (kl) *kl += ctx->group[r]->launches;
+    if (h2d) *h2d += ctx->group[r]->h2d;
+    if (d2h) *d2h += ctx->group[r]->d2h;
+  }
   return RBSLAM_OK;
 }
 
@@ -1045,8 +1117,24 @@ static int filter_step_impl(rbslam_ctx *ctx) {
   return RBSLAM_OK;
 }
 
+// group leader: run `fn` on every shard (its own device current), first error wins
+template <typename F>
+static int group_each(rbslam_ctx *ctx, F fn) {
+  for (rbslam_ctx *m : ctx->group) {
+    if (cudaSetDevice(m->cfg.device) != cudaSuccess) return ctx->fail(RBSLAM_ECUDA, "cudaSetDevice failed");
+    int rc = fn(m);
+    if (rc) { if (m != ctx) ctx->err = m->err; return rc; }
+  }
+  return RBSLAM_OK;
+}
+
 extern "C" int rbslam_filter_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
   if (!ctx) return RBSLAM_EARG;
+  if (!ctx->group.empty()) {
+    int rc = group_each(ctx, [&](rbslam_ctx *m) { return rb_shard_begin(m, in, 1); });
+    if (rc) return rc;
+    return group_each(ctx, [&](rbslam_ctx *m) { return rb_shard_begin(m, in, 2); });
+  }
   if (ctx->shard_ws) return rb_shard_begin(ctx, in);
   int rc = rb_upload_inputs(ctx, in, 1);
   if (rc) return rc;
@@ -1060,6 +1148,7 @@ extern "C" int rbslam_filter_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
 
 extern "C" int rbslam_filter_step(rbslam_ctx *ctx) {
   if (!ctx) return RBSLAM_EARG;
+  if (!ctx->group.empty()) return group_each(ctx, [&](rbslam_ctx *m) { return rb_shard_step(m); });
   if (ctx->shard_ws) return rb_shard_step(ctx);
   return filter_step_impl(ctx);
 }
@@ -1073,6 +1162,12 @@ int rb_enable_taps(rbslam_ctx *ctx, bool logw, bool w) {
 
 extern "C" int rbslam_filter_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
   if (!ctx || !out) return RBSLAM_EARG;
+  if (!ctx->group.empty()) {
+    int rc;
+    for (int phase = 1; phase <= 3; ++phase)
+      if ((rc = group_each(ctx, [&](rbslam_ctx *m) { return rb_shard_end(m, out, phase); }))) return rc;
+    return RBSLAM_OK;
+  }
   if (ctx->shard_ws) return rb_shard_end(ctx, out);
   if (!ctx->running) return ctx->fail(RBSLAM_EARG, "filter_end without filter_begin");
   CK(cudaSetDevice(ctx->cfg.device));

@@ -45,7 +45,7 @@ struct rbslam_ctx {
   // kalman_variant 7: packed symmetric tile slabs (packed_kernels.cuh)
   bool pt = false;
   int layout = 0;            // RB_LAYOUT_FULL / _SYM / _PT: how element (r,c) of a slab is stored
-  int pt_ts = 84, pt_ns = 3; // tiles per stage, ring slots (RBSLAM_PT_CFG="TS,NS")
+  int pt_ts = 120, pt_ns = 2; // tiles per stage, ring slots (RBSLAM_PT_CFG="TS,NS")
   int pt_nw = 15;            // consumer warps per CTA (+ the service warp = 16 warps x 128 registers)
   int pt_psplit[9] = {0};    // panel ranges of the nsplit items per family
   const int *item_group = nullptr;   // sharded engine: work group of each local item (see stream_groups)
@@ -97,6 +97,8 @@ struct rbslam_ctx {
 
   void *smoother_ws = nullptr;   // SmootherWs (smoother.cu)
   void *shard_ws = nullptr;      // ShardWs (sharded.cu); N is the LOCAL particle count when set
+  std::vector<rbslam_ctx *> group;   // leader of a single-process group (rbslam_create_group): every shard, itself first
+  bool group_member = false;         // a non-leader shard of such a group (destroyed with its leader)
   const int *anc_override = nullptr;   // sharded engine: thin arrays are slot-indexed
   // streaming pass in groups: group g uses listA/listB + group_off[g][phase], counts d_counts[2g+phase];
   // group_hook(ctx, g) runs before group g>0 (sharded engine: wait for migrants + peer barrier)

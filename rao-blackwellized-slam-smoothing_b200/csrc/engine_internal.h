@@ -60,9 +60,10 @@ int rb_flush_pending(rbslam_ctx *ctx);
 // sharded.cu
 int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN);
 void rb_shard_free(rbslam_ctx *ctx);
-int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in);
+int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in, int phase = 0);
 int rb_shard_step(rbslam_ctx *ctx);
-int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out);
+int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out, int phase = 0);
+int rb_shard_wire(rbslam_ctx *a, rbslam_ctx *b);
 int64_t rb_shard_migrated(rbslam_ctx *ctx);
 // smoother.cu
 int rb_info_init(rbslam_ctx *ctx);

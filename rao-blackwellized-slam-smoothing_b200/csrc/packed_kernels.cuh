@@ -157,7 +157,7 @@ struct PtColDesc {   // what a column-side buffer holds: panel p of the batch (c
 
 static inline size_t pt_smem_bytes(int ld, int ts, int ns, int nw) {
   const int nb = ld >> 3;
-  return (size_t)ns * ts * 512 + (size_t)nb * 32 * 16 + (size_t)RB_PT_NBUF * nw * 64 * 8;
+  return (size_t)ns * ts * 512 + (size_t)nb * 32 * 16 + (size_t)RB_PT_NBUF * nw * 64 * 8 + (size_t)nw * 2 * 32 * 8;
 }
 
 // Warp roles: NW consumer warps and one service warp (lane 0 = producer, lanes 1..31 = reducer).
@@ -176,6 +176,7 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
   double *ring = reinterpret_cast<double *>(smraw);                             // [NS][TS][64]
   double2 *s_bC = reinterpret_cast<double2 *>(ring + (size_t)NS * TS * 64);     // [nb][32] fragment order
   double *s_colp = reinterpret_cast<double *>(s_bC + (size_t)nb * 32);          // [NBUF][NW][64]
+  double *s_gpre = s_colp + (size_t)NBUF * NW * 64;                             // [NW][2][32] G fragments, prefetched
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int n_items = (*f.n_fam) * a.nsplit;
@@ -272,7 +273,15 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
   double acc[MAXQ][2], ksA[MAXQ];
 #pragma unroll
   for (int qq = 0; qq < MAXQ; ++qq) { acc[qq][0] = acc[qq][1] = 0.0; ksA[qq] = 0.0; }
-  double col0 = 0.0, col1 = 0.0, gB = 0.0, gB_next = 0.0, hB0 = 0.0, hB1 = 0.0;
+  double col0 = 0.0, col1 = 0.0, gB = 0.0, hB0 = 0.0, hB1 = 0.0;
+  // G(8p + g, tg) of the next panel travels global -> shared memory with cp.async while the current
+  // panel is processed (a register prefetch would be waited for at the loop's back edge)
+  double *const gpre = s_gpre + (size_t)wid * 64 + lane;   // two slots of 32 doubles per warp
+  auto prefetch_g = [&](const double *Ga, int p) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\ncp.async.commit_group;" ::"r"(smem_u32(gpre + (p & 1) * 32)),
+                 "l"(Ga + (size_t)p * 32 + lane)
+                 : "memory");
+  };
   int n_panel = 0;   // panels finished so far by this warp (selects the column-side buffer)
   int cur_p = -1;    // panel whose gB / hB are loaded
 
@@ -345,7 +354,8 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
         }
       }
       cur_p = -1;
-      gB_next = Ga[(size_t)s_desc[slot].p * 32 + lane];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");   // a prefetch of the previous batch may still be landing
+      prefetch_g(Ga, s_desc[slot].p);
       named_barrier_sync(1, NW * 32);
     }
     const double *st = ring + (size_t)slot * TS * 64;
@@ -354,8 +364,9 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
     while (t < d_nt) {
       const int seg = min(d_nt - t, nb - j), jend = j + seg;
       if (p != cur_p) {   // operands of the panel: G(8p + g, tg) (prefetched one panel ahead) and the siblings' H at columns 8p..
-        gB = gB_next;
-        if (p + 1 < nb) gB_next = s_bat.Ga[(size_t)(p + 1) * 32 + lane];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        gB = gpre[(p & 1) * 32];
+        if (p + 1 < nb) prefetch_g(s_bat.Ga, p + 1);
         const double2 hv = s_bC[(size_t)p * 32 + lane];
         hB0 = hv.x; hB1 = hv.y;
         cur_p = p;

@@ -4,3 +4,4 @@
 #include "smoother.cu"
 #include "ops.cu"
 #include "sharded.cu"
+#include "ekf.cu"

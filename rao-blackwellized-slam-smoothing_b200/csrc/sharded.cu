@@ -309,6 +309,15 @@ extern "C" int rbslam_ipc_import(rbslam_ctx *ctx, int32_t peer, int32_t which, c
 
 extern "C" int rbslam_ipc_count(void) { return SH_COUNT; }
 
+// single-process group (rbslam_create_group): peers are wired with plain device pointers
+// (cudaDeviceEnablePeerAccess between different devices; nothing to do on one device)
+int rb_shard_wire(rbslam_ctx *a, rbslam_ctx *b) {
+  ShardWs *sa = sh_of(a), *sb = sh_of(b);
+  if (!sa || !sb) return RBSLAM_EARG;
+  for (int w = 0; w < SH_COUNT; ++w) sa->peers.p[w][sb->rank] = sb->peers.p[w][sb->rank];
+  return RBSLAM_OK;
+}
+
 // ---------------------------------------------------------------------------
 // sharded filter
 // ---------------------------------------------------------------------------
@@ -327,8 +336,12 @@ static int shard_group_hook(rbslam_ctx *ctx, int) {
   return peer_barrier(ctx);
 }
 
-int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
+// phase 0: everything (one process per GPU); 1: all but the closing barrier; 2: the barrier only.
+// A single process that drives several shards (rbslam_create_group) must finish phase 1 on every
+// shard -- it allocates, frees and synchronises -- before any shard's barrier kernel starts to spin.
+int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in, int phase) {
   ShardWs *s = sh_of(ctx);
+  if (phase == 2) return peer_barrier(ctx);
   for (int w = 0; w < SH_COUNT; ++w)
     for (int r = 0; r < s->world; ++r)
       if (!s->peers.p[w][r]) return ctx->fail(RBSLAM_EARG, "peer buffers not imported (rbslam_ipc_import)");
@@ -360,6 +373,7 @@ int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in) {
   ctx->running = true;
   ctx->t = 0;
   CK(cudaMemsetAsync(s->flags + 16, 0, 16 * sizeof(unsigned long long), ctx->stream));   // peers' failure flags of an earlier run
+  if (phase == 1) { CK(cudaStreamSynchronize(ctx->stream)); return RBSLAM_OK; }
   if ((rc = peer_barrier(ctx))) return rc;   // nobody starts before everybody is initialised
   return RBSLAM_OK;
 }
@@ -535,11 +549,19 @@ int rb_shard_step(rbslam_ctx *ctx) {
   return RBSLAM_OK;
 }
 
-int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
+// phase 0: everything; 1: status + outputs; 2: enqueue the closing barrier; 3: wait for it
+int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out, int phase) {
   ShardWs *s = sh_of(ctx);
   const int gN = s->gN, M = ctx->M, n = ctx->n, T = ctx->t, ld = ctx->ld;
   if (T < 1) return ctx->fail(RBSLAM_EARG, "no step was run");
-  int rc = rb_check_status(ctx);
+  int rc;
+  if (phase == 2) return peer_barrier(ctx);
+  if (phase == 3) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->running = false;
+    return rb_check_status(ctx);
+  }
+  rc = rb_check_status(ctx);
   if (rc) return rc;
   if (s->rank == 0) {
     const int cur = s->cur;
@@ -597,6 +619,7 @@ int rb_shard_end(rbslam_ctx *ctx, rbslam_filter_outputs *out) {
     }
     if (out->ancestors && (rc = rb_d2h(ctx, out->ancestors, s->g_Ahist, sizeof(int) * (size_t)gN * T))) return rc;
   }
+  if (phase == 1) return RBSLAM_OK;
   // peers keep their slabs alive until rank 0 has read what it needs
   if ((rc = peer_barrier(ctx))) return rc;
   CK(cudaStreamSynchronize(ctx->stream));

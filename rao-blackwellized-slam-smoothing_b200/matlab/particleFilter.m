@@ -13,10 +13,10 @@ function [traj_max,traj_mean,xl_max,xl_mean,P_max,P_mean,traj_sample_iwmax,xn_tr
   if logical(sparseFeatures) ~= strcmp(desc.family, 'sparseVisual2D')
     error('rbslam:unsupportedModel', 'sparseFeatures does not match the model family');
   end
-  if ~isempty(makePlots)
-    warning('rbslam:makePlots', 'per-step makePlots callbacks are not forwarded by the MEX gateway');
-  end
   opts = rbslam_opts();
+  % makePlots(xn,xl(:,iw_max),P(:,:,iw_max),traj_max,yhattraj,xn_traj,traj_mean,xl,P) is called by the
+  % gateway after every time step, as src/particleFilter.m:215-217 does
+  opts.makePlots = makePlots;
   if strcmp(opts.rng, 'compat')
     opts = rbslam_streams(opts, desc, N_P, size(y,1), 1, false);
   end

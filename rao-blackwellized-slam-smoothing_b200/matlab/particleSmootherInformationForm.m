@@ -9,12 +9,12 @@ function [XNK,XLK,PK] = particleSmootherInformationForm(dynModel,measModel,dynRe
   end
   desc = rbslam_resolve(dynModel, measModel, dynResNorm);
   opts = rbslam_opts();
+  % per sweep the gateway calls makePlots(xnk,xlk,k,XNK,XLK,PK) and prints the progress line,
+  % as src/particleSmoother.m:359-365 does
+  opts.makePlots = makePlots;
   if strcmp(opts.rng, 'compat')
     opts = rbslam_streams(opts, desc, N_P, size(y,1), N_K, true);
   end
   [XNK,XLK,PK] = rbslam_mex('smoother', desc, 1, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, ...
                             N_P, N_K, dt, opts);
-  if ~isempty(makePlots)
-    for k = 1:N_K, makePlots(XNK(:,:,k), XLK(:,k), k, XNK, XLK, PK); end
-  end
 end

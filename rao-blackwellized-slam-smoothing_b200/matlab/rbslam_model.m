@@ -15,7 +15,10 @@ function m = rbslam_model(family, varargin)
     case {'denseMag3D','denseRadio2D'}
       desc.NN = double(varargin{1});
       L = varargin{2};
-      if size(L,1) > 1, L = (max(L,[],1) - min(L,[],1))/2; end   % domain_cartesian_dx.m:27-29
+      if size(L,1) > 1   % the 2 x d domain bounds LL
+        desc.LL = double(L);                                     % kept for measModel_ekf's JacobianPhi3D call
+        L = (max(L,[],1) - min(L,[],1))/2;                       % domain_cartesian_dx.m:27-29
+      end
       desc.L = double(L(:)');
     case 'sparseVisual2D'
       desc.nLandmarks = varargin{1};
@@ -26,6 +29,10 @@ function m = rbslam_model(family, varargin)
   m = desc;
   m.dynModel   = @(varargin) rbslam_handle_stub(desc, 'dynModel');
   m.measModel  = @(varargin) rbslam_handle_stub(desc, 'measModel');
+  if strcmp(family, 'denseMag3D')   % the EKF baseline's closures (run_dense3D_magfield.m:281-316)
+    m.dynModel_ekf  = @(varargin) rbslam_handle_stub(desc, 'dynModel_ekf');
+    m.measModel_ekf = @(varargin) rbslam_handle_stub(desc, 'measModel_ekf');
+  end
   if strcmp(family, 'sparseVisual2D')
     m.dynResNorm = [];                                   % psslam.m:118 passes []
   else

@@ -32,6 +32,10 @@ mxArray *mxCreateNumericArray(mwSize ndim, const mwSize *dims, mxClassID cls, mx
 void mexErrMsgIdAndTxt(const char *id, const char *fmt, ...);
 int mexPrintf(const char *fmt, ...);
 void mexLock(void);
+void mexUnlock(void);
+int mexCallMATLAB(int nlhs, mxArray *plhs[], int nrhs, mxArray *prhs[], const char *name);
+void mxDestroyArray(mxArray *a);
+int mxIsClass(const mxArray *a, const char *classname);
 int mexAtExit(void (*fn)(void));
 #ifdef __cplusplus
 }

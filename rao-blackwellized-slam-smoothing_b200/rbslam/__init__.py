@@ -7,8 +7,8 @@ mirror the reference's MATLAB entry points; all compute runs in librbslam.so
 from . import basis, synth, models
 from ._capi import RbslamError, UnsupportedModelError, LIB_PATH
 from .api import (Context, particleFilter, particleSmoother, particleSmootherInformationForm,
-                  plan_migration)
+                  plan_migration, ekf_dense)
 
 __all__ = ["basis", "synth", "models", "Context", "particleFilter", "particleSmoother",
-           "particleSmootherInformationForm", "plan_migration", "RbslamError",
+           "particleSmootherInformationForm", "plan_migration", "ekf_dense", "RbslamError",
            "UnsupportedModelError", "LIB_PATH"]

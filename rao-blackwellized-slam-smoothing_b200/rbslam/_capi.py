@@ -66,6 +66,7 @@ SYMBOLS = {
     "rbslam_version": (C.c_int, []),
     "rbslam_device_count": (C.c_int, []),
     "rbslam_create": (C.c_int, [C.POINTER(_ctx), C.POINTER(Config)]),
+    "rbslam_create_group": (C.c_int, [C.POINTER(_ctx), C.POINTER(Config), c_int32_p, C.c_int32]),
     "rbslam_destroy": (None, [_ctx]),
     "rbslam_last_error": (C.c_char_p, [_ctx]),
     "rbslam_dims": (C.c_int, [_ctx, c_int32_p]),
@@ -102,6 +103,9 @@ SYMBOLS = {
     "rbslam_op_ancestor_weights": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p,
                                              c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                              C.c_double, c_double_p]),
+    "rbslam_ekf_run": (C.c_int, [_ctx, C.c_int32, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                 c_double_p, c_double_p, C.c_int32, c_double_p, c_double_p, C.c_int32, c_double_p,
+                                 c_double_p, c_double_p, c_double_p, c_double_p]),
     "rbslam_plan_migration": (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p,
                                         c_int32_p]),
     "rbslam_plan_shard": (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p,

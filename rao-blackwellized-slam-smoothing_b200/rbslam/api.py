@@ -36,7 +36,10 @@ class Context:
     """Owns one rbslam_ctx (one GPU)."""
 
     def __init__(self, model, N, T, device=0, rng_mode=_capi.RNG_PHILOX, seed=0,
-                 information_form=False, keep_history=True, ld=0, kalman_variant=0, rank=0, world=1):
+                 information_form=False, keep_history=True, ld=0, kalman_variant=0, rank=0, world=1,
+                 devices=None):
+        """devices=[0, 1, ...]: ONE filter sharded over several GPUs, driven from this process
+        (rbslam_create_group); filter entry points with the device RNG only."""
         self._lib = _capi.lib()
         self.model = model
         self.N, self.T = int(N), int(T)
@@ -59,7 +62,13 @@ class Context:
         self.rank, self.world = rank, world
         cfg.kalman_variant = kalman_variant
         self._h = C.c_void_p()
-        rc = self._lib.rbslam_create(C.byref(self._h), C.byref(cfg))
+        if devices is not None and len(devices) > 1:
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            rc = self._lib.rbslam_create_group(C.byref(self._h), C.byref(cfg), _capi.iptr(dv), dv.shape[0])
+        else:
+            if devices is not None and len(devices) == 1:
+                cfg.device = int(devices[0])
+            rc = self._lib.rbslam_create(C.byref(self._h), C.byref(cfg))
         if rc != _capi.OK:
             msg = self._lib.rbslam_last_error(None) or b""
             self._h = C.c_void_p()
@@ -419,6 +428,43 @@ class Context:
                                                    _capi.dptr(dx), float(dt), _capi.dptr(Q),
                                                    int(use_default), _capi.dptr(out)))
         return out
+
+
+def ekf_dense(model, odometry, y, x0, q0, P0, Q, R, dt, LL=None, *, device=0, keep_P=False):
+    """EKF baseline of the dense magnetic-field example; mirrors
+    ``[xf_traj,qnb_traj,Pf_traj] = ekf_dense(dynModel,measModel,odometry,y,x0,q0,P0,Q,R,dt)``
+    (examples/slam-dense-mag/ekf_dense.m:1-2) with ``model`` standing for the two closures
+    (run_dense3D_magfield.m:281-316).  LL [2 x 3]: the domain bounds measModel_ekf passes to
+    JacobianPhi3D (default [-L; L]).  Returns (xf_traj, qnb_traj, Pf): the last filtered covariance,
+    or all of them [ns x ns x T] with keep_P."""
+    if model.family != _capi.MODEL_DENSE_MAG3D:
+        raise _capi.UnsupportedModelError(_capi.EMODEL, "ekf_dense is defined for the dense magnetic-field model")
+    y = np.asarray(y, dtype=np.float64)
+    T = y.shape[0]
+    with Context(model, 1, max(T, 1), device=device) as ctx:
+        ns = ctx.M + 6
+        F = _capi.fcol
+        odo, yy = F(np.atleast_2d(odometry)), F(y)
+        x0c = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(-1))
+        q0c = np.ascontiguousarray(np.asarray(q0, dtype=np.float64).reshape(-1))
+        P0c, Rc = F(P0), F(np.atleast_2d(R))
+        Qc = np.asarray(Q, dtype=np.float64)
+        Qc = F(Qc[:, :, None] if Qc.ndim == 2 else Qc)
+        dtc = np.ascontiguousarray(np.asarray(dt, dtype=np.float64).reshape(-1))
+        if x0c.shape[0] != ns or q0c.shape[0] != 4 or P0c.shape != (ns, ns) or yy.shape[1] != 3:
+            raise ValueError("ekf_dense: x0 [%d], q0 [4], P0 [%d x %d], y [T x 3]" % (ns, ns, ns))
+        if Qc.shape[:2] != (6, 6) or Rc.shape != (3, 3) or (T > 1 and (odo.shape[1] != 7 or odo.shape[0] < T - 1)):
+            raise ValueError("ekf_dense: Q [6 x 6 (x pages)], R [3 x 3], odometry [>= T-1 x 7]")
+        LLc = F(np.vstack([-model.L, model.L]) if LL is None else np.asarray(LL, dtype=np.float64).reshape(2, 3))
+        xf = np.zeros((ns, T), order="F")
+        qn = np.zeros((4, T), order="F")
+        Pl = np.zeros((ns, ns), order="F")
+        Pt = np.zeros((ns, ns, T), order="F") if keep_P else None
+        ctx._ck(ctx._lib.rbslam_ekf_run(ctx._h, T, _capi.dptr(odo), odo.shape[0], _capi.dptr(yy), _capi.dptr(x0c),
+                                        _capi.dptr(q0c), _capi.dptr(P0c), _capi.dptr(Qc), Qc.shape[2],
+                                        _capi.dptr(Rc), _capi.dptr(dtc), dtc.shape[0], _capi.dptr(LLc),
+                                        _capi.dptr(xf), _capi.dptr(qn), _capi.dptr(Pl), _capi.dptr(Pt)))
+    return xf, qn, (Pt if keep_P else Pl)
 
 
 def plan_migration(ai, old_owner, world):

@@ -182,3 +182,28 @@ def test_plan_shard_invariants():
                     assert nl[kids[0]] == lslot[a]
                     assert np.count_nonzero(nl[kids] == lslot[a]) == 1
             owner, lslot = no.copy(), nl.copy()
+
+
+def test_runner_patches_only_swap_the_handles():
+    """matlab/examples/*.patch: zero-context diffs against the reference's four L2
+    runners; every added line hands rbslam model handles to the drop-ins, nothing else changes."""
+    import glob
+    pdir = os.path.join(PKG, "matlab", "examples")
+    files = sorted(glob.glob(os.path.join(pdir, "*.patch")))
+    assert [os.path.basename(f) for f in files] == ["pfslam.patch", "psslam.patch", "run_dense2D_withHeading.patch",
+                                                    "run_dense3D_magfield.patch"]
+    for f in files:
+        added = [ln[1:] for ln in open(f) if ln.startswith("+") and not ln.startswith("+++")]
+        removed = [ln[1:] for ln in open(f) if ln.startswith("-") and not ln.startswith("---")]
+        assert added and all("mdl" in ln for ln in added), f
+        assert len(added) <= 5 and len(removed) <= 4, f
+        assert any("rbslam_model(" in ln for ln in added), f
+    ref = "/root/reference"
+    if os.path.isdir(ref):        # in the build container: the patterns still match the reference
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("patch_runners", os.path.join(pdir, "patch_runners.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        for rel in mod.EDITS:
+            out = mod.patch_text(rel, open(os.path.join(ref, rel)).read())
+            assert "mdl." in out

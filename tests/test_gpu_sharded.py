@@ -159,3 +159,43 @@ def test_device_planner_equals_host_planner(rbslam_lib, world):
                     old = np.flatnonzero((owner == rank) & (lslot == j))[0]
                     assert n_child[old] == 0
             owner, lslot = ho.copy(), hl.copy()
+
+
+@pytest.mark.parametrize("world,N,m,T,variant", [(2, 32, 64, 10, 2), (2, 64, 253, 8, 7), (4, 64, 64, 8, 2)])
+def test_group_single_process_matches_single_gpu(rbslam_lib, world, N, m, T, variant):
+    """rbslam_create_group: the same sharded filter driven from ONE process (what a MATLAB caller
+    has).  Shards sit on devices 0..n-1 cyclically (all on device 0 on a 1-GPU box); outputs must
+    equal the unsharded run to rounding, for every shard count."""
+    rb = rbslam_lib
+    from rbslam import _capi
+    ndev = _capi.lib().rbslam_device_count()
+    pr = _problem(rb, m, T)
+    gm = rb.models.from_problem(pr)
+    args = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
+    seed = 31
+    with rb.Context(gm, N, T, rng_mode=1, seed=seed, kalman_variant=variant,
+                    devices=[r % ndev for r in range(world)]) as ctx:
+        grp = ctx.filter_run(*args, pr["dt"], want_xn_traj=True)
+        n_launch = ctx.counters()["kernel_launches"]
+        grp2 = ctx.filter_run(*args, pr["dt"], want_xn_traj=False)      # a context is reusable
+    with rb.Context(gm, N, T, rng_mode=1, seed=seed, kalman_variant=variant) as ctx:
+        single = ctx.filter_run(*args, pr["dt"], want_xn_traj=True)
+    assert n_launch > 0
+    for k in ["traj_max", "traj_mean", "xl_max", "xl_mean", "P_max", "P_mean", "traj_sample_iwmax", "xn_traj"]:
+        assert_close_norm(grp[k], single[k], 1e-12, "group vs single: " + k)
+    for k in ["traj_max", "xl_mean", "P_max"]:
+        assert np.array_equal(grp2[k], grp[k]), k
+
+
+def test_group_rejects_what_it_cannot_do(rbslam_lib):
+    rb = rbslam_lib
+    pr = _problem(rb, 64, 6)
+    gm = rb.models.from_problem(pr)
+    with pytest.raises(rb.RbslamError):
+        rb.Context(gm, 33, 6, rng_mode=1, devices=[0, 0])              # N not divisible by the shard count
+    with pytest.raises(rb.RbslamError):
+        rb.Context(gm, 32, 6, rng_mode=0, devices=[0, 0])              # injected streams are single-GPU only
+    with rb.Context(gm, 32, 6, rng_mode=1, kalman_variant=2, devices=[0, 0]) as ctx:
+        with pytest.raises(rb.RbslamError):
+            ctx.smoother_run(pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"],
+                             pr["dt"], 2)
