@@ -169,6 +169,17 @@ RBSLAM_API int rbslam_create(rbslam_ctx **out, const rbslam_config *cfg);
    (cudaDeviceEnablePeerAccess); the step never synchronises with the host. */
 RBSLAM_API int rbslam_create_group(rbslam_ctx **out, const rbslam_config *cfg, const int32_t *devices,
                         int32_t n_devices);
+/* The smoothers on several GPUs from one process.  A sweep is sequential in time and over sweeps; what
+   parallelises is the ancestor-weight evaluation of the reference trajectory (src/particleSmoother.m:171-233,
+   src/particleSmootherInformationForm.m:203-239: N independent dense factorisations per time step, the
+   FP64-bound bulk of a sweep).  Every device holds a full replica of the particle state and runs the
+   filter part of the sweep redundantly (bit-identical on identical GPUs); replica r evaluates the ancestor
+   weights of its block of N / n_devices particles and stores them into every replica's array over peer
+   memory -- the all-gather of weights BASELINE.json's north_star names -- then all replicas normalise and
+   draw the same ancestor.  rbslam_smoother_run on the returned leader drives the group (one host thread
+   per replica); rbslam_destroy(leader) destroys it.  cfg->device/rank/world are ignored. */
+RBSLAM_API int rbslam_create_replicas(rbslam_ctx **out, const rbslam_config *cfg, const int32_t *devices,
+                           int32_t n_devices);
 RBSLAM_API void rbslam_destroy(rbslam_ctx *ctx);
 RBSLAM_API const char *rbslam_last_error(const rbslam_ctx *ctx); /* ctx may be NULL: last create error */
 /* derived sizes: n, d, M, nz, nw, n_odo, ld (in that order) */

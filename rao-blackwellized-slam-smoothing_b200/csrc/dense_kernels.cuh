@@ -149,21 +149,30 @@ struct CholArgs {
 };
 
 #define RB_CH_NB 32
-// Right-looking blocked Cholesky, NB = 32.  The right-hand side rides along as row n of the
-// workspace (ldl >= n+1): the panel solve and the trailing update applied to that row ARE the
+#define RB_CH_LDB 40    // leading dimension of the panel-row operand tile ( = 8 mod 16: conflict-free fragment reads)
+// Left-looking blocked Cholesky, NB = 32.  The right-hand side rides along as row n of the
+// workspace (ldl >= n+1): the panel update and the panel solve applied to that row ARE the
 // forward substitution, so after the last panel L(n, 0:n-1) = (L \ rhs)'.
-//   per panel: (1) 32x32 diagonal block in shared memory, left-looking by one warp;
-//              (2) L21 = A21 L11^-T, one row per thread, registers;
-//              (3) A22 -= L21 L21' with fp64 tensor-core tiles (mma_tile_k32), lower tiles only.
+//   per panel jb (columns jb .. jb+31, rows jb .. n):
+//     (0) C = (A1 + A2 [+ jitter I])(rows, panel) - L(rows, 0:jb) L(panel, 0:jb)'   on the fp64 tensor
+//         cores: row tiles of TR rows, the tile of C preloaded into the accumulators (negated), the two
+//         operands streamed through a double-buffered cp.async stage ring in 32-column steps;
+//     (1) 32x32 diagonal block in shared memory, left-looking by one warp;
+//     (2) L21 = C21 L11^-T, one row per thread, registers.
+// Every element of the factor is written once and the finished panels are only ever READ again
+// (K = jb columns per panel): n^3 / (6 NB) * 8 B = 5.7 MB of operand reads per 515 x 515 matrix, mostly
+// L2 hits, against 22.6 MB of read-modify-write traffic for the right-looking form this replaces
+// (which re-streamed the whole trailing matrix after every panel and was HBM-bound at 21 % of the fp64
+// peak, profiles/tuning_r1.md section 4).
 // NT threads per matrix: 256 (row tiles of 128, 2 CTAs/SM) or 128 (row tiles of 64, 4 CTAs/SM --
 // more CTAs per SM overlap one matrix's serial panel phases with another's tensor-core phase)
 template <int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
   constexpr int TR = NT / 2, LDA_T = TR + 8, NWARP = NT / 32;
   extern __shared__ double sm[];
-  double *sD = sm;                           // [32][33]
-  double *As = sD + 32 * 34;                 // [32][LDA_T] L21 rows of the row tile (16-B aligned)
-  double *Bs = As + 32 * LDA_T;              // [32][RB_LDB] L21 rows of the column tile
+  double *sD = sm;                           // [32][33] (+ pad to a 16-byte boundary)
+  double *As = sD + 32 * 34;                 // [2][32][LDA_T] rows of the row tile, columns k0 .. k0+31
+  double *Bs = As + 2 * 32 * LDA_T;          // [2][32][RB_CH_LDB] rows of the panel
   __shared__ int s_fail;
   __shared__ double s_red[2][8];
   const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,34 +180,86 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
   double *L = a.L + (size_t)b * a.strideL;
   const int ldl = a.ldl;
   const int nr = n + 1;                      // rows incl. the right-hand-side row
+  const int gq = lane >> 2, tg = lane & 3;
+  const int wr = warp * 16;                  // warp tile: 16 rows x 32 columns = 2 x 4 DMMA tiles
   bool ok = false;
   for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
     const double jit = attempt ? a.jitter : 0.0;
-    // lower triangle, one warp per column, four independent loads in flight per lane
-    for (int c = warp; c < n; c += NWARP) {
-      const double *a1 = A1 + (size_t)c * a.lda1;
-      const double *a2 = a.A2 ? a.A2 + (size_t)c * a.lda2 : nullptr;
-      double *lc = L + (size_t)c * ldl;
-      for (int r = c + lane; r < n; r += 128) {
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int rr = r + 32 * u;
-          v[u] = rr < n ? a1[rr] + (a2 ? a2[rr] : 0.0) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int rr = r + 32 * u;
-          if (rr < n) lc[rr] = v[u] + (rr == c ? jit : 0.0);
-        }
-      }
-    }
-    for (int c = tid; c < n; c += blockDim.x)
-      L[n + (size_t)c * ldl] = a.rhs[(size_t)b * a.stride_rhs + c] + (a.rhs2 ? a.rhs2[c] : 0.0);
     if (tid == 0) s_fail = 0;
     __syncthreads();
     for (int jb = 0; jb < n; jb += RB_CH_NB) {
       const int nb = min(RB_CH_NB, n - jb);
+      // (0) panel update: rows jb .. n (row n = right-hand side), columns jb .. jb+nb-1, K = jb
+      for (int ti = jb; ti < nr; ti += TR) {
+        // C tile: all 32 loads of a thread are issued back to back (clamped addresses, no branches:
+        // the loads are latency-bound, one dependent load at a time costs a third of the kernel)
+        double acc[2][4][2];
+        {
+          double c1[2][4][2], c2[2][4][2];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int gr = min(ti + wr + 8 * mi + gq, n - 1), gc = min(jb + 8 * nj + 2 * tg + e, n - 1);
+                c1[mi][nj][e] = A1[gr + (size_t)gc * a.lda1];
+                c2[mi][nj][e] = a.A2 ? a.A2[gr + (size_t)gc * a.lda2] : 0.0;
+              }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int gr = ti + wr + 8 * mi + gq, gc = jb + 8 * nj + 2 * tg + e;
+                double v = c1[mi][nj][e] + c2[mi][nj][e] + (gr == gc ? jit : 0.0);
+                if (gr == n && gc < n) v = a.rhs[(size_t)b * a.stride_rhs + gc] + (a.rhs2 ? a.rhs2[gc] : 0.0);
+                acc[mi][nj][e] = (gc < n && gr >= gc && gr <= n) ? -v : 0.0;   // acc = -C, acc += A B', C_new = -acc
+              }
+        }
+        if (jb > 0) {
+          __syncthreads();                       // the stage ring is free (previous tile / diagonal block done)
+          stage_rows_k32<TR, LDA_T, NT>(As, L, ldl, ti, nr, tid);
+          stage_rows_k32<32, RB_CH_LDB, NT>(Bs, L, ldl, jb, n, tid);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          int buf = 0;
+          for (int k0 = 0; k0 < jb; k0 += 32, buf ^= 1) {
+            if (k0 + 32 < jb) {                  // next step's operands fly while this one is multiplied
+              stage_rows_k32<TR, LDA_T, NT>(As + (buf ^ 1) * 32 * LDA_T, L + (size_t)(k0 + 32) * ldl, ldl, ti, nr, tid);
+              stage_rows_k32<32, RB_CH_LDB, NT>(Bs + (buf ^ 1) * 32 * RB_CH_LDB, L + (size_t)(k0 + 32) * ldl, ldl, jb, n, tid);
+              asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;" ::: "memory");
+            } else {
+              asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            const double *Ab = As + buf * 32 * LDA_T, *Bb = Bs + buf * 32 * RB_CH_LDB;
+#pragma unroll
+            for (int kk = 0; kk < 32; kk += 4) {
+              double av[2], bv[4];
+#pragma unroll
+              for (int mi = 0; mi < 2; ++mi) av[mi] = Ab[(kk + tg) * LDA_T + wr + 8 * mi + gq];
+#pragma unroll
+              for (int nj = 0; nj < 4; ++nj) bv[nj] = Bb[(kk + tg) * RB_CH_LDB + 8 * nj + gq];
+#pragma unroll
+              for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], av[mi], bv[nj]);
+            }
+            __syncthreads();                     // buffer `buf` may be refilled two steps from now
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int gr = ti + wr + 8 * mi + gq, gc = jb + 8 * nj + 2 * tg + e;
+              if (gr < nr && gc < n && gr >= gc) L[gr + (size_t)gc * ldl] = -acc[mi][nj][e];
+            }
+      }
+      __syncthreads();
       // (1) diagonal block
       for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
         const int r = idx % nb, c = idx / nb;
@@ -257,43 +318,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
         }
       }
       __syncthreads();
-      if (r0 >= n) break;
-      // (3) trailing update on lower tiles: rows r0..n, columns r0..n-1
-      const int wr = (warp % (TR / 32)) * 32, wc = (warp / (TR / 32)) * 32;
-      const int gq = lane >> 2, tg = lane & 3;
-      const double *Lp = L + (size_t)jb * ldl;   // the factored panel: columns jb..jb+31
-      for (int tj = r0; tj < n; tj += 64) {
-        stage_rows_k32<64, RB_LDB, NT>(Bs, Lp, ldl, tj, n, tid);
-        for (int ti = tj; ti < nr; ti += TR) {
-          // C tile first: its loads fly while the operand tile is staged.  acc = -C, then
-          // acc += A B' on the tensor cores, store C = -acc  (C -= A B').
-          double acc[4][4][2];
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int gr = ti + wr + 8 * mi + gq, gc = tj + wc + 8 * nj + 2 * tg + e;
-                acc[mi][nj][e] = (gr < nr && gc < n && gr >= gc) ? -L[gr + (size_t)gc * ldl] : 0.0;
-              }
-          __syncthreads();                       // previous tile fully consumed
-          stage_rows_k32<TR, LDA_T, NT>(As, Lp, ldl, ti, nr, tid);
-          cp_async_wait_all();
-          __syncthreads();
-          mma_tile_k32<LDA_T>(As, Bs, wr, wc, lane, acc);
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int gr = ti + wr + 8 * mi + gq, gc = tj + wc + 8 * nj + 2 * tg + e;
-                if (gr < nr && gc < n && gr >= gc) L[gr + (size_t)gc * ldl] = -acc[mi][nj][e];
-              }
-        }
-        __syncthreads();
-      }
     }
     __syncthreads();
     ok = !s_fail;
@@ -329,7 +353,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
 }
 
 static inline size_t chol_solve_smem(int nt) {
-  return sizeof(double) * (32 * 34 + 32 * (nt / 2 + 8) + 32 * RB_LDB);
+  return sizeof(double) * (32 * 34 + 2 * 32 * (nt / 2 + 8) + 2 * 32 * RB_CH_LDB);
 }
 // workspace leading dimension: n rows + the right-hand-side row, 64-byte aligned columns
 static inline int chol_ldl(int n) { return ((n + 1 + 7) / 8) * 8; }

@@ -486,6 +486,7 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
     ctx->group.clear();
     for (rbslam_ctx *m : members) { m->group_member = false; rbslam_destroy(m); }
   }
+  if (ctx->replica_group && ctx->replica_rank == 0) rb_replicas_free(ctx);   // leader: the other replicas go first
   if (ctx->cfg.device >= 0) cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_run_inputs(ctx);

@@ -99,6 +99,8 @@ struct rbslam_ctx {
   void *shard_ws = nullptr;      // ShardWs (sharded.cu); N is the LOCAL particle count when set
   std::vector<rbslam_ctx *> group;   // leader of a single-process group (rbslam_create_group): every shard, itself first
   bool group_member = false;         // a non-leader shard of such a group (destroyed with its leader)
+  void *replica_group = nullptr;     // ReplicaGroup (smoother.cu): full replicas on several GPUs, smoothers
+  int replica_rank = 0;
   const int *anc_override = nullptr;   // sharded engine: thin arrays are slot-indexed
   // streaming pass in groups: group g uses listA/listB + group_off[g][phase], counts d_counts[2g+phase];
   // group_hook(ctx, g) runs before group g>0 (sharded engine: wait for migrants + peer barrier)

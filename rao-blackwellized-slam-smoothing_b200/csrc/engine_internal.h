@@ -68,3 +68,4 @@ int64_t rb_shard_migrated(rbslam_ctx *ctx);
 // smoother.cu
 int rb_info_init(rbslam_ctx *ctx);
 void rb_smoother_free(rbslam_ctx *ctx);
+void rb_replicas_free(rbslam_ctx *leader);

@@ -6,7 +6,9 @@
 // form) and the information-form state update (K8).
 #include <vector>
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <thread>
 #include "engine_internal.h"
 #include "step_kernels.cuh"
 #include "kalman_stream.cuh"
@@ -33,6 +35,107 @@ struct SmootherWs {
 };
 
 static SmootherWs *ws_of(rbslam_ctx *ctx) { return static_cast<SmootherWs *>(ctx->smoother_ws); }
+
+// ---------------------------------------------------------------------------
+// Replica group (rbslam_create_replicas): the smoothers on several GPUs from one process.
+// A sweep is a Markov chain over time and over sweeps; what parallelises is the ancestor-weight
+// evaluation of the reference trajectory -- N independent dense factorisations per time step, the
+// FP64-bound part that dominates a sweep (src/particleSmoother.m:171-233, ...InformationForm.m:203-239).
+// Every device holds a full replica of the particle state and runs the (HBM-bound, far cheaper)
+// filter part of the sweep redundantly and bit-identically; replica r evaluates the ancestor weights
+// of its block of particles only and stores them into EVERY replica's paNtLog array over peer memory
+// (NVLink): the all-gather.  One host thread per replica; per step one cross-device event wait.
+// ---------------------------------------------------------------------------
+struct ReplicaGroup {
+  int world = 1;
+  std::vector<rbslam_ctx *> ctx;             // ctx[0] = leader
+  cudaEvent_t ev[8][2] = {{nullptr}};        // replica r's block is stored everywhere (step parity)
+  double *paNtLog[8] = {nullptr};
+  std::atomic<int> arrived{0}, generation{0}, failed{0};
+  // host barrier between the replicas' threads; false if a replica failed meanwhile
+  bool barrier() {
+    const int gen = generation.load();
+    if (arrived.fetch_add(1) + 1 == world) { arrived.store(0); generation.fetch_add(1); return !failed.load(); }
+    while (generation.load() == gen) {
+      if (failed.load()) return false;
+      std::this_thread::yield();
+    }
+    return !failed.load();
+  }
+};
+static ReplicaGroup *rep_of(rbslam_ctx *ctx) { return static_cast<ReplicaGroup *>(ctx->replica_group); }
+
+void rb_replicas_free(rbslam_ctx *leader) {
+  ReplicaGroup *g = rep_of(leader);
+  if (!g) return;
+  for (size_t r = 1; r < g->ctx.size(); ++r) { g->ctx[r]->replica_group = nullptr; rbslam_destroy(g->ctx[r]); }
+  for (auto &e : g->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
+  leader->replica_group = nullptr;
+  delete g;
+}
+
+extern "C" int rbslam_create_replicas(rbslam_ctx **out, const rbslam_config *cfg, const int32_t *devices, int32_t n_devices) {
+  if (!out || !cfg || !devices || n_devices < 1 || n_devices > 8) return RBSLAM_EARG;
+  *out = nullptr;
+  ReplicaGroup *g = new ReplicaGroup();
+  g->world = n_devices;
+  int rc = RBSLAM_OK;
+  for (int r = 0; r < n_devices && rc == RBSLAM_OK; ++r) {
+    rbslam_config c = *cfg;
+    c.device = devices[r]; c.rank = 0; c.world = 1;
+    rbslam_ctx *ctx = nullptr;
+    rc = rbslam_create(&ctx, &c);
+    if (rc == RBSLAM_OK) { ctx->replica_group = g; ctx->replica_rank = r; g->ctx.push_back(ctx); }
+  }
+  for (int r = 0; r < (int)g->ctx.size() && rc == RBSLAM_OK; ++r) {
+    cudaSetDevice(devices[r]);
+    for (int q = 0; q < 2; ++q)
+      if (cudaEventCreateWithFlags(&g->ev[r][q], cudaEventDisableTiming) != cudaSuccess) rc = RBSLAM_ECUDA;
+    for (int p = 0; p < (int)g->ctx.size() && rc == RBSLAM_OK; ++p) {
+      if (devices[p] == devices[r]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[r], devices[p]);
+      cudaError_t e = can ? cudaDeviceEnablePeerAccess(devices[p], 0) : cudaErrorPeerAccessUnsupported;
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      if (e != cudaSuccess) rc = RBSLAM_ECUDA;
+    }
+  }
+  if (rc != RBSLAM_OK) {
+    for (rbslam_ctx *c : g->ctx) { c->replica_group = nullptr; rbslam_destroy(c); }
+    for (auto &e : g->ev) for (auto &x : e) if (x) cudaEventDestroy(x);
+    delete g;
+    return rc;
+  }
+  *out = g->ctx[0];
+  return RBSLAM_OK;
+}
+
+// this replica's block of particles [lo, hi) for the ancestor weights
+static void rep_block(rbslam_ctx *ctx, int N, int &lo, int &hi) {
+  ReplicaGroup *g = rep_of(ctx);
+  lo = 0; hi = N;
+  if (!g || g->world == 1) return;
+  const int blk = (N + g->world - 1) / g->world;
+  lo = std::min(N, ctx->replica_rank * blk); hi = std::min(N, lo + blk);
+}
+struct OutPtrs { double *p[8]; int n; };
+static OutPtrs rep_outs(rbslam_ctx *ctx, double *own) {
+  OutPtrs o; o.n = 1; o.p[0] = own;
+  ReplicaGroup *g = rep_of(ctx);
+  if (g && g->world > 1) { o.n = g->world; for (int r = 0; r < g->world; ++r) o.p[r] = g->paNtLog[r]; }
+  return o;
+}
+// all-gather point: every replica's block has been stored into every paNtLog array
+static int rep_exchange(rbslam_ctx *ctx, int t) {
+  ReplicaGroup *g = rep_of(ctx);
+  if (!g || g->world == 1) return RBSLAM_OK;
+  const int r = ctx->replica_rank, q = t & 1;
+  CK(cudaEventRecord(g->ev[r][q], ctx->stream));
+  if (!g->barrier()) return ctx->fail(RBSLAM_ECUDA, "a smoother replica failed");
+  for (int p = 0; p < g->world; ++p)
+    if (p != r) CK(cudaStreamWaitEvent(ctx->stream, g->ev[p][q], 0));
+  return RBSLAM_OK;
+}
 
 void rb_smoother_free(rbslam_ctx *ctx) {
   SmootherWs *w = ws_of(ctx);
@@ -110,22 +213,24 @@ __global__ void k_add_RS(int nobs, const int *__restrict__ obs_t, const int *__r
 // paNtLog = log w + logwDyn + logwMeas  (src/particleSmoother.m:229-232 / ...InformationForm.m:234-239)
 __global__ void k_combine_cov(int N, int i0, int cnt, const double *__restrict__ w,
                               const double *__restrict__ lwdyn, const double *__restrict__ sumlog,
-                              const double *__restrict__ vtv, double ne, double *__restrict__ out) {
+                              const double *__restrict__ vtv, double ne, OutPtrs out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= cnt) return;
   const int i = i0 + b;
   const double lwm = -sumlog[b] - 0.5 * vtv[b] - ne / 2.0 * RB_LOG2PI;
-  out[i] = log(w[i]) + lwdyn[i] + lwm;
+  const double v = log(w[i]) + lwdyn[i] + lwm;
+  for (int r = 0; r < out.n; ++r) out.p[r][i] = v;   // every replica's array (peer stores)
 }
 __global__ void k_combine_info(int N, int i0, int cnt, const double *__restrict__ w,
                                const double *__restrict__ lwdyn, const double *__restrict__ sumlog,
                                const double *__restrict__ vtv, const double *__restrict__ q2,
-                               const double *__restrict__ hld, double *__restrict__ out) {
+                               const double *__restrict__ hld, OutPtrs out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= cnt) return;
   const int i = i0 + b;
   const double lwm = -0.5 * q2[i] - hld[i] - sumlog[b] + 0.5 * vtv[b];
-  out[i] = log(w[i]) + lwdyn[i] + lwm;
+  const double v = log(w[i]) + lwdyn[i] + lwm;
+  for (int r = 0; r < out.n; ++r) out.p[r][i] = v;
 }
 
 // ---- information form -------------------------------------------------------------
@@ -527,8 +632,11 @@ static int ancestor_weights_cov(rbslam_ctx *ctx, int t, bool use_default_dyn) {
   const int *slot_old = ctx->d_slot[ctx->cs];
   const size_t sW = (size_t)M * w->ntau_max, sS = w->ntau_max * w->ntau_max;
   const size_t sLw = (size_t)chol_ldl((int)w->ntau_max) * w->ntau_max;
-  for (int b0 = 0; b0 < N; b0 += (int)w->batch) {
-    const int cnt = std::min<int>((int)w->batch, N - b0);
+  int blo, bhi;
+  rep_block(ctx, N, blo, bhi);
+  const OutPtrs outs = rep_outs(ctx, w->paNtLog);
+  for (int b0 = blo; b0 < bhi; b0 += (int)w->batch) {
+    const int cnt = std::min<int>((int)w->batch, bhi - b0);
     if (ne > 0) {
       GemmArgs g1{};   // W = P_i * D'
       g1.m = M; g1.n = ne; g1.k = M;
@@ -571,11 +679,11 @@ static int ancestor_weights_cov(rbslam_ctx *ctx, int t, bool use_default_dyn) {
       CK(cudaMemsetAsync(w->vtv, 0, sizeof(double) * cnt, ctx->stream));
     }
     k_combine_cov<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(N, b0, cnt, ctx->d_w, w->lwdyn, w->sumlog, w->vtv,
-                                                              (double)ne, w->paNtLog);
+                                                              (double)ne, outs);
     ctx->launches += 1;
   }
   CK(cudaGetLastError());
-  return RBSLAM_OK;
+  return rep_exchange(ctx, t);
 }
 
 // information form (K7): ...InformationForm.m:187-254
@@ -594,8 +702,11 @@ static int ancestor_weights_info(rbslam_ctx *ctx, int t, bool use_default_dyn) {
                                                             ctx->h_dt[t - 1], Qp, use_default_dyn ? 1 : 0, w->lwdyn);
   ctx->launches += 1;
   const size_t sL = (size_t)chol_ldl(M) * M;
-  for (int b0 = 0; b0 < N; b0 += (int)w->batch) {
-    const int cnt = std::min<int>((int)w->batch, N - b0);
+  int blo, bhi;
+  rep_block(ctx, N, blo, bhi);
+  const OutPtrs outs = rep_outs(ctx, w->paNtLog);
+  for (int b0 = blo; b0 < bhi; b0 += (int)w->batch) {
+    const int cnt = std::min<int>((int)w->batch, bhi - b0);
     CholArgs c{};
     c.n = M; c.A1 = ctx->d_Imat; c.lda1 = ctx->ld; c.strideA1 = ctx->slab; c.slot1 = ctx->d_slot[ctx->cs] + b0;
     c.A2 = w->ImatAddt; c.lda2 = M; c.L = w->Lw; c.ldl = chol_ldl(M); c.strideL = sL;
@@ -604,19 +715,47 @@ static int ancestor_weights_info(rbslam_ctx *ctx, int t, bool use_default_dyn) {
     c.sum_log_diag = w->sumlog; c.vtv = w->vtv; c.status = ctx->d_status; c.t = t;
     if ((rc = launch_chol(ctx, c, cnt))) return rc;
     k_combine_info<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(N, b0, cnt, ctx->d_w, w->lwdyn, w->sumlog, w->vtv,
-                                                               w->q2, ctx->d_hld[ctx->cx], w->paNtLog);
+                                                               w->q2, ctx->d_hld[ctx->cx], outs);
     ctx->launches += 1;
   }
   CK(cudaGetLastError());
-  return RBSLAM_OK;
+  return rep_exchange(ctx, t);
 }
 
 // ---------------------------------------------------------------------------
 // the sweep loop
 // ---------------------------------------------------------------------------
+static int smoother_run_impl(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N_K, int32_t form,
+                             rbslam_smoother_outputs *out);
+
 extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N_K, int32_t form,
                                    rbslam_smoother_outputs *out) {
   if (!ctx || !in || !out || N_K < 1 || (form != 0 && form != 1)) return RBSLAM_EARG;
+  ReplicaGroup *g = rep_of(ctx);
+  if (!g || g->world == 1) return smoother_run_impl(ctx, in, N_K, form, out);
+  if (ctx->replica_rank != 0) return ctx->fail(RBSLAM_EARG, "call the smoother on the leader of the replica group");
+  // one host thread per replica: every replica runs the same sweeps on the same inputs and streams
+  g->arrived.store(0); g->failed.store(0);
+  std::vector<int> rcs(g->world, RBSLAM_OK);
+  std::vector<std::thread> th;
+  rbslam_smoother_outputs none;
+  memset(&none, 0, sizeof none);
+  for (int r = 1; r < g->world; ++r)
+    th.emplace_back([&, r]() {
+      rcs[r] = smoother_run_impl(g->ctx[r], in, N_K, form, &none);
+      if (rcs[r]) g->failed.store(1);
+    });
+  rcs[0] = smoother_run_impl(ctx, in, N_K, form, out);
+  if (rcs[0]) g->failed.store(1);
+  for (auto &t : th) t.join();
+  cudaSetDevice(ctx->cfg.device);
+  for (int r = 0; r < g->world; ++r)
+    if (rcs[r]) { if (r) ctx->err = "replica " + std::to_string(r) + ": " + g->ctx[r]->err; return rcs[r]; }
+  return RBSLAM_OK;
+}
+
+static int smoother_run_impl(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N_K, int32_t form,
+                             rbslam_smoother_outputs *out) {
   if (ctx->shard_ws) return ctx->fail(RBSLAM_EARG, "rbslam_smoother_run: this context is a filter shard (world > 1)");
   if (!ctx->cfg.keep_history) return ctx->fail(RBSLAM_EARG, "the smoother needs keep_history=1");
   if (ctx->pt) return ctx->fail(RBSLAM_EARG, "packed symmetric slabs (kalman_variant 7 / -1) are filter-only: create the context with kalman_variant 0");
@@ -638,6 +777,10 @@ extern "C" int rbslam_smoother_run(rbslam_ctx *ctx, const rbslam_inputs *in, int
   ctx->smoother_ws = w;
   RB_ALLOC(w->xnk, (size_t)T * n);
   RB_ALLOC(w->lwdyn, N); RB_ALLOC(w->paNtLog, N); RB_ALLOC(w->paNt, N);
+  if (ReplicaGroup *g = rep_of(ctx)) {   // publish this replica's array, wait for everybody's
+    g->paNtLog[ctx->replica_rank] = w->paNtLog;
+    if (g->world > 1 && !g->barrier()) return ctx->fail(RBSLAM_ECUDA, "a smoother replica failed");
+  }
   RB_ALLOC(w->Uend, N_K); RB_ALLOC(w->ak, N_K);
   if ((rc = rb_h2d(ctx, w->Uend, ctx->h_Uend.data(), sizeof(double) * N_K))) return rc;
   if (out->AI) {

@@ -67,6 +67,7 @@ SYMBOLS = {
     "rbslam_device_count": (C.c_int, []),
     "rbslam_create": (C.c_int, [C.POINTER(_ctx), C.POINTER(Config)]),
     "rbslam_create_group": (C.c_int, [C.POINTER(_ctx), C.POINTER(Config), c_int32_p, C.c_int32]),
+    "rbslam_create_replicas": (C.c_int, [C.POINTER(_ctx), C.POINTER(Config), c_int32_p, C.c_int32]),
     "rbslam_destroy": (None, [_ctx]),
     "rbslam_last_error": (C.c_char_p, [_ctx]),
     "rbslam_dims": (C.c_int, [_ctx, c_int32_p]),

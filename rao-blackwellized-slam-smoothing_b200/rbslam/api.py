@@ -37,9 +37,11 @@ class Context:
 
     def __init__(self, model, N, T, device=0, rng_mode=_capi.RNG_PHILOX, seed=0,
                  information_form=False, keep_history=True, ld=0, kalman_variant=0, rank=0, world=1,
-                 devices=None):
+                 devices=None, replicas=False):
         """devices=[0, 1, ...]: ONE filter sharded over several GPUs, driven from this process
-        (rbslam_create_group); filter entry points with the device RNG only."""
+        (rbslam_create_group); filter entry points with the device RNG only.
+        devices=[...], replicas=True: full replicas for the smoothers, the ancestor weights split
+        over the devices (rbslam_create_replicas)."""
         self._lib = _capi.lib()
         self.model = model
         self.N, self.T = int(N), int(T)
@@ -64,7 +66,8 @@ class Context:
         self._h = C.c_void_p()
         if devices is not None and len(devices) > 1:
             dv = np.ascontiguousarray(devices, dtype=np.int32)
-            rc = self._lib.rbslam_create_group(C.byref(self._h), C.byref(cfg), _capi.iptr(dv), dv.shape[0])
+            create = self._lib.rbslam_create_replicas if replicas else self._lib.rbslam_create_group
+            rc = create(C.byref(self._h), C.byref(cfg), _capi.iptr(dv), dv.shape[0])
         else:
             if devices is not None and len(devices) == 1:
                 cfg.device = int(devices[0])

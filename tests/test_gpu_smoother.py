@@ -111,6 +111,8 @@ def test_smoother_information_form(rbslam_lib, fam, N, K, kw):
                                            forced=dict(ai=ai, ak=ak), tap=tap)
     with rb.Context(gm, N, T, rng_mode=0, information_form=True) as ctx:
         def cb(k, t):
+            if t == T:        # sweep-complete notification (outputs of sweep k are written)
+                return
             assert_close_norm(ctx.read_particles(P=False)["w"], lws[(k, t)], 1e-6, "w k=%d t=%d" % (k, t))
         ctx.set_step_callback(cb)
         ctx.smoother_run(*_args(pr), pr["dt"], K, 1, streams=st, forced_ancestors=ai, forced_ak=ak)
@@ -247,3 +249,32 @@ def test_particlesmoother_makeplots_and_progress(rbslam_lib, capsys):
         assert_close_norm(g[3][:, :, :g[2] + 1], w[3][:, :, :w[2] + 1], 1e-8, "XNK so far")
     out = capsys.readouterr().out
     assert out.count("Particle smoother iteration") == K and "iteration %d/%d done." % (K, K) in out
+
+
+@pytest.mark.parametrize("form,fam,N,K,kw,world", [
+    (1, "mag", 10, 3, {"m": 64, "T": 10}, 2),       # information form: K7 split over two replicas
+    (0, "mag", 9, 2, {"m": 64, "T": 8}, 2),         # covariance form, N not divisible by the replica count
+    (1, "radio", 16, 2, {"traj": "square_3D", "m": 40}, 4),
+    (0, "sparse", 8, 2, {"T": 20}, 2),              # re-linearised future Jacobians per particle
+])
+def test_smoother_replicas_match_single_gpu(rbslam_lib, form, fam, N, K, kw, world):
+    """rbslam_create_replicas: the ancestor weights of each time step are evaluated block-wise on
+    several devices (all on device 0 on a 1-GPU box) and all-gathered over peer memory; the run
+    must reproduce the single-GPU smoother exactly (same kernels on the same numbers)."""
+    rb = rbslam_lib
+    from rbslam import _capi
+    ndev = _capi.lib().rbslam_device_count()
+    pr, om, gm = _setup(rb, fam, N, **kw)
+    T = pr["y"].shape[0]
+    st = oracle.Streams.from_numpy_rng(np.random.default_rng(11), K, T, N, om.nz)
+    with rb.Context(gm, N, T, rng_mode=0, information_form=(form == 1)) as ctx:
+        one = ctx.smoother_run(*_args(pr), pr["dt"], K, form, streams=st, want_AI=True)
+    with rb.Context(gm, N, T, rng_mode=0, information_form=(form == 1), replicas=True,
+                    devices=[r % ndev for r in range(world)]) as ctx:
+        rep = ctx.smoother_run(*_args(pr), pr["dt"], K, form, streams=st, want_AI=True)
+        rep2 = ctx.smoother_run(*_args(pr), pr["dt"], K, form, streams=st)      # reusable
+    assert np.array_equal(rep["ak"], one["ak"])
+    for k in ["XNK", "XLK", "PK"]:
+        assert_close_norm(rep[k], one[k], 1e-12, "replicas vs single: " + k)
+        assert np.array_equal(rep2[k], rep[k]), k
+    assert_close_norm(np.nan_to_num(rep["AI"]), np.nan_to_num(one["AI"]), 1e-12, "AI")
