@@ -294,6 +294,23 @@ RBSLAM_API int rbslam_ekf_run(rbslam_ctx *ctx, int32_t T, const double *odometry
                    const double *R, const double *dt, int32_t dt_len, const double *LL, double *xf_traj,
                    double *qnb_traj, double *Pf_last, double *Pf_traj);
 
+/* ---- localisation-only particle filter (fixed map) --------------------------- */
+/* examples/mag-localization-mapping/particleFilterLocalization.m:50-132 with the closures dynModel / measModel
+   of run_localization.m:241-280, for a dense-mag context (its basis NN, L).  Bootstrap particle filter of the
+   7-state pose against a FIXED reduced-rank GP map: map_mean [M] (the example's `foo`), var_rows [N x 3]
+   (row i = the predictive variance the reference reads for particle i, dVarft(i,:)), sigma2.
+   odometry [odo_rows x 7]; y [T x 3]; x0 [7 x x0_cols], x0_cols 1 or N; Q [6 x 6 x Q_pages]; dt [dt_len].
+   U [N x T], Z [6 x N x T]: injected uniforms / normals in the reference's order (column 0 unused), or both
+   NULL for the device Philox stream.  Weights are w = measModel(yt, xn) ./ sum (plain sum, the reference's
+   quirk of SUMMING the three component densities kept).  Outputs (any may be NULL): traj_max, traj_mean
+   [7 x T]; xn_traj [7 x N x T]; ancestors [N x T] 0-based; w_hist [N x T]; n_diverged = steps with
+   sum(w) <= 1e-12 (the reference prints a message and carries on). */
+RBSLAM_API int rbslam_localization_run(rbslam_ctx *ctx, int32_t N, int32_t T, const double *odometry, int32_t odo_rows,
+                            const double *y, const double *x0, int32_t x0_cols, const double *Q, int32_t Q_pages,
+                            const double *dt, int32_t dt_len, const double *map_mean, const double *var_rows,
+                            double sigma2, const double *U, const double *Z, double *traj_max, double *traj_mean,
+                            double *xn_traj, int32_t *ancestors, double *w_hist, int32_t *n_diverged);
+
 /* ---- multi-GPU sharding (one process per GPU) --------------------------- */
 /* Host-only planner: given the ancestors of all N new particles and the owner
    rank of every old particle, assign new particles to ranks so that offspring

@@ -34,11 +34,12 @@ from .particle_smoother import particleSmoother
 from .particle_smoother_info import particleSmootherInformationForm
 from .streams import Streams, philox_uniforms_normals
 from .ekf import ekf_dense
+from .localization import particleFilterLocalization
 
 __all__ = [
     "sample", "expq", "qLeft", "quat2rmat", "quat2rmat_batch", "qInv", "logq",
     "mcross", "chol_lower", "domain_cartesian_dx", "eigenfun", "eigenfun_dx",
     "eigenval", "DenseMag3D", "DenseRadio2D", "SparseVisual2D",
     "particleFilter", "particleSmoother", "particleSmootherInformationForm",
-    "Streams", "philox_uniforms_normals", "ekf_dense",
+    "Streams", "philox_uniforms_normals", "ekf_dense", "particleFilterLocalization",
 ]

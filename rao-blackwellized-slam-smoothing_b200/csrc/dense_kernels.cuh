@@ -146,6 +146,7 @@ struct CholArgs {
   double *vtv;          // [batch]  v'v with v = L\rhs
   DevStatus *status;
   int t;
+  const int *only_failed = nullptr;   // k_chol_solve: process only matrices with only_failed[b] != 0
 };
 
 #define RB_CH_NB 32
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
   __shared__ int s_fail;
   __shared__ double s_red[2][8];
   const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (a.only_failed && !a.only_failed[b]) return;   // retry pass after the batched panel path
   const double *A1 = a.A1 + (size_t)(a.slot1 ? a.slot1[b] : b) * a.strideA1;
   double *L = a.L + (size_t)b * a.strideL;
   const int ldl = a.ldl;
@@ -349,6 +351,255 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
     for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { l2 += s_red[0][q]; v2 += s_red[1][q]; }
     a.sum_log_diag[b] = l2;
     a.vtv[b] = v2;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Batched Cholesky, panel by panel ACROSS the batch (large batches: C5, N = 4096).
+// One CTA per matrix (k_chol_solve) keeps 3-4 matrices per SM in flight and is bound by the latency of
+// its own serial chain (operand loads, one warp on the diagonal block, barriers; ncu: issue slots 17 %
+// busy).  Here every panel step is a pair of kernels over the whole batch:
+//   k_chol_panel_gemm   C(rows, panel) = (A1 + A2)(rows, panel) - L(rows, 0:jb) L(panel, 0:jb)'
+//                       128 x 64 x jb tiles on the fp64 tensor cores, grid (row tiles, 1, batch):
+//                       thousands of independent tiles, double-buffered cp.async operand staging;
+//   k_chol_panel_factor diagonal 64 x 64 block (two 32 x 32 warp-level factorisations + the update
+//                       between them) and the triangular solve of the rows below, one CTA per matrix;
+// then k_chol_finalize (log-determinant, v'v).  Left-looking: every factor element is written once.
+// ---------------------------------------------------------------------------
+#define RB_CP_NB 64
+struct CholPanelArgs {
+  CholArgs c;
+  int jb;          // first column of the panel
+  int *fail;       // [batch] != 0: a pivot was not positive (matrix not PD)
+};
+
+__global__ void __launch_bounds__(256, 2) k_chol_panel_gemm(CholPanelArgs p) {
+  extern __shared__ double sm_cp[];
+  double *As = sm_cp;                        // [2][32][RB_LDA]
+  double *Bs = sm_cp + 2 * 32 * RB_LDA;      // [2][32][RB_LDB]
+  const CholArgs &a = p.c;
+  const int b = blockIdx.z, n = a.n, nr = n + 1, jb = p.jb;
+  const int ti = jb + 128 * blockIdx.x;
+  if (ti >= nr) return;
+  const double *A1 = a.A1 + (size_t)(a.slot1 ? a.slot1[b] : b) * a.strideA1;
+  double *L = a.L + (size_t)b * a.strideL;
+  const int ldl = a.ldl;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+  const int gq = lane >> 2, tg = lane & 3;
+  double acc[4][4][2];
+  {   // C tile, negated; all loads issued back to back (clamped addresses, no branches)
+    double c1[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gr = min(ti + wr + 8 * mi + gq, n - 1), gc = min(jb + wc + 8 * nj + 2 * tg + e, n - 1);
+          c1[mi][nj][e] = A1[gr + (size_t)gc * a.lda1] + (a.A2 ? a.A2[gr + (size_t)gc * a.lda2] : 0.0);
+        }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gr = ti + wr + 8 * mi + gq, gc = jb + wc + 8 * nj + 2 * tg + e;
+          double v = c1[mi][nj][e];
+          if (gr == n && gc < n) v = a.rhs[(size_t)b * a.stride_rhs + gc] + (a.rhs2 ? a.rhs2[gc] : 0.0);
+          acc[mi][nj][e] = (gc < n && gr >= gc && gr <= n) ? -v : 0.0;
+        }
+  }
+  if (jb > 0) {
+    stage_rows_k32<128, RB_LDA, 256>(As, L, ldl, ti, nr, tid);
+    stage_rows_k32<64, RB_LDB, 256>(Bs, L, ldl, jb, n, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int buf = 0;
+    for (int k0 = 0; k0 < jb; k0 += 32, buf ^= 1) {
+      if (k0 + 32 < jb) {
+        stage_rows_k32<128, RB_LDA, 256>(As + (buf ^ 1) * 32 * RB_LDA, L + (size_t)(k0 + 32) * ldl, ldl, ti, nr, tid);
+        stage_rows_k32<64, RB_LDB, 256>(Bs + (buf ^ 1) * 32 * RB_LDB, L + (size_t)(k0 + 32) * ldl, ldl, jb, n, tid);
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      mma_tile_k32(As + buf * 32 * RB_LDA, Bs + buf * 32 * RB_LDB, wr, wc, lane, acc);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gr = ti + wr + 8 * mi + gq, gc = jb + wc + 8 * nj + 2 * tg + e;
+        if (gr < nr && gc < n && gr >= gc) L[gr + (size_t)gc * ldl] = -acc[mi][nj][e];
+      }
+}
+
+// 32 x 32 Cholesky in shared memory by one warp (left-looking); sD row-major with stride 33.
+// Returns false when a pivot is not positive.
+__device__ __forceinline__ bool warp_chol32(double *sD, int nb, int lane) {
+  for (int j = 0; j < nb; ++j) {
+    double s = 0.0;
+    if (lane >= j && lane < nb) {
+      s = sD[lane * 33 + j];
+      for (int k = 0; k < j; ++k) s = fma(-sD[lane * 33 + k], sD[j * 33 + k], s);
+    }
+    const double dj = __shfl_sync(0xffffffffu, s, j);
+    if (!(dj > 0.0)) return false;
+    const double ljj = sqrt(dj);
+    if (lane == j) sD[j * 33 + j] = ljj;
+    else if (lane > j && lane < nb) sD[lane * 33 + j] = s / ljj;
+    __syncwarp();
+  }
+  return true;
+}
+// x (one row of 32) <- x L^-T by forward substitution, L in shared memory (row-major, stride 33)
+__device__ __forceinline__ void row_solve32(double (&x)[32], const double *sD) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    double sx = x[k];
+#pragma unroll
+    for (int q = 0; q < 32; ++q)
+      if (q < k) sx = fma(-x[q], sD[k * 33 + q], sx);
+    x[k] = sx / sD[k * 33 + k];
+  }
+}
+
+__global__ void __launch_bounds__(128, 3) k_chol_panel_factor(CholPanelArgs p) {
+  __shared__ double sD1[32 * 33], sD2[32 * 33], sL21[32 * 33];   // L11, L22, L21 (row-major, stride 33)
+  __shared__ int s_ok;
+  const CholArgs &a = p.c;
+  const int b = blockIdx.x, n = a.n, nr = n + 1, jb = p.jb, ldl = a.ldl;
+  double *L = a.L + (size_t)b * a.strideL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = min(RB_CP_NB, n - jb), nb1 = min(32, nb), nb2 = nb - nb1;
+  if (p.fail[b]) return;                     // an earlier panel failed: the retry path redoes this matrix
+  for (int idx = tid; idx < 32 * 33; idx += blockDim.x) { sD1[idx] = 0.0; sD2[idx] = 0.0; sL21[idx] = 0.0; }
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
+  for (int idx = tid; idx < nb1 * nb1; idx += blockDim.x) {
+    const int r = idx % nb1, c = idx / nb1;
+    if (r >= c) sD1[r * 33 + c] = L[(jb + r) + (size_t)(jb + c) * ldl];
+  }
+  for (int idx = tid; idx < nb2 * nb1; idx += blockDim.x) {   // A21 of the diagonal block
+    const int r = idx % nb2, c = idx / nb2;
+    sL21[r * 33 + c] = L[(jb + 32 + r) + (size_t)(jb + c) * ldl];
+  }
+  for (int idx = tid; idx < nb2 * nb2; idx += blockDim.x) {
+    const int r = idx % nb2, c = idx / nb2;
+    if (r >= c) sD2[r * 33 + c] = L[(jb + 32 + r) + (size_t)(jb + 32 + c) * ldl];
+  }
+  __syncthreads();
+  if (warp == 0 && !warp_chol32(sD1, nb1, lane) && lane == 0) s_ok = 0;
+  __syncthreads();
+  if (s_ok && nb2 > 0) {
+    if (warp == 0) {   // L21 = A21 L11^-T: lane = row
+      if (lane < nb2) {
+        double x[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x[k] = sL21[lane * 33 + k];
+        row_solve32(x, sD1);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sL21[lane * 33 + k] = x[k];
+      }
+      __syncwarp();
+      // A22 -= L21 L21'  (lower part), then factor it
+      for (int idx = lane; idx < nb2 * nb2; idx += 32) {
+        const int r = idx % nb2, c = idx / nb2;
+        if (r >= c) {
+          double s = sD2[r * 33 + c];
+          for (int k = 0; k < 32; ++k) s = fma(-sL21[r * 33 + k], sL21[c * 33 + k], s);
+          sD2[r * 33 + c] = s;
+        }
+      }
+      __syncwarp();
+      if (!warp_chol32(sD2, nb2, lane) && lane == 0) s_ok = 0;
+    }
+  }
+  __syncthreads();
+  if (!s_ok) { if (tid == 0) p.fail[b] = 1; return; }
+  // the factored diagonal block
+  for (int idx = tid; idx < nb1 * nb1; idx += blockDim.x) {
+    const int r = idx % nb1, c = idx / nb1;
+    if (r >= c) L[(jb + r) + (size_t)(jb + c) * ldl] = sD1[r * 33 + c];
+  }
+  for (int idx = tid; idx < nb2 * nb1; idx += blockDim.x) {
+    const int r = idx % nb2, c = idx / nb2;
+    L[(jb + 32 + r) + (size_t)(jb + c) * ldl] = sL21[r * 33 + c];
+  }
+  for (int idx = tid; idx < nb2 * nb2; idx += blockDim.x) {
+    const int r = idx % nb2, c = idx / nb2;
+    if (r >= c) L[(jb + 32 + r) + (size_t)(jb + 32 + c) * ldl] = sD2[r * 33 + c];
+  }
+  // rows below the diagonal block (row n = right-hand side): X = C L_JJ^-T, 32 columns at a time
+  const int r0 = jb + nb;
+  if (nb == RB_CP_NB) {
+#pragma unroll 1
+    for (int r = r0 + tid; r < nr; r += blockDim.x) {
+      asm volatile("" ::: "memory");
+      double x[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) x[k] = L[r + (size_t)(jb + k) * ldl];
+      row_solve32(x, sD1);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) L[r + (size_t)(jb + k) * ldl] = x[k];
+      double y[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) y[k] = L[r + (size_t)(jb + 32 + k) * ldl];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {     // second half: c2 - x1 L21'
+        double sy = y[k];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) sy = fma(-x[q], sL21[k * 33 + q], sy);
+        y[k] = sy;
+      }
+      row_solve32(y, sD2);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) L[r + (size_t)(jb + 32 + k) * ldl] = y[k];
+    }
+  } else {   // last, narrower panel: only the right-hand-side row is left below it
+    if (tid == 0) {
+      double x[RB_CP_NB];
+      for (int k = 0; k < nb; ++k) x[k] = L[n + (size_t)(jb + k) * ldl];
+      for (int k = 0; k < nb; ++k) {
+        double sx = x[k];
+        for (int q = 0; q < k; ++q) {
+          const double lkq = k < 32 ? sD1[k * 33 + q] : (q < 32 ? sL21[(k - 32) * 33 + q] : sD2[(k - 32) * 33 + (q - 32)]);
+          sx = fma(-x[q], lkq, sx);
+        }
+        x[k] = sx / (k < 32 ? sD1[k * 33 + k] : sD2[(k - 32) * 33 + (k - 32)]);
+      }
+      for (int k = 0; k < nb; ++k) L[n + (size_t)(jb + k) * ldl] = x[k];
+    }
+  }
+}
+
+// sum(log(diag(L))) and v'v with v = L \ rhs (row n of the workspace); failed matrices get NaN
+__global__ void __launch_bounds__(128) k_chol_finalize(CholArgs a, const int *__restrict__ fail) {
+  __shared__ double s_red[2][4];
+  const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double *L = a.L + (size_t)b * a.strideL;
+  if (fail[b]) {
+    if (tid == 0) { a.sum_log_diag[b] = nan(""); a.vtv[b] = nan(""); }
+    return;
+  }
+  double ld = 0.0, vv = 0.0;
+  for (int r = tid; r < n; r += blockDim.x) {
+    ld += log(L[r + (size_t)r * a.ldl]);
+    const double v = L[n + (size_t)r * a.ldl];
+    vv = fma(v, v, vv);
+  }
+  ld = warp_sum(ld); vv = warp_sum(vv);
+  if (lane == 0) { s_red[0][warp] = ld; s_red[1][warp] = vv; }
+  __syncthreads();
+  if (tid == 0) {
+    a.sum_log_diag[b] = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
+    a.vtv[b] = (s_red[1][0] + s_red[1][1]) + (s_red[1][2] + s_red[1][3]);
   }
 }
 

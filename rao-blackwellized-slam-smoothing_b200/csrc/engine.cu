@@ -498,7 +498,7 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
                   ctx->d_counts, ctx->d_H, ctx->d_yhat, ctx->d_PHpart, ctx->d_G, ctx->d_KS,
                   ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_PHp, ctx->d_fam,
                   ctx->d_logw, ctx->d_w, ctx->d_wc, ctx->d_Xhist, ctx->d_Ahist, ctx->d_traj_max,
-                  ctx->d_traj_mean, ctx->d_iwmax, ctx->d_status, ctx->d_scratch, ctx->d_yhattraj};
+                  ctx->d_traj_mean, ctx->d_iwmax, ctx->d_status, ctx->d_scratch, ctx->d_yhattraj, ctx->d_chol_fail};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (auto e : ctx->ph_events) cudaEventDestroy(e);
   for (auto &e : ctx->user_events) if (e) cudaEventDestroy(e);

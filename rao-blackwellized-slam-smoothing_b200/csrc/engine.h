@@ -96,6 +96,8 @@ struct rbslam_ctx {
   cudaEvent_t user_events[16] = {nullptr};
 
   void *smoother_ws = nullptr;   // SmootherWs (smoother.cu)
+  int *d_chol_fail = nullptr;    // [chol_fail_cap] not-PD flags of the batched panel Cholesky
+  int chol_fail_cap = 0;
   void *shard_ws = nullptr;      // ShardWs (sharded.cu); N is the LOCAL particle count when set
   std::vector<rbslam_ctx *> group;   // leader of a single-process group (rbslam_create_group): every shard, itself first
   bool group_member = false;         // a non-leader shard of such a group (destroyed with its leader)

@@ -5,3 +5,4 @@
 #include "ops.cu"
 #include "sharded.cu"
 #include "ekf.cu"
+#include "localization.cu"

@@ -600,13 +600,49 @@ static int launch_gemm(rbslam_ctx *ctx, bool ta, const GemmArgs &g, int batch) {
 }
 
 static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
-  static int nt = 0;
+  static int nt = 0, panel_min = 0;
   if (!nt) {
     nt = 128;
     if (const char *e = getenv("RBSLAM_CHOL_THREADS")) nt = atoi(e) == 256 ? 256 : 128;
+    // batches at least this large go panel by panel across the batch.  Measured at C5 (N = 4096, M = 515):
+    // 21.6 ms per step against 19.8 ms for one CTA per matrix (profiles/tuning_r2.md), so the path is
+    // opt-in (RBSLAM_CHOL_PANEL_MIN=<batch size>) until its two kernels are tuned
+    panel_min = 1 << 30;
+    if (const char *e = getenv("RBSLAM_CHOL_PANEL_MIN")) panel_min = std::max(1, atoi(e));
   }
   RB_OPTIN_SMEM(k_chol_solve<128>, chol_solve_smem(128));
   RB_OPTIN_SMEM(k_chol_solve<256>, chol_solve_smem(256));
+  if (batch >= panel_min && c.n > RB_CP_NB) {
+    // panel by panel across the batch (dense_kernels.cuh): thousands of independent tensor-core tiles
+    // per launch instead of 3-4 latency-bound matrices per SM
+    if (ctx->chol_fail_cap < batch) {
+      if (ctx->d_chol_fail) cudaFree(ctx->d_chol_fail);
+      ctx->d_chol_fail = nullptr; ctx->chol_fail_cap = 0;
+      RB_ALLOC(ctx->d_chol_fail, batch);
+      ctx->chol_fail_cap = batch;
+    }
+    CK(cudaMemsetAsync(ctx->d_chol_fail, 0, sizeof(int) * batch, ctx->stream));
+    const size_t gsm = sizeof(double) * 2 * 32 * (RB_LDA + RB_LDB);
+    RB_OPTIN_SMEM(k_chol_panel_gemm, gsm);
+    CholPanelArgs p;
+    p.c = c; p.fail = ctx->d_chol_fail;
+    const int nr = c.n + 1;
+    for (int jb = 0; jb < c.n; jb += RB_CP_NB) {
+      p.jb = jb;
+      k_chol_panel_gemm<<<dim3((nr - jb + 127) / 128, 1, batch), 256, gsm, ctx->stream>>>(p);
+      k_chol_panel_factor<<<batch, 128, 0, ctx->stream>>>(p);
+      ctx->launches += 2;
+    }
+    k_chol_finalize<<<batch, 128, 0, ctx->stream>>>(c, ctx->d_chol_fail);
+    // matrices that were not positive definite: the one-CTA-per-matrix kernel redoes them with the
+    // reference's retry (jitter) / error semantics; it returns at once for all the others
+    CholArgs c2 = c;
+    c2.only_failed = ctx->d_chol_fail;
+    k_chol_solve<128><<<batch, 128, chol_solve_smem(128), ctx->stream>>>(c2);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return RBSLAM_OK;
+  }
   if (nt == 256) k_chol_solve<256><<<batch, 256, chol_solve_smem(256), ctx->stream>>>(c);
   else k_chol_solve<128><<<batch, 128, chol_solve_smem(128), ctx->stream>>>(c);
   ctx->launches += 1;

@@ -6,6 +6,7 @@
 //       rbslam_mex('smoother', model, form, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P, N_K, dt, opts)
 //   J = rbslam_mex('jacobianphi3d', x, N_m, xl, xu, yl, yu, zl, zu, Indices)      (tools/JacobianPhi3D.m:1)
 //   [xf_traj,qnb_traj,Pf_traj] = rbslam_mex('ekf', model, odometry, y, x0, q0, P0, Q, R, dt, LL)   (ekf_dense.m:1-2)
+//   [traj_max,traj_mean] = rbslam_mex('localization', model, odometry, y, x0_nonLin, Q, N_P, dt, foo, dVarft, sigma2, opts)
 //   rbslam_mex('release')
 //
 // `model` is the descriptor struct made by matlab/rbslam_model.m (family, NN, L, camera);
@@ -424,6 +425,55 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     plhs[0] = X;
     if (nlhs > 1) plhs[1] = Qn;
     if (nlhs > 2) plhs[2] = P;
+  } else if (c == "localization") {
+    // [traj_max, traj_mean] = rbslam_mex('localization', model, odometry, y, x0_nonLin, Q, N_P, dt, foo, dVarft, sigma2, opts)
+    // examples/mag-localization-mapping/particleFilterLocalization.m:1-2; foo / dVarft / sigma2 are what the
+    // reference's measModel closure captures (run_localization.m:259-270)
+    if (nrhs < 11) mexErrMsgIdAndTxt("rbslam:badArgument", "localization: 10 or 11 arguments expected");
+    const mxArray *model = prhs[1], *opts = nrhs > 11 ? prhs[11] : nullptr;
+    need_double(prhs[3], "y"); need_double(prhs[6], "N_P");
+    const int T = (int)mxGetM(prhs[3]), N = (int)mxGetScalar(prhs[6]);
+    make_context(model, opts, 1, 1, 0, 0);
+    int32_t d7[7];
+    rbslam_dims(g_ctx, d7);
+    const size_t M = d7[2];
+    need_matrix(prhs[3], "y", T, 3);
+    if (T > 1) {
+      need_double(prhs[2], "odometry");
+      if (mxGetN(prhs[2]) != 7 || (int)mxGetM(prhs[2]) < T - 1) bad("odometry must be (>= N_T-1) x 7");
+    }
+    need_double(prhs[4], "x0_nonLin");
+    if (mxGetM(prhs[4]) != 7 || (mxGetN(prhs[4]) != 1 && (int)mxGetN(prhs[4]) != N)) bad("x0_nonLin must be 7 x 1 or 7 x N_P");
+    need_double(prhs[5], "Q");
+    if (dim_of(prhs[5], 0) != 6 || dim_of(prhs[5], 1) != 6 || (dim_of(prhs[5], 2) != 1 && (int)dim_of(prhs[5], 2) < T - 1))
+      bad("Q must be 6 x 6 or 6 x 6 x (>= N_T-1)");
+    need_double(prhs[7], "dt");
+    if (mxGetNumberOfElements(prhs[7]) != 1 && (int)mxGetNumberOfElements(prhs[7]) < T - 1) bad("dt must be a scalar or have >= N_T-1 elements");
+    need_vector(prhs[8], "foo", M);
+    need_double(prhs[9], "dVarft");
+    if ((int)mxGetM(prhs[9]) < N || mxGetN(prhs[9]) != 3) bad("dVarft must have >= N_P rows and 3 columns");
+    need_double(prhs[10], "sigma2");
+    std::vector<double> var((size_t)N * 3);   // rows 1..N_P of dVarft, as the reference indexes them
+    for (int a = 0; a < 3; ++a)
+      for (int i = 0; i < N; ++i) var[i + (size_t)N * a] = mxGetDoubles(prhs[9])[i + mxGetM(prhs[9]) * a];
+    const bool compat = compat_mode(opts);
+    const mxArray *U = field(opts, "U"), *Z = field(opts, "Z");
+    if (compat) {
+      need_double(U, "opts.U"); need_double(Z, "opts.Z");
+      if (mxGetNumberOfElements(U) != (size_t)N * T || mxGetNumberOfElements(Z) != (size_t)6 * N * T) bad("opts.U must be N_P x N_T and opts.Z 6 x N_P x N_T");
+    }
+    mxArray *tm = mxCreateDoubleMatrix(7, T, mxREAL), *tmean = mxCreateDoubleMatrix(7, T, mxREAL);
+    int32_t ndiv = 0;
+    int rc = rbslam_localization_run(g_ctx, N, T, doubles_or_null(prhs[2]), (int32_t)(T > 1 ? mxGetM(prhs[2]) : 0),
+                                     mxGetDoubles(prhs[3]), mxGetDoubles(prhs[4]), (int32_t)mxGetN(prhs[4]), mxGetDoubles(prhs[5]),
+                                     (int32_t)dim_of(prhs[5], 2), mxGetDoubles(prhs[7]), (int32_t)mxGetNumberOfElements(prhs[7]),
+                                     mxGetDoubles(prhs[8]), var.data(), mxGetScalar(prhs[10]), compat ? mxGetDoubles(U) : nullptr,
+                                     compat ? mxGetDoubles(Z) : nullptr, mxGetDoubles(tm), mxGetDoubles(tmean), nullptr, nullptr,
+                                     nullptr, &ndiv);
+    if (rc) fail(g_ctx, rc);
+    if (ndiv > 0) mexPrintf("Weights filter close to zero at %d time step(s) !!!\n", ndiv);   // particleFilterLocalization.m:113-115
+    plhs[0] = tm;
+    if (nlhs > 1) plhs[1] = tmean;
   } else if (c == "release") {
     release_all();
   } else {

@@ -7,8 +7,8 @@ mirror the reference's MATLAB entry points; all compute runs in librbslam.so
 from . import basis, synth, models
 from ._capi import RbslamError, UnsupportedModelError, LIB_PATH
 from .api import (Context, particleFilter, particleSmoother, particleSmootherInformationForm,
-                  plan_migration, ekf_dense)
+                  plan_migration, ekf_dense, particleFilterLocalization)
 
 __all__ = ["basis", "synth", "models", "Context", "particleFilter", "particleSmoother",
-           "particleSmootherInformationForm", "plan_migration", "ekf_dense", "RbslamError",
+           "particleSmootherInformationForm", "plan_migration", "ekf_dense", "particleFilterLocalization", "RbslamError",
            "UnsupportedModelError", "LIB_PATH"]

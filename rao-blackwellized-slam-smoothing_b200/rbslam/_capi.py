@@ -107,6 +107,10 @@ SYMBOLS = {
     "rbslam_ekf_run": (C.c_int, [_ctx, C.c_int32, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p,
                                  c_double_p, c_double_p, C.c_int32, c_double_p, c_double_p, C.c_int32, c_double_p,
                                  c_double_p, c_double_p, c_double_p, c_double_p]),
+    "rbslam_localization_run": (C.c_int, [_ctx, C.c_int32, C.c_int32, c_double_p, C.c_int32, c_double_p, c_double_p,
+                                          C.c_int32, c_double_p, C.c_int32, c_double_p, C.c_int32, c_double_p,
+                                          c_double_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p,
+                                          c_double_p, c_int32_p, c_double_p, c_int32_p]),
     "rbslam_plan_migration": (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p,
                                         c_int32_p]),
     "rbslam_plan_shard": (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p,

@@ -470,6 +470,58 @@ def ekf_dense(model, odometry, y, x0, q0, P0, Q, R, dt, LL=None, *, device=0, ke
     return xf, qn, (Pt if keep_P else Pl)
 
 
+def particleFilterLocalization(dynModel, measModel, odometry, y, x0_nonLin, Q, R, N_P, dt, makePlots=None, *,
+                               map_mean, var_rows, sigma2, rng=None, device=0, want_xn_traj=False, taps=False):
+    """Localisation-only particle filter against a fixed map; positional signature of
+    examples/mag-localization-mapping/particleFilterLocalization.m:1-2 (``R`` is unused there too).
+    dynModel / measModel are the handles of a dense-mag model (rbslam.models.DenseMag3D); the constants
+    the reference's measModel closure captures are keyword arguments: ``map_mean`` [M] (`foo`),
+    ``var_rows`` [N_P x 3] (dVarft(i,:) per particle) and ``sigma2`` (run_localization.m:259-270).
+    rng: int seed (device Philox) or an object with U [T, N], Z [T, N, 6].
+    Returns (traj_max, traj_mean) [7 x T] (+ a dict of xn_traj / ancestors / w_hist / n_diverged with
+    want_xn_traj / taps)."""
+    model = _models.resolve(dynModel, measModel)
+    if model.family != _capi.MODEL_DENSE_MAG3D:
+        raise _capi.UnsupportedModelError(_capi.EMODEL, "particleFilterLocalization needs the dense-mag model")
+    if makePlots is not None:
+        raise _capi.RbslamError(_capi.EARG, "particleFilterLocalization: the per-step plotting hook is not forwarded")
+    y = np.asarray(y, dtype=np.float64)
+    T, N = y.shape[0], int(N_P)
+    seed = int(rng) if isinstance(rng, (int, np.integer)) else 0
+    streams = None if (rng is None or isinstance(rng, (int, np.integer))) else rng
+    F = _capi.fcol
+    with Context(model, 1, 1, device=device, seed=seed) as ctx:
+        odo, yy = F(np.atleast_2d(odometry)), F(y)
+        x0 = np.asarray(x0_nonLin, dtype=np.float64)
+        x0 = F(x0.reshape(7, -1))
+        Qc = np.asarray(Q, dtype=np.float64)
+        Qc = F(Qc[:, :, None] if Qc.ndim == 2 else Qc)
+        dtc = np.ascontiguousarray(np.asarray(dt, dtype=np.float64).reshape(-1))
+        mm = np.ascontiguousarray(np.asarray(map_mean, dtype=np.float64).reshape(-1))
+        vr = F(np.asarray(var_rows, dtype=np.float64))
+        if yy.shape[1] != 3 or x0.shape[1] not in (1, N) or mm.shape[0] != ctx.M or vr.shape != (N, 3) or Qc.shape[:2] != (6, 6):
+            raise ValueError("particleFilterLocalization: y [T x 3], x0 [7 x (1|N)], map_mean [%d], var_rows [N x 3], Q [6 x 6]" % ctx.M)
+        if T > 1 and (odo.shape[1] != 7 or odo.shape[0] < T - 1):
+            raise ValueError("odometry must be [>= T-1 x 7]")
+        U = Z = None
+        if streams is not None:
+            U = np.ascontiguousarray(np.asarray(streams.U, dtype=np.float64).reshape(T, N))
+            Z = np.ascontiguousarray(np.asarray(streams.Z, dtype=np.float64).reshape(T, N, 6))
+        tm, tmean = np.zeros((7, T), order="F"), np.zeros((7, T), order="F")
+        xt = np.zeros((7, N, T), order="F") if want_xn_traj else None
+        anc = np.zeros((N, T), dtype=np.int32, order="F") if taps else None
+        wh = np.zeros((N, T), order="F") if taps else None
+        nd = C.c_int32()
+        ctx._ck(ctx._lib.rbslam_localization_run(
+            ctx._h, N, T, _capi.dptr(odo), odo.shape[0], _capi.dptr(yy), _capi.dptr(x0), x0.shape[1], _capi.dptr(Qc),
+            Qc.shape[2], _capi.dptr(dtc), dtc.shape[0], _capi.dptr(mm), _capi.dptr(vr), float(sigma2), _capi.dptr(U),
+            _capi.dptr(Z), _capi.dptr(tm), _capi.dptr(tmean), _capi.dptr(xt), _capi.iptr(anc), _capi.dptr(wh),
+            C.byref(nd)))
+    if want_xn_traj or taps:
+        return tm, tmean, dict(xn_traj=xt, ancestors=anc, w_hist=wh, n_diverged=int(nd.value))
+    return tm, tmean
+
+
 def plan_migration(ai, old_owner, world):
     """Host-only planner (rbslam_plan_migration): returns (new_owner [N], n_migrate)."""
     ai = np.ascontiguousarray(ai, dtype=np.int32)
