@@ -376,7 +376,9 @@ static int create_impl(rbslam_ctx *ctx, const rbslam_config *cfg) {
     }
     // the packed pass keeps one more partial slot (the column-side sums)
     RB_ALLOC(ctx->d_PHp, (size_t)N * (ctx->nsplit + (ctx->pt ? 1 : 0)) * ctx->ld * 4);
-    RB_ALLOC(ctx->d_fam, (size_t)17 * N + 8);   // + counters: n_fb, n_fa, work counters [2]
+    // 7 scratch arrays over the source keys (N slabs; + N migrant keys in a sharded filter), two family
+    // lists of 5 arrays over the items, counters: n_fb, n_fa, work counters [2]
+    RB_ALLOC(ctx->d_fam, (size_t)(cfg->world > 1 ? 24 : 17) * N + 8);
     ctx->use_fam = getenv("RBSLAM_NO_FAM") == nullptr;
   }
   RB_ALLOC(ctx->d_logw, N); RB_ALLOC(ctx->d_w, N); RB_ALLOC(ctx->d_wc, N);
@@ -742,6 +744,38 @@ static int launch_large(rbslam_ctx *ctx, const KalmanArgs &a) {
   return RBSLAM_OK;
 }
 
+// where family sources live (single GPU: all local; sharded with fused migration: see SrcTab)
+static SrcTab make_src_tab(const rbslam_ctx *ctx) {
+  SrcTab t;
+  if (ctx->st_nloc > 0) {
+    const double *const *tab = ctx->d_peer_tab;
+    t.nloc = ctx->st_nloc; t.fetch = ctx->st_fetch;
+    t.P = tab + SH_P * (RB_MAXW + 1);
+    t.G4 = tab + (ctx->cg ? SH_G4B : SH_G4A) * (RB_MAXW + 1);
+    t.KS4 = tab + (ctx->cg ? SH_KS4B : SH_KS4A) * (RB_MAXW + 1);
+    t.xl = tab + (ctx->cx ? SH_XLB : SH_XLA) * (RB_MAXW + 1);
+  }
+  return t;
+}
+// carve the family-construction scratch out of d_fam: 7 arrays over the source-key space, the two
+// family lists (5 arrays over the items each), counters
+static void fam_layout(rbslam_ctx *ctx, const KalmanArgs &a, int cb, FamBuildArgs &fb, int *&la, int *&lb, int *&cnts) {
+  const int N = ctx->N;
+  const size_t NS = ctx->fam_slabs > 0 ? ctx->fam_slabs : N;
+  int *fm = ctx->d_fam;
+  fb.n_items = N; fb.n_slabs = (int)NS; fb.n_items_dev = nullptr;
+  fb.src_slot = a.src_slot; fb.dst_slot = a.dst_slot; fb.anc = a.ai;
+  fb.s_cnt = fm; fb.s_keeper = fm + NS; fb.s_cursor = fm + 2 * NS; fb.s_first = fm + 3 * NS;
+  fb.s_fid = fm + 4 * NS; fb.s_xoff = fm + 5 * NS; fb.s_xfam = fm + 6 * NS;
+  lb = fm + 7 * NS; la = lb + 5 * (size_t)N; cnts = la + 5 * (size_t)N;
+  fb.fb_src = lb; fb.fb_anc = lb + N; fb.fb_first = lb + 2 * (size_t)N; fb.fb_cnt = lb + 3 * (size_t)N;
+  fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
+  fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
+  fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
+  fb.work_ctr = cnts + 2;
+  fb.cb = cb; fb.kf = 2 * cb;
+}
+
 // streaming path: one pass per slab with the deferred downdate (kalman_stream.cuh)
 // (KC columns per stage, S stages) is a tuning knob: RBSLAM_STREAM_CFG="KC,S" (d=3 only)
 template <int D, int R2, int KC, int S>
@@ -761,19 +795,10 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
   const int grid = std::min(N * ctx->nsplit, per_sm * ctx->num_sms);
   if (ctx->use_fam) {
     // sibling fusion: families of offspring share one read of the ancestor slab
-    int *fm = ctx->d_fam;
     FamBuildArgs fb;
-    fb.n_items = N; fb.n_slabs = N; fb.n_items_dev = nullptr;
-    fb.src_slot = a.src_slot; fb.dst_slot = a.dst_slot; fb.anc = a.ai;
-    fb.s_cnt = fm; fb.s_keeper = fm + N; fb.s_cursor = fm + 2 * (size_t)N; fb.s_first = fm + 3 * (size_t)N;
-    fb.s_fid = fm + 4 * (size_t)N; fb.s_xoff = fm + 5 * (size_t)N; fb.s_xfam = fm + 6 * (size_t)N;
-    int *lb = fm + 7 * (size_t)N, *la = fm + 12 * (size_t)N, *cnts = fm + 17 * (size_t)N;
-    fb.fb_src = lb; fb.fb_anc = lb + N; fb.fb_first = lb + 2 * (size_t)N; fb.fb_cnt = lb + 3 * (size_t)N;
-    fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
-    fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
-    fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
-    fb.work_ctr = cnts + 2;
-    fb.cb = RB_CB; fb.kf = RB_KF;
+    int *la, *lb, *cnts;
+    fam_layout(ctx, a, RB_CB, fb, la, lb, cnts);
+    sa.st = make_src_tab(ctx);
     auto fkern = k_stream_fam<D, R2, KC, S, RB_CB>;
     const size_t fsmem = sizeof(double) * (size_t)S * ((size_t)KC * ld + 4 * KC * (1 + RB_CB));
     RB_OPTIN_SMEM(fkern, ctx->smem_optin - 1024);
@@ -817,6 +842,7 @@ static int launch_stream_cfg(rbslam_ctx *ctx, const KalmanArgs &a, bool resample
   }
   }
   Innov4Args ia;
+  ia.st = make_src_tab(ctx);
   ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = ctx->nsplit; ia.PHp = ctx->d_PHp; ia.H4 = a.H;
   ia.xl_old = a.xl_old; ia.anc = a.ai; ia.xl_new = a.xl_new;
   ia.G4new = ctx->d_G4[1 - ctx->cg]; ia.KS4new = ctx->d_KS4[1 - ctx->cg];
@@ -854,19 +880,10 @@ static int launch_pt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
   for (int q = 0; q <= RB_PT_MAXSPLIT; ++q) pa.psplit[q] = ctx->pt_psplit[std::min(q, ctx->nsplit)];
   pa.slab = ctx->slab; pa.P = ctx->d_P; pa.dst_slot = a.dst_slot;
   pa.G4prev = ctx->d_G4[ctx->cg]; pa.KS4prev = ctx->d_KS4[ctx->cg]; pa.H4 = a.H; pa.PHp = ctx->d_PHp;
-  int *fm = ctx->d_fam;
   FamBuildArgs fb;
-  fb.n_items = N; fb.n_slabs = N; fb.n_items_dev = nullptr;
-  fb.src_slot = a.src_slot; fb.dst_slot = a.dst_slot; fb.anc = a.ai;
-  fb.s_cnt = fm; fb.s_keeper = fm + N; fb.s_cursor = fm + 2 * (size_t)N; fb.s_first = fm + 3 * (size_t)N;
-  fb.s_fid = fm + 4 * (size_t)N; fb.s_xoff = fm + 5 * (size_t)N; fb.s_xfam = fm + 6 * (size_t)N;
-  int *lb = fm + 7 * (size_t)N, *la = fm + 12 * (size_t)N, *cnts = fm + 17 * (size_t)N;
-  fb.fb_src = lb; fb.fb_anc = lb + N; fb.fb_first = lb + 2 * (size_t)N; fb.fb_cnt = lb + 3 * (size_t)N;
-  fb.fb_child = lb + 4 * (size_t)N; fb.n_fb = cnts;
-  fb.fa_src = la; fb.fa_anc = la + N; fb.fa_first = la + 2 * (size_t)N; fb.fa_cnt = la + 3 * (size_t)N;
-  fb.fa_child = la + 4 * (size_t)N; fb.n_fa = cnts + 1;
-  fb.work_ctr = cnts + 2;
-  fb.cb = CB; fb.kf = 2 * CB;
+  int *la, *lb, *cnts;
+  fam_layout(ctx, a, CB, fb, la, lb, cnts);
+  pa.st = make_src_tab(ctx);
   auto fkern = k_stream_fam_pt<NW, MAXQ>;
   const size_t fsmem = pt_smem_bytes(ld, ctx->pt_ts, ctx->pt_ns, NW);
   RB_OPTIN_SMEM(fkern, ctx->smem_optin - 1024);
@@ -894,6 +911,7 @@ static int launch_pt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
     }
   }
   Innov4Args ia;
+  ia.st = make_src_tab(ctx);
   ia.N = N; ia.M = ctx->M; ia.ld = ld; ia.nsplit = ctx->nsplit + 1; ia.PHp = ctx->d_PHp; ia.H4 = a.H;
   ia.xl_old = a.xl_old; ia.anc = a.ai; ia.xl_new = a.xl_new;
   ia.G4new = ctx->d_G4[1 - ctx->cg]; ia.KS4new = ctx->d_KS4[1 - ctx->cg];

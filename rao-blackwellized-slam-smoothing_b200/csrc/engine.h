@@ -49,6 +49,12 @@ struct rbslam_ctx {
   int pt_nw = 15;            // consumer warps per CTA (+ the service warp = 16 warps x 128 registers)
   int pt_psplit[9] = {0};    // panel ranges of the nsplit items per family
   const int *item_group = nullptr;   // sharded engine: work group of each local item (see stream_groups)
+  // sharded engine, fused migration: source keys >= st_nloc name migrants whose ancestor state is read in
+  // place from a peer (kalman_stream.cuh, SrcTab); d_peer_tab [kind][1 + world] base pointers
+  int st_nloc = 0;
+  const int *st_fetch = nullptr;
+  const double **d_peer_tab = nullptr;
+  int fam_slabs = 0;                 // source-key space of k_build_families (0: N)
   int stream_ctas_per_sm = 0, stream_hints = 0;   // tuning knobs (env)
   size_t hs_p = 0; int hs_a = 0, hs_c = 1;   // layout of d_H: H_i(a,c) at i*hs_p + a*hs_a + c*hs_c
   double *d_logw = nullptr, *d_w = nullptr, *d_wc = nullptr;

@@ -57,6 +57,9 @@ int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled);
 int rb_normalize_phase(rbslam_ctx *ctx);
 int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host);
 int rb_flush_pending(rbslam_ctx *ctx);
+// buffers every rank of a sharded filter shares with its peers (sharded.cu)
+#define RB_MAXW 8
+enum { SH_P = 0, SH_G4A, SH_G4B, SH_KS4A, SH_KS4B, SH_XLA, SH_XLB, SH_LOGW, SH_FLAGS, SH_COUNT };
 // sharded.cu
 int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN);
 void rb_shard_free(rbslam_ctx *ctx);

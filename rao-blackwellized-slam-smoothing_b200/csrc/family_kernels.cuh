@@ -154,8 +154,8 @@ k_stream_fam(StreamArgs a, FamLists f) {
     uint64_t *bar = &full[p_q % S];
     const uint32_t bytes_p = (uint32_t)ncols * ld * 8u, bytes_v = (uint32_t)ncols * 32u;
     mbar_expect_tx(bar, bytes_p + (1 + nv) * bytes_v);
-    tma_load_1d(st, a.P + (size_t)f.src[fam] * a.slab + (size_t)c * ld, bytes_p, bar);
-    tma_load_1d(st + (size_t)KC * ld, a.G4prev + ((size_t)f.anc[fam] * ld + c) * 4, bytes_v, bar);
+    tma_load_1d(st, src_base(a.st, a.st.P, a.P, f.src[fam], a.slab) + (size_t)c * ld, bytes_p, bar);
+    tma_load_1d(st + (size_t)KC * ld, src_base(a.st, a.st.G4, a.G4prev, f.anc[fam], (size_t)ld * 4) + (size_t)c * 4, bytes_v, bar);
     for (int q = 0; q < nv; ++q) {
       const int ch = f.child[first + p_b * CB + q];
       tma_load_1d(st + (size_t)KC * ld + 4 * KC * (1 + q), a.H4 + ((size_t)ch * ld + c) * 4, bytes_v, bar);
@@ -181,12 +181,13 @@ k_stream_fam(StreamArgs a, FamLists f) {
     const int fam = it / a.nsplit, sp = it % a.nsplit;
     const int c0 = sp * a.cw, c1 = min(M, c0 + a.cw);
     const int an = f.anc[fam], cnt = f.cnt[fam], first = f.first[fam];
+    const double *KSan = src_base(a.st, a.st.KS4, a.KS4prev, an, (size_t)ld * 4);
     double2 ks[R2][D];
 #pragma unroll
     for (int k = 0; k < R2; ++k) {
       const int rp = tid + k * RB_STREAM_THREADS;
       if (rp < npairs) {
-        const double4 *kp = reinterpret_cast<const double4 *>(a.KS4prev + ((size_t)an * ld + 2 * rp) * 4);
+        const double4 *kp = reinterpret_cast<const double4 *>(KSan + (size_t)2 * rp * 4);
         const double4 k0 = kp[0], k1 = kp[1];
         const double r0[4] = {k0.x, k0.y, k0.z, k0.w}, r1[4] = {k1.x, k1.y, k1.z, k1.w};
 #pragma unroll

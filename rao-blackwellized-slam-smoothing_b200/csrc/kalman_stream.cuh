@@ -86,7 +86,25 @@ __device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gme
       : "memory");
 }
 
+// Where the SOURCE of a family lives.  Single GPU (nloc == 0) or key < nloc: slab `key` of this GPU.
+// Sharded filter, key >= nloc: migrant number key - nloc of this step -- its ancestor's state (slab,
+// pending pair, mean) stays where it is, on rank fetch[4f+1] in slab fetch[4f+2], and is read in place
+// through the peer mapping (NVLink) by the pass that needs it: no staging copy, no extra trip through
+// local HBM.  The tables hold one base pointer per rank ([0] = this GPU, [1 + r] = rank r).
+struct SrcTab {
+  int nloc = 0;
+  const int *fetch = nullptr;
+  const double *const *P = nullptr, *const *G4 = nullptr, *const *KS4 = nullptr, *const *xl = nullptr;
+};
+__device__ __forceinline__ const double *src_base(const SrcTab &t, const double *const *tab, const double *local,
+                                                  int key, size_t stride) {
+  if (t.nloc == 0 || key < t.nloc) return local + (size_t)key * stride;
+  const int f = key - t.nloc;
+  return tab[1 + t.fetch[4 * f + 1]] + (size_t)t.fetch[4 * f + 2] * stride;
+}
+
 struct StreamArgs {
+  SrcTab st;
   int hints;               // bit0: L2 evict_first on the slab loads, bit1: streaming (.cs) stores
   int gk_by_particle;      // 1: G4prev/KS4prev are indexed by the particle, not its ancestor
   int M, ld, cw, nsplit;
@@ -231,6 +249,7 @@ k_stream_pass(StreamArgs a, const int *__restrict__ list, const int *__restrict_
 
 // innovation / gain for the streaming path (layouts [row][4]); one CTA per particle
 struct Innov4Args {
+  SrcTab st;
   int N, M, ld, nsplit;
   const double *PHp;       // [N][nsplit][ld][4]
   const double *H4;        // [N][ld][4]
@@ -259,13 +278,13 @@ k_innov4(Innov4Args a) {
   __shared__ double s_L[D * D], s_SS[D * D], s_e[D];
   const int i = blockIdx.x;
   const double *Hi = a.H4 + (size_t)i * ld * 4;
-  const double *xls = a.xl_old + (size_t)(a.anc ? a.anc[i] : i) * M;
+  const double *xls = src_base(a.st, a.st.xl, a.xl_old, a.anc ? a.anc[i] : i, M);
   __shared__ double s_W[D * D];   // W(k,b) = sum_c G_anc(c,k) H(b,c)
   const double *KSa = nullptr;
   if (a.G4prev != nullptr) {
     const int an = a.anc ? a.anc[i] : i;
-    const double *Ga = a.G4prev + (size_t)an * ld * 4;
-    KSa = a.KS4prev + (size_t)an * ld * 4;
+    const double *Ga = src_base(a.st, a.st.G4, a.G4prev, an, (size_t)ld * 4);
+    KSa = src_base(a.st, a.st.KS4, a.KS4prev, an, (size_t)ld * 4);
     double wp[D * D];
 #pragma unroll
     for (int q = 0; q < D * D; ++q) wp[q] = 0.0;

@@ -131,6 +131,7 @@ k_apply_pending_pt(double *__restrict__ P, size_t slab, int ld, const int *__res
 #define RB_PT_NBUF 4                        // column-side partial tiles in flight (panels)
 
 struct PtArgs {
+  SrcTab st;
   int M, ld, nb, nsplit;
   int ts, ns;                     // tiles per stage, ring slots
   int psplit[RB_PT_MAXSPLIT + 1]; // item sp streams the panels [psplit[sp], psplit[sp+1])
@@ -215,7 +216,7 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
       d.item = it; d.b0 = b * CB; d.t0 = t_cur; d.nt = nt; d.p = p; d.j = j;
       s_desc[slot] = d;
       mbar_expect_tx(&full[slot], (uint32_t)nt * 512u);
-      tma_load_1d(ring + (size_t)slot * TS * 64, a.P + (size_t)f.src[fam] * a.slab + (size_t)t_cur * 64,
+      tma_load_1d(ring + (size_t)slot * TS * 64, src_base(a.st, a.st.P, a.P, f.src[fam], a.slab) + (size_t)t_cur * 64,
                   (uint32_t)nt * 512u, &full[slot]);
       // advance (p, j) by nt tiles
       t_cur += nt;
@@ -321,9 +322,9 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
       const int fam = d_item / a.nsplit, b0 = s_desc[slot].b0;
       const int first = f.first[fam], nv = min(CB, f.cnt[fam] - b0);
       const int ch0 = f.child[first + b0], ch1 = nv > 1 ? f.child[first + b0 + 1] : -1;
-      const double *Ga = a.G4prev + (size_t)f.anc[fam] * ld * 4;
+      const double *Ga = src_base(a.st, a.st.G4, a.G4prev, f.anc[fam], (size_t)ld * 4);
       if (d_item != s_bat.item) {   // KS fragments of the family's ancestor: registers for the whole item
-        const double *KSa = a.KS4prev + (size_t)f.anc[fam] * ld * 4;
+        const double *KSa = src_base(a.st, a.st.KS4, a.KS4prev, f.anc[fam], (size_t)ld * 4);
 #pragma unroll
         for (int qq = 0; qq < MAXQ; ++qq) {
           const int jj = wid + NW * qq;

@@ -28,6 +28,9 @@ struct PlanArgs {
   int *fetch;                             // [Nloc][4]: dst slot, source rank, source slot, 0
   int *item_group;                        // [Nloc] or nullptr: 0 = safe, 1 = deferred behind the barrier
   int *counts;                            // [8]: nA0, nB0, nA1, nB1, nFetch, nMigTotal
+  int fused;                              // 1: migrants are not fetched ahead of the pass: their source key is
+                                          // Nloc + (index in fetch[]) and they belong to the safe group, which
+                                          // runs before any exporter overwrites a slab a peer reads
 };
 
 // exclusive scan across the block of W ints per thread; totals (all threads get them)
@@ -241,8 +244,8 @@ __global__ void __launch_bounds__(1024) k_plan_shard(PlanArgs p) {
       const int f = cl_[4]++;
       p.fetch[4 * f] = j; p.fetch[4 * f + 1] = p.owner_old[a]; p.fetch[4 * f + 2] = p.lslot_old[a];
       p.fetch[4 * f + 3] = 0;
-      p.src_slot[j] = j;
-      if (p.item_group) p.item_group[j] = 1;
+      p.src_slot[j] = p.fused ? Nloc + f : j;
+      if (p.item_group) p.item_group[j] = p.fused ? 0 : 1;
       p.listB[tl[1] + cl_[3]++] = j;
     } else {
       const int grp = p.unsafe[a] ? 1 : 0, inplace = p.keeper[a] == i ? 1 : 0;

@@ -28,8 +28,6 @@
 
 using namespace rb;
 
-#define RB_MAXW 8
-enum { SH_P = 0, SH_G4A, SH_G4B, SH_KS4A, SH_KS4B, SH_XLA, SH_XLB, SH_LOGW, SH_FLAGS, SH_COUNT };
 
 struct PeerTable {
   void *p[SH_COUNT][RB_MAXW];
@@ -47,6 +45,9 @@ struct ShardWs {
   int *d_nchild = nullptr, *d_keeper = nullptr, *d_unsafe = nullptr, *d_inv = nullptr, *d_dead = nullptr, *d_expo = nullptr;
   bool host_plan = false;
   bool overlap = false;    // RBSLAM_OVERLAP=1: migrants travel while the safe work group runs (measured slower)
+  bool fused = true;       // migrants' ancestor state is read in place from the exporter by the Kalman pass
+                           // itself (no k_peer_fetch, no staging copy); RBSLAM_FUSED=0 restores fetch-then-pass
+  const double **d_tab = nullptr;   // [SH_COUNT][1 + RB_MAXW] base pointers: [0] this rank, [1 + r] rank r
   PeerTable peers{};
   bool imported[SH_COUNT][RB_MAXW] = {};
   std::vector<int> owner[2], lslot[2];
@@ -68,7 +69,7 @@ void rb_shard_free(rbslam_ctx *ctx) {
       if (s->imported[w][r]) cudaIpcCloseMemHandle(s->peers.p[w][r]);
   void *ptrs[] = {s->g_Xhist, s->g_w, s->g_wc, s->g_logw, s->traj_max, s->traj_mean, s->g_Ahist, s->iwmax,
                   s->flags, s->d_glob, s->d_fetch, s->d_own[0], s->d_own[1], s->d_lsl[0], s->d_lsl[1], s->d_nchild,
-                  s->d_keeper, s->d_unsafe, s->d_inv, s->d_dead, s->d_expo, s->d_group};
+                  s->d_keeper, s->d_unsafe, s->d_inv, s->d_dead, s->d_expo, s->d_group, (void *)s->d_tab};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete s;
   ctx->shard_ws = nullptr;
@@ -271,6 +272,9 @@ int rb_shard_create(rbslam_ctx *ctx, int world, int rank, int gN) {
   RB_ALLOC(s->d_dead, gN); RB_ALLOC(s->d_expo, gN); RB_ALLOC(s->d_group, s->Nloc);
   s->host_plan = getenv("RBSLAM_HOST_PLAN") != nullptr;
   s->overlap = getenv("RBSLAM_OVERLAP") != nullptr;
+  if (const char *e = getenv("RBSLAM_FUSED")) s->fused = atoi(e) != 0;
+  if (s->overlap || s->host_plan || !ctx->use_fam) s->fused = false;   // the fused path is the family path with the device planner
+  RB_ALLOC(s->d_tab, (size_t)SH_COUNT * (RB_MAXW + 1));
   CK(cudaMemset(s->flags, 0, 64 * sizeof(unsigned long long)));
   CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_fetch, cudaEventDisableTiming));
@@ -339,6 +343,9 @@ static int shard_group_hook(rbslam_ctx *ctx, int) {
 // phase 0: everything (one process per GPU); 1: all but the closing barrier; 2: the barrier only.
 // A single process that drives several shards (rbslam_create_group) must finish phase 1 on every
 // shard -- it allocates, frees and synchronises -- before any shard's barrier kernel starts to spin.
+// fused migration: every peer is done reading the slabs that group 1 is about to overwrite
+static int shard_barrier_hook(rbslam_ctx *ctx, int) { return peer_barrier(ctx); }
+
 int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in, int phase) {
   ShardWs *s = sh_of(ctx);
   if (phase == 2) return peer_barrier(ctx);
@@ -369,6 +376,15 @@ int rb_shard_begin(rbslam_ctx *ctx, const rbslam_inputs *in, int phase) {
   s->h_glob.assign(Nloc, 0);
   for (int j = 0; j < Nloc; ++j) s->h_glob[j] = s->rank * Nloc + j;
   CK(cudaMemcpyAsync(s->d_glob, s->h_glob.data(), sizeof(int) * Nloc, cudaMemcpyHostToDevice, ctx->stream));
+  {   // base pointers of every shared buffer: [0] this rank, [1 + r] rank r (fused migration reads through them)
+    std::vector<const double *> tab((size_t)SH_COUNT * (RB_MAXW + 1), nullptr);
+    for (int w = 0; w < SH_COUNT; ++w) {
+      tab[(size_t)w * (RB_MAXW + 1)] = static_cast<const double *>(s->peers.p[w][s->rank]);
+      for (int r = 0; r < s->world; ++r) tab[(size_t)w * (RB_MAXW + 1) + 1 + r] = static_cast<const double *>(s->peers.p[w][r]);
+    }
+    if ((rc = rb_h2d(ctx, s->d_tab, tab.data(), sizeof(double *) * tab.size()))) return rc;
+    ctx->d_peer_tab = s->d_tab;
+  }
   s->migrated = 0;
   ctx->running = true;
   ctx->t = 0;
@@ -409,6 +425,7 @@ int rb_shard_step(rbslam_ctx *ctx) {
       pa.dead_list = s->d_dead; pa.expo_list = s->d_expo;
       pa.src_slot = ctx->d_src_slot; pa.glob = s->d_glob; pa.listA = ctx->d_listA; pa.listB = ctx->d_listB;
       pa.fetch = s->d_fetch; pa.counts = ctx->d_counts; pa.item_group = s->d_group;
+      pa.fused = s->fused ? 1 : 0;
       CK(launch_plan_shard(pa, ctx->stream));
       ctx->launches += 1;
       s->cur = nw;
@@ -501,6 +518,11 @@ int rb_shard_step(rbslam_ctx *ctx) {
     // migrants travel on a second stream while the families that touch no exported slab
     // (work group 0) are processed; group 1 waits for the landing + the peer barrier
     cudaStream_t fs = s->overlap ? ctx->stream2 : ctx->stream;
+    if (s->fused) {
+      // nothing travels ahead of the pass: the Kalman pass reads each migrant's ancestor slab, pending pair
+      // and mean in place from the exporter (SrcTab).  Group 0 = families no peer reads + the migrants;
+      // peer barrier; group 1 = families that overwrite a slab a peer had to read first.
+    } else {
     if (s->overlap) {
       CK(cudaEventRecord(ctx->ev_plan, ctx->stream));
       CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_plan, 0));
@@ -510,7 +532,8 @@ int rb_shard_step(rbslam_ctx *ctx) {
         ctx->d_G4[ctx->cg], ctx->d_KS4[ctx->cg], ctx->d_xl[ctx->cx]);
     ctx->launches += 1;
     if (s->overlap) CK(cudaEventRecord(ctx->ev_fetch, ctx->stream2));
-    else if ((rc = peer_barrier(ctx))) return rc;   // default: land everything, then one pass over all families
+    else if ((rc = peer_barrier(ctx))) return rc;   // land everything, then one pass over all families
+    }
   } else {
     k_plan_identity<<<(Nloc + 255) / 256, 256, 0, ctx->stream>>>(Nloc, ctx->d_slot[ctx->cs], ctx->d_src_slot,
                                                                 ctx->d_listB, ctx->d_counts);
@@ -526,12 +549,17 @@ int rb_shard_step(rbslam_ctx *ctx) {
   rb_phase_begin(ctx, RB_PH_KALMAN);
   ctx->anc_override = ctx->d_src_slot;     // thin arrays are slot-indexed: ancestor index = source slot
   ctx->stream_groups = resampled ? 2 : 1;
-  ctx->group_hook = s->overlap ? shard_group_hook : nullptr;
-  ctx->item_group = s->overlap ? s->d_group : nullptr;
+  const bool fused_step = s->fused && resampled;
+  ctx->group_hook = fused_step ? shard_barrier_hook : (s->overlap ? shard_group_hook : nullptr);
+  ctx->item_group = (fused_step || s->overlap) ? s->d_group : nullptr;
+  ctx->st_nloc = fused_step ? Nloc : 0;    // source keys >= Nloc: migrants, read in place from their exporter
+  ctx->st_fetch = s->d_fetch;
+  ctx->fam_slabs = fused_step ? 2 * Nloc : 0;
   rc = rb_kalman_phase(ctx, ctx->d_y + (size_t)t * d, resampled);
   ctx->anc_override = nullptr;
   ctx->group_hook = nullptr;
   ctx->item_group = nullptr;
+  ctx->st_nloc = 0; ctx->fam_slabs = 0;
   ctx->stream_groups = 1;
   ctx->group_off[0][0] = ctx->group_off[0][1] = 0;
   rb_phase_end(ctx);

@@ -26,12 +26,13 @@ def _problem(rb, m, T):
     return rb.synth.dense_mag_problem(N_T=T, m=m, seed=3, m_sim=300)
 
 
-def _worker(rank, world, port, N, m, T, seed, q, overlap=False, variant=2):
+def _worker(rank, world, port, N, m, T, seed, q, overlap=False, variant=2, fused=True):
     import sys
     if overlap:   # read by the library when the sharded context is created
         os.environ["RBSLAM_OVERLAP"] = "1"
     else:
         os.environ.pop("RBSLAM_OVERLAP", None)
+    os.environ["RBSLAM_FUSED"] = "1" if fused else "0"   # 0: fetch the migrants ahead of the pass (k_peer_fetch)
     for p in (ROOT, PKG):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -62,12 +63,15 @@ def _worker(rank, world, port, N, m, T, seed, q, overlap=False, variant=2):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,N,m,T,overlap,variant", [
-    (2, 32, 64, 12, False, 2), (2, 64, 253, 8, False, 2), (4, 64, 64, 8, False, 2),
-    (2, 32, 64, 12, True, 2), (2, 64, 253, 8, True, 2), (4, 64, 64, 8, True, 2),
-    (2, 32, 64, 12, False, 7), (2, 64, 253, 8, False, 7),        # packed symmetric slabs
+@pytest.mark.parametrize("world,N,m,T,overlap,variant,fused", [
+    # fused migration (default): migrants are read in place from their exporter by the Kalman pass
+    (2, 32, 64, 12, False, 2, True), (2, 64, 253, 8, False, 2, True), (4, 64, 64, 8, False, 2, True),
+    (2, 32, 64, 12, False, 7, True), (2, 64, 253, 8, False, 7, True), (4, 64, 64, 8, False, 7, True),
+    # fetch-then-pass (RBSLAM_FUSED=0) and its overlapped variant
+    (2, 32, 64, 12, False, 2, False), (4, 64, 64, 8, False, 2, False), (2, 64, 253, 8, False, 7, False),
+    (2, 32, 64, 12, True, 2, False), (2, 64, 253, 8, True, 2, False), (4, 64, 64, 8, True, 2, False),
 ])
-def test_sharded_filter_matches_single_gpu_and_oracle(rbslam_lib, world, N, m, T, overlap, variant):
+def test_sharded_filter_matches_single_gpu_and_oracle(rbslam_lib, world, N, m, T, overlap, variant, fused):
     rb = rbslam_lib
     import torch.multiprocessing as mp
     import oracle
@@ -75,7 +79,7 @@ def test_sharded_filter_matches_single_gpu_and_oracle(rbslam_lib, world, N, m, T
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = _free_port()
-    procs = [ctxm.Process(target=_worker, args=(r, world, port, N, m, T, seed, q, overlap, variant)) for r in range(world)]
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, N, m, T, seed, q, overlap, variant, fused)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
