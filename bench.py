@@ -165,9 +165,12 @@ def cpu_baseline(pr, m, n_particles, n_steps):
     secs, cores = filter_steps_timed(om, pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"],
                                      pr["P0_lin"], pr["Q"], pr["R"], n_particles, pr["dt"], st,
                                      n_steps=n_steps, warmup=1)
-    return {"value": n_particles * n_steps / secs, "unit": UNIT, "cores": cores, "kind": "port",
+    med = float(np.median(filter_steps_timed.last_step_secs))
+    return {"value": n_particles / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "mean_value": n_particles * n_steps / secs,
             "sample": "N=%d particles x %d steps at M=%d (oracle NumPy/OpenBLAS port of "
-                      "src/particleFilter.m, thread per particle chunk, 1 BLAS thread each)"
+                      "src/particleFilter.m, thread per particle chunk, 1 BLAS thread each); value = particles / "
+                      "median step time (robust against host hiccups), mean_value = particles x steps / total time"
                       % (n_particles, n_steps, m + 3)}
 
 
@@ -185,10 +188,12 @@ def run_reference(args):
     secs, cores = filter_steps_timed(om, pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"],
                                      pr["P0_lin"], pr["Q"], pr["R"], Np, pr["dt"], st,
                                      n_steps=K, warmup=max(W, 1))
-    val = Np * K / secs
+    med = float(np.median(filter_steps_timed.last_step_secs))
+    val = Np / med          # particles per MEDIAN step time: the arm shares a noisy host (3.4x run-to-run spread in round 1)
+    secs = med * K
     sample = ("each step = %d particles of the C4 workload (M=%d); oracle NumPy/OpenBLAS port of "
-              "src/particleFilter.m on %d host threads; MATLAB/Octave are not installed"
-              % (Np, args.basis + 3, cores))
+              "src/particleFilter.m on %d host threads; value = particles / median step time over the K timed "
+              "steps; MATLAB/Octave are not installed" % (Np, args.basis + 3, cores))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -219,6 +224,34 @@ def fp64_peak():
         return float(json.load(open(p))["fp64_dmma_m8n8k4_tflops"]), "measured (profiles/fp64_peaks_r1.json, tools/fp64_peak.cu)"
     except Exception:
         return 37.0, "fallback"
+
+
+def smoother_block_multi(rbslam, world):
+    """C5 (BASELINE.json configs[4]: information-form smoother, N = 4096, M = 515, T = 5000, "on 8xB200") on
+    all GPUs of the job: rank 0 drives a replica group over devices 0..world-1 (rbslam_create_replicas: the
+    ancestor weights of each step are evaluated block-wise on the devices and all-gathered over peer memory).
+    T-slice as in smoother_block, extrapolated to T = 5000."""
+    Ts, N5 = 24, 4096
+    pr = rbslam.synth.dense_mag_problem(N_T=Ts, m=512, seed=1, n_laps=3, m_sim=2000)
+    gm = rbslam.models.from_problem(pr)
+    a = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
+    with rbslam.Context(gm, N5, Ts, rng_mode=1, seed=1, information_form=True, replicas=True,
+                        devices=list(range(world))) as ctx:
+        ctx.smoother_run(*a, pr["dt"], 2, 1)          # warm-up
+        t0 = time.perf_counter()
+        ctx.smoother_run(*a, pr["dt"], 1, 1)
+        t_filter = time.perf_counter() - t0
+        ctx.phase_timing(True)
+        t0 = time.perf_counter()
+        ctx.smoother_run(*a, pr["dt"], 2, 1)
+        t_two = time.perf_counter() - t0
+        ph = ctx.phase_times()
+    ms_step = 1e3 * (t_two - t_filter) / Ts
+    return {"c5_ms_per_step": ms_step, "c5_s_per_sweep": ms_step * 5000 / 1e3, "n_gpus": world,
+            "c5_ancestor_ms_per_step": ph["ancestor"] / (Ts - 1),
+            "c5": "information form, N=4096, M=515: sweep 2 of an N_K=2 run on a T=%d slice, extrapolated to T=5000; "
+                  "%d GPUs as one replica group (every GPU runs the filter part, the ancestor weights are split "
+                  "%d ways and all-gathered over peer memory)" % (Ts, world, world)}
 
 
 def smoother_block(rbslam, device):
@@ -352,12 +385,16 @@ def run_cuda(args):
             for _ in range(4):
                 ctx.filter_step()
             ctx.sync()
-            barrier()
-            cA = ctx.counters()
-            t0 = time.perf_counter()
-            ctx.filter_run(*fargs, pr["dt"], want_xn_traj=False)
-            e2e_s = time.perf_counter() - t0
-            cB = ctx.counters()
+            e2e_s = None
+            for _rep in range(2):        # best of two calls: a host-side hiccup must not decide the headline
+                barrier()
+                cA = ctx.counters()
+                t0 = time.perf_counter()
+                ctx.filter_run(*fargs, pr["dt"], want_xn_traj=False)
+                dt_run = time.perf_counter() - t0
+                cB = ctx.counters()
+                dt_run = reduce_max([dt_run])[0]
+                e2e_s = dt_run if e2e_s is None else min(e2e_s, dt_run)
             res["h2d"] = (cB["h2d_bytes"] - cA["h2d_bytes"]) / T
             res["d2h"] = (cB["d2h_bytes"] - cA["d2h_bytes"]) / T
         ctx.close()
@@ -412,7 +449,7 @@ def run_cuda(args):
             "e2e": {"value": gN * T / r["e2e_s"], "unit": UNIT,
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "what": "rbslam_filter_run from host buffers: upload, init of %d slabs, %d steps, "
-                            "final extraction, download" % (n_loc, T)},
+                            "final extraction, download; best of 2 calls" % (n_loc, T)},
             "gpu_launches": r["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None,
@@ -437,6 +474,11 @@ def run_cuda(args):
                                                    for k, v in weak["phases"].items() if v > 0}}
         if world == 1 and not args.no_smoother:
             line["smoother"] = smoother_block(rbslam, local_rank)
+        elif world > 1 and not args.no_smoother:
+            try:
+                line["smoother"] = smoother_block_multi(rbslam, world)
+            except Exception as e:      # the filter line must survive a smoother problem
+                line["smoother"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(pr, m, args.cpu_sample_particles,
                                                 args.cpu_sample_steps)

@@ -58,11 +58,13 @@ def filter_steps_timed(model, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P,
 
     ctxm = threadpool_limits(limits=1) if threadpool_limits else None
     t0 = None
+    step_secs = []
     try:
         with ThreadPoolExecutor(max_workers=cores) as pool:
             for t in range(N_T):
+                ts = time.perf_counter()
                 if t == warmup:
-                    t0 = time.perf_counter()
+                    t0 = ts
                 if t != 0:
                     ai = sample_many(w, streams.U[0, t, :N_P])
                     xn_ = xn.copy()
@@ -76,8 +78,11 @@ def filter_steps_timed(model, odometry, y, x0_nonLin, x0_lin, P0_lin, Q, R, N_P,
                 list(pool.map(lambda c: weights(c, dy, yt), chunks))
                 w = normalise(logw)
                 list(pool.map(lambda c: update(c, dy, yt), chunks))
+                if t >= warmup:
+                    step_secs.append(time.perf_counter() - ts)
         secs = time.perf_counter() - t0
     finally:
         if ctxm is not None:
             ctxm.__exit__(None, None, None)
+    filter_steps_timed.last_step_secs = step_secs   # per-step wall times of the timed steps (for a robust rate)
     return secs, cores
