@@ -99,6 +99,20 @@ __device__ __forceinline__ void cluster_scan_vec(int (&v)[W], int (&tot)[W], int
   cl.sync();   // s_blk / s_all are reused by the next scan
 }
 
+// Work group of a local offspring i of the local ancestor a (0 = safe: runs while peers may still read this
+// rank's slabs; 1 = deferred behind the peer barrier).  Fetch-then-pass mode defers the whole family of an
+// ancestor that is exported or has a copy landing in a slab a peer reads (one family = one group, copies
+// before the in-place update).  Fused mode defers per item: only what WRITES a slab a peer reads -- the
+// in-place offspring of such an ancestor, and a copy whose destination is such a slab; the other copies
+// stay in the safe group (the family splits, its safe part simply runs first).
+__device__ __forceinline__ int plan_group(const PlanArgs &p, int i, int a, int inplace) {
+  const int u = p.unsafe[a];
+  if (!p.fused) return u ? 1 : 0;
+  if (inplace) return u ? 1 : 0;
+  const int old = p.inv[p.lslot_new[i]];
+  return (old != a && old >= 0 && p.n_child[old] > 0) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(1024) k_plan_shard(PlanArgs p) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster();
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(1024) k_plan_shard(PlanArgs p) {
       int r2 = 0;
       while (r2 + 1 < W && k >= s_defp[r2 + 1]) ++r2;
       p.owner_new[i] = r2;
-      p.unsafe[p.ai[i]] = 1;          // the ancestor's slab is exported
+      atomicOr(&p.unsafe[p.ai[i]], 1);   // bit 0: the ancestor's slab is exported (a peer reads it)
       ++k;
     }
     if (tid == 0) p.counts[5] = t1[0];
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(1024) k_plan_shard(PlanArgs p) {
     const int a = p.ai[i];
     if (p.owner_old[a] != me || p.keeper[a] == i) continue;
     const int old = p.inv[p.lslot_new[i]];
-    if (old != a && old >= 0 && p.n_child[old] > 0) p.unsafe[a] = 1;
+    if (old != a && old >= 0 && p.n_child[old] > 0) atomicOr(&p.unsafe[a], 2);   // bit 1: a copy lands in a slab a peer reads
   }
   cl.sync();
   // ---- 5. this rank's lists, in particle order
@@ -231,7 +245,8 @@ __global__ void __launch_bounds__(1024) k_plan_shard(PlanArgs p) {
     if (p.owner_new[i] != me) continue;
     const int a = p.ai[i];
     if (p.owner_old[a] != me) { ++cl_[3]; ++cl_[4]; continue; }
-    const int grp = p.unsafe[a] ? 1 : 0, inplace = p.keeper[a] == i ? 1 : 0;
+    const int inplace = p.keeper[a] == i ? 1 : 0;
+    const int grp = plan_group(p, i, a, inplace);
 #pragma unroll
     for (int q = 0; q < 4; ++q) cl_[q] += (q == 2 * grp + inplace);
   }
@@ -248,7 +263,8 @@ __global__ void __launch_bounds__(1024) k_plan_shard(PlanArgs p) {
       if (p.item_group) p.item_group[j] = p.fused ? 0 : 1;
       p.listB[tl[1] + cl_[3]++] = j;
     } else {
-      const int grp = p.unsafe[a] ? 1 : 0, inplace = p.keeper[a] == i ? 1 : 0;
+      const int inplace = p.keeper[a] == i ? 1 : 0;
+      const int grp = plan_group(p, i, a, inplace);
       p.src_slot[j] = p.lslot_old[a];
       if (p.item_group) p.item_group[j] = grp;
       const int q = 2 * grp + inplace;

@@ -63,14 +63,35 @@ def test_quaternion_identities():
 
 
 # ---------------------------------------------------------------- eigenbasis
-def test_domain_cartesian_dx_matches_package_and_is_sorted():
-    LL = np.array([[-3.0, -2.0, -1.0], [5.0, 2.5, 1.0]])
-    L, NN = tools.domain_cartesian_dx(100, 3, LL)
-    L2, NN2 = basis.domain_cartesian_dx(100, 3, LL)
-    assert np.array_equal(NN, NN2) and np.allclose(L, L2)
-    lam = tools.eigenval(NN, L)
-    assert np.all(np.diff(lam) >= 0)
-    assert len({tuple(r) for r in NN.astype(int)}) == 100
+def _basis_by_definition(m, LL):
+    """The index selection of tools/domain_cartesian_dx.m:26-43 straight from its definition, written
+    independently of both restatements: all index tuples of the grid, eigenvalues
+    sum((pi n_j / (2 L_j))^2), stable ascending sort, first m."""
+    import itertools
+    L = (LL[1] - LL[0]) / 2.0
+    d = L.shape[0]
+    grid = np.ceil(m ** (1.0 / d) * L / L.min()).astype(int)                  # :33
+    # ndgridm enumerates (1,1),(1,2),...,(1,N2),(2,1),...: the LAST index runs fastest (:186-188, 207-214)
+    tuples = list(itertools.product(*[range(1, g + 1) for g in grid]))
+    lam = [sum((np.pi * n / (2.0 * Lj)) ** 2 for n, Lj in zip(t, L)) for t in tuples]
+    order = sorted(range(len(tuples)), key=lambda k: lam[k])                  # Python's sort is stable, like MATLAB's
+    return L, np.array([tuples[k] for k in order[:m]])
+
+
+def test_domain_cartesian_dx_against_its_definition():
+    """Both restatements of the index selection (oracle/tools.py and the product's rbslam/basis.py) against
+    an independent enumeration from the definition, incl. the stable order among equal eigenvalues
+    (a square domain makes (a,b) / (b,a) ties)."""
+    for m, LL in [(100, np.array([[-3.0, -2.0, -1.0], [5.0, 2.5, 1.0]])),
+                  (60, np.array([[-2.0, -2.0], [2.0, 2.0]])),                 # ties: L_1 == L_2
+                  (200, np.array([[-12.02, -12.02, -2.4], [12.02, 12.02, 2.4]]))]:
+        d = LL.shape[1]
+        Lr, NNr = _basis_by_definition(m, LL)
+        for impl in (tools.domain_cartesian_dx, basis.domain_cartesian_dx):
+            L, NN = impl(m, d, LL)
+            assert np.allclose(L, Lr) and np.array_equal(np.asarray(NN, dtype=int), NNr), impl.__module__
+        lam = tools.eigenval(NNr.astype(float), Lr)
+        assert np.all(np.diff(lam) >= 0) and len({tuple(r) for r in NNr}) == m
     # C1/C4 claims of SURVEY 8a row A12: max index (18,18,3) for m=512 and (22,22,4) for m=1024
     pr_LL = np.array([[-12.02, -12.02, -2.4], [12.02, 12.02, 2.4]])
     assert tuple(basis.domain_cartesian_dx(512, 3, pr_LL)[1].max(0)) == (18, 18, 3)
@@ -286,3 +307,61 @@ def test_philox_streams_are_uniform_and_normal():
     assert abs(Z.mean()) < 0.01 and abs(Z.std() - 1) < 0.01
     U2, Z2 = oracle.philox_uniforms_normals(42, 0, 3, 100, 6)
     assert np.array_equal(U[:100], U2) and np.array_equal(Z[:100], Z2)   # counter-based: N-invariant
+
+
+# ---------------------------------------------------------------- the (f) rows: EKF baseline, localisation filter
+def test_ekf_map_block_equals_single_particle_rbpf_when_the_pose_is_known():
+    """Two independent restatements against each other: with a perfectly known pose (zero pose covariance,
+    zero process noise) the EKF of ekf_dense.m:67-102 never moves its pose states, so its map block must be
+    the Rao-Blackwellized filter's map update (src/particleFilter.m:184-198) of ONE particle that follows the
+    same dead-reckoned poses."""
+    from oracle.ekf import ekf_dense
+    T, m = 12, 30
+    pr = synth.dense_mag_problem(N_T=T, m=m, seed=4, m_sim=100)
+    M = m + 3
+    L = pr["L"]
+    x0 = np.concatenate([pr["x0_nonLin"][:3], np.zeros(3), pr["x0_lin"].reshape(-1)])
+    P0 = np.zeros((M + 6, M + 6))
+    P0[6:, 6:] = pr["P0_lin"]
+    Q0 = np.zeros((6, 6))
+    xf, qn, Pf = ekf_dense(pr["NN"], L, np.vstack([-L, L]), pr["odometry"], pr["y"], x0, pr["x0_nonLin"][3:7], P0, Q0,
+                           pr["R"], pr["dt"])
+    om = oracle.DenseMag3D(pr["NN"], L)
+    st = oracle.Streams(np.zeros((1, T, 1)), np.zeros((1, T, 1, 6)))
+    Qeps = 1e-300 * np.eye(6)          # chol(dt*Q) must exist; the noise it scales is zero anyway
+    out = oracle.particleFilter(om, pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], Qeps, pr["R"],
+                                1, pr["dt"], st)
+    traj_max, xl_max, P_max = out[0], out[2], out[4]
+    assert_close_norm(xf[:3], traj_max[:3], 1e-12, "EKF pose == dead-reckoned pose")
+    assert_close_norm(qn, traj_max[3:7], 1e-12, "linearisation point == dead-reckoned orientation")
+    assert_close_norm(xf[6:, -1], xl_max, 1e-9, "map mean")
+    assert_close_norm(Pf[6:, 6:], P_max, 1e-9, "map covariance")
+    assert np.max(np.abs(Pf[:6, :])) == 0.0
+
+
+def test_localization_oracle_pieces():
+    """run_localization.m:241-280 restated: qRight(q)*p = p (x) q, the weight of one particle from the
+    normal densities written out, and weights that prefer the particle sitting on the true pose."""
+    from oracle.localization import qRight, dynModel_loc, measModel_loc
+    rng = np.random.default_rng(2)
+    q, p = rng.standard_normal(4), rng.standard_normal(4)
+    assert_close_norm(qRight(q) @ p, tools.qLeft(p) @ q, 1e-14, "qRight")
+    Q = np.diag([1e-2, 2e-2, 3e-2, 1e-4, 2e-4, 3e-4])
+    xn = np.concatenate([rng.standard_normal(3), q / np.linalg.norm(q)])
+    dx = np.concatenate([0.1 * rng.standard_normal(3), p / np.linalg.norm(p)])
+    z = rng.standard_normal(6)
+    out = dynModel_loc(xn, dx, 0.5, Q, z)
+    assert_close_norm(out[:3], xn[:3] + dx[:3] + np.sqrt(0.5 * np.diag(Q)[:3]) * z[:3], 1e-14, "position")
+    assert_close_norm(out[3:], tools.qLeft(tools.qLeft(dx[3:]) @ xn[3:]) @ tools.expq(np.sqrt(0.5 * np.diag(Q)[3:]) * z[3:]),
+                      1e-14, "orientation")
+    pr = synth.dense_mag_problem(N_T=4, m=40, seed=6, m_sim=100)
+    foo = rng.standard_normal(43)
+    om = oracle.DenseMag3D(pr["NN"], pr["L"])
+    x_true = pr["x0_nonLin"]
+    y = om.measModel(x_true[:, None])[0] @ foo
+    xs = np.stack([x_true, x_true + np.array([1.5, -1.0, 0.2, 0, 0, 0, 0])], axis=1)
+    dVar = np.full((2, 3), 0.3)
+    w = measModel_loc(y, xs, pr["NN"], pr["L"], foo, dVar, 0.1)
+    sd = np.sqrt(0.4)
+    assert abs(w[0] - 3.0 / (sd * np.sqrt(2 * np.pi))) < 1e-12       # zero residual: three density peaks added up
+    assert w[0] > w[1] > 0
