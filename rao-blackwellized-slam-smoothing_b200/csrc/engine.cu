@@ -500,7 +500,7 @@ extern "C" void rbslam_destroy(rbslam_ctx *ctx) {
                   ctx->d_counts, ctx->d_H, ctx->d_yhat, ctx->d_PHpart, ctx->d_G, ctx->d_KS,
                   ctx->d_G4[0], ctx->d_G4[1], ctx->d_KS4[0], ctx->d_KS4[1], ctx->d_PHp, ctx->d_fam,
                   ctx->d_logw, ctx->d_w, ctx->d_wc, ctx->d_Xhist, ctx->d_Ahist, ctx->d_traj_max,
-                  ctx->d_traj_mean, ctx->d_iwmax, ctx->d_status, ctx->d_scratch, ctx->d_yhattraj, ctx->d_chol_fail};
+                  ctx->d_traj_mean, ctx->d_iwmax, ctx->d_status, ctx->d_scratch, ctx->d_yhattraj, ctx->d_chol_fail, ctx->d_normws};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (auto e : ctx->ph_events) cudaEventDestroy(e);
   for (auto &e : ctx->user_events) if (e) cudaEventDestroy(e);
@@ -1077,16 +1077,39 @@ int rb_meas_phase(rbslam_ctx *ctx, bool resampled) {
   return RBSLAM_OK;
 }
 
-int rb_normalize_phase(rbslam_ctx *ctx) {
-  const int N = ctx->N, t = ctx->t, n = ctx->n, tb = t % ctx->T_hist;
-  k_normalize<<<1, 1024, 0, ctx->stream>>>(
-      N, n, ctx->d_logw, ctx->d_w, ctx->d_Xhist + (size_t)tb * N * n, ctx->d_traj_max + (size_t)t * n,
-      ctx->d_traj_mean + (size_t)t * n, ctx->d_iwmax + t,
-      ctx->d_logw_hist ? ctx->d_logw_hist + (size_t)t * N : nullptr,
-      ctx->d_w_hist ? ctx->d_w_hist + (size_t)t * N : nullptr);
-  ctx->launches += 1;
+// w = exp(logw - lse), first arg-max, traj_max / traj_mean: one CTA with a fixed tree up to 32 767 weights,
+// fixed chunks of 4096 (one CTA each, combined in chunk order) above -- both deterministic for a given N
+int rb_normalize(rbslam_ctx *ctx, int N, int n, const double *logw, double *w, const double *xn, double *traj_max_t,
+                 double *traj_mean_t, int *iw_max, double *logw_hist_t, double *w_hist_t) {
+  const int nchunk = (N + RB_NCHUNK - 1) / RB_NCHUNK;
+  if (N < 32768 || nchunk > RB_NCHUNK_MAX || n > 8) {
+    k_normalize<<<1, 1024, 0, ctx->stream>>>(N, n, logw, w, xn, traj_max_t, traj_mean_t, iw_max, logw_hist_t, w_hist_t);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return RBSLAM_OK;
+  }
+  if (!ctx->d_normws) {
+    RB_ALLOC(ctx->d_normws, (size_t)RB_NCHUNK_MAX * 12);
+  }
+  NormWs ws;
+  ws.pmax = ctx->d_normws; ws.psum = ws.pmax + RB_NCHUNK_MAX; ws.pbest = ws.psum + RB_NCHUNK_MAX;
+  ws.pmean = ws.pbest + RB_NCHUNK_MAX;
+  ws.pidx = reinterpret_cast<int *>(ws.pmean + (size_t)RB_NCHUNK_MAX * 8);
+  k_norm_max<<<nchunk, 1024, 0, ctx->stream>>>(N, logw, ws);
+  k_norm_sum<<<nchunk, 1024, 0, ctx->stream>>>(N, logw, ws);
+  k_norm_write<<<nchunk, 1024, 0, ctx->stream>>>(N, n, logw, w, xn, ws, logw_hist_t, w_hist_t);
+  k_norm_final<<<1, 32, 0, ctx->stream>>>(N, n, nchunk, xn, ws, traj_max_t, traj_mean_t, iw_max);
+  ctx->launches += 4;
   CK(cudaGetLastError());
   return RBSLAM_OK;
+}
+
+int rb_normalize_phase(rbslam_ctx *ctx) {
+  const int N = ctx->N, t = ctx->t, n = ctx->n, tb = t % ctx->T_hist;
+  return rb_normalize(ctx, N, n, ctx->d_logw, ctx->d_w, ctx->d_Xhist + (size_t)tb * N * n, ctx->d_traj_max + (size_t)t * n,
+                      ctx->d_traj_mean + (size_t)t * n, ctx->d_iwmax + t,
+                      ctx->d_logw_hist ? ctx->d_logw_hist + (size_t)t * N : nullptr,
+                      ctx->d_w_hist ? ctx->d_w_hist + (size_t)t * N : nullptr);
 }
 
 static int filter_step_impl(rbslam_ctx *ctx) {

@@ -102,6 +102,7 @@ struct rbslam_ctx {
   cudaEvent_t user_events[16] = {nullptr};
 
   void *smoother_ws = nullptr;   // SmootherWs (smoother.cu)
+  double *d_normws = nullptr;    // partials of the chunked normalisation (large N)
   int *d_chol_fail = nullptr;    // [chol_fail_cap] not-PD flags of the batched panel Cholesky
   int chol_fail_cap = 0;
   void *shard_ws = nullptr;      // ShardWs (sharded.cu); N is the LOCAL particle count when set

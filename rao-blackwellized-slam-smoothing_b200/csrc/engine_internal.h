@@ -55,6 +55,8 @@ int rb_propagate_phase(rbslam_ctx *ctx, int n_prop);
 int rb_meas_phase(rbslam_ctx *ctx, bool resampled);
 int rb_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, bool resampled);
 int rb_normalize_phase(rbslam_ctx *ctx);
+int rb_normalize(rbslam_ctx *ctx, int N, int n, const double *logw, double *w, const double *xn, double *traj_max_t,
+                 double *traj_mean_t, int *iw_max, double *logw_hist_t, double *w_hist_t);
 int rb_read_slabs(rbslam_ctx *ctx, const double *slabs, double *host);
 int rb_flush_pending(rbslam_ctx *ctx);
 // buffers every rank of a sharded filter shares with its peers (sharded.cu)

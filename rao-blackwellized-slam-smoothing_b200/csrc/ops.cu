@@ -55,9 +55,7 @@ extern "C" int rbslam_op_normalize(rbslam_ctx *ctx, int32_t N, const double *log
   TMP_ALLOC(d_i, int, 1);
   int rc;
   if ((rc = rb_h2d(ctx, d_lw, logw, sizeof(double) * N))) return rc;
-  k_normalize<<<1, 1024, 0, ctx->stream>>>(N, 0, d_lw, d_w, nullptr, nullptr, nullptr, d_i, nullptr, nullptr);
-  ctx->launches += 1;
-  CK(cudaGetLastError());
+  if ((rc = rb_normalize(ctx, N, 0, d_lw, d_w, nullptr, nullptr, nullptr, d_i, nullptr, nullptr))) return rc;
   if ((rc = rb_d2h(ctx, w, d_w, sizeof(double) * N))) return rc;
   if (iw_max && (rc = rb_d2h(ctx, iw_max, d_i, sizeof(int)))) return rc;
   return RBSLAM_OK;

@@ -568,9 +568,9 @@ int rb_shard_step(rbslam_ctx *ctx) {
   k_logw_scatter<<<(Nloc + 127) / 128, 128, 0, ctx->stream>>>(Nloc, s->world, s->d_glob, ctx->d_logw, s->peers);
   ctx->launches += 1;
   if ((rc = peer_barrier(ctx))) return rc;
-  k_normalize<<<1, 1024, 0, ctx->stream>>>(gN, n, s->g_logw, s->g_w, xn_t, s->traj_max + (size_t)t * n,
-                                           s->traj_mean + (size_t)t * n, s->iwmax + t, nullptr, nullptr);
-  ctx->launches += 1;
+  if ((rc = rb_normalize(ctx, gN, n, s->g_logw, s->g_w, xn_t, s->traj_max + (size_t)t * n, s->traj_mean + (size_t)t * n,
+                         s->iwmax + t, nullptr, nullptr)))
+    return rc;
   rb_phase_end(ctx);
   CK(cudaGetLastError());
   ctx->t += 1;

@@ -452,6 +452,127 @@ k_normalize(int N, int n, const double *__restrict__ logw, double *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------
+// K4 for large populations (sharded filter, N in the tens of thousands): the same normalisation in
+// fixed chunks of RB_NCHUNK weights, one CTA per chunk, partial results combined in chunk order --
+// deterministic for a given N on every GPU (all ranks of a sharded filter normalise the same replicated
+// log-weights and must agree bit for bit), but no longer one CTA walking 80 000 weights three times.
+//   pass 1: chunk maxima;  pass 2: c = max, chunk sums of exp(logw - c);
+//   pass 3: lse = c + log(sum), w = exp(logw - lse), chunk arg-max (first index) and chunk sums xn.*w;
+//   final : arg-max over the chunks (first index on ties), traj_max, traj_mean.
+// ---------------------------------------------------------------------------
+#define RB_NCHUNK 4096
+#define RB_NCHUNK_MAX 256
+struct NormWs {
+  double *pmax, *psum, *pbest, *pmean;   // [nchunk], [nchunk], [nchunk], [nchunk][8]
+  int *pidx;                             // [nchunk]
+};
+__device__ __forceinline__ double block_reduce_1024(double v, bool is_max, double *s_red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double x = lane < (int)(blockDim.x >> 5) ? s_red[lane] : (is_max ? -INFINITY : 0.0);
+    x = is_max ? warp_max(x) : warp_sum(x);
+    if (lane == 0) s_red[32] = x;
+  }
+  __syncthreads();
+  return s_red[32];
+}
+__global__ void __launch_bounds__(1024) k_norm_max(int N, const double *__restrict__ logw, NormWs ws) {
+  __shared__ double s_red[33];
+  const int c0 = blockIdx.x * RB_NCHUNK, c1 = min(N, c0 + RB_NCHUNK);
+  double m = -INFINITY;
+  for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) m = fmax(m, logw[i]);
+  m = block_reduce_1024(m, true, s_red);
+  if (threadIdx.x == 0) ws.pmax[blockIdx.x] = m;
+}
+__global__ void __launch_bounds__(1024) k_norm_sum(int N, const double *__restrict__ logw, NormWs ws) {
+  __shared__ double s_red[33];
+  double c = -INFINITY;
+  for (int q = 0; q < (int)gridDim.x; ++q) c = fmax(c, ws.pmax[q]);
+  const int c0 = blockIdx.x * RB_NCHUNK, c1 = min(N, c0 + RB_NCHUNK);
+  double s = 0.0;
+  for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) s += exp(logw[i] - c);
+  s = block_reduce_1024(s, false, s_red);
+  if (threadIdx.x == 0) ws.psum[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(1024)
+k_norm_write(int N, int n, const double *__restrict__ logw, double *__restrict__ w, const double *__restrict__ xn,
+             NormWs ws, double *__restrict__ logw_hist_t, double *__restrict__ w_hist_t) {
+  __shared__ double s_red[33];
+  __shared__ double s_b[32];
+  __shared__ int s_i[32];
+  double c = -INFINITY, tot = 0.0;
+  for (int q = 0; q < (int)gridDim.x; ++q) c = fmax(c, ws.pmax[q]);
+  for (int q = 0; q < (int)gridDim.x; ++q) tot += ws.psum[q];
+  const double lse = c + log(tot);
+  const int c0 = blockIdx.x * RB_NCHUNK, c1 = min(N, c0 + RB_NCHUNK);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double best = -1.0;
+  int bidx = 0x7fffffff;
+  for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+    const double wi = exp(logw[i] - lse);
+    w[i] = wi;
+    if (logw_hist_t) logw_hist_t[i] = logw[i];
+    if (w_hist_t) w_hist_t[i] = wi;
+    if (wi > best) { best = wi; bidx = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+  }
+  if (lane == 0) { s_b[wid] = best; s_i[wid] = bidx; }
+  __syncthreads();
+  if (wid == 0) {
+    best = lane < nwarp ? s_b[lane] : -1.0;
+    bidx = lane < nwarp ? s_i[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { ws.pbest[blockIdx.x] = best; ws.pidx[blockIdx.x] = bidx; }
+  }
+  if (xn != nullptr) {   // chunk contribution to traj_mean = sum(xn .* w, 2)
+    for (int j = 0; j < n; ++j) {
+      double acc = 0.0;
+      for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) acc += xn[j + (size_t)i * n] * w[i];
+      acc = block_reduce_1024(acc, false, s_red);
+      if (threadIdx.x == 0) ws.pmean[(size_t)blockIdx.x * 8 + j] = acc;
+    }
+  }
+}
+__global__ void k_norm_final(int N, int n, int nchunk, const double *__restrict__ xn, NormWs ws,
+                             double *__restrict__ traj_max_t, double *__restrict__ traj_mean_t,
+                             int *__restrict__ iw_max_out) {
+  __shared__ int s_imax;
+  if (threadIdx.x == 0) {
+    double best = -1.0;
+    int bidx = 0x7fffffff;
+    for (int q = 0; q < nchunk; ++q)
+      if (ws.pbest[q] > best || (ws.pbest[q] == best && ws.pidx[q] < bidx)) { best = ws.pbest[q]; bidx = ws.pidx[q]; }
+    if (bidx < 0 || bidx >= N) bidx = 0;     // all-NaN weights: MATLAB's max returns index 1
+    s_imax = bidx;
+    if (iw_max_out) *iw_max_out = bidx;
+  }
+  __syncthreads();
+  if (xn == nullptr) return;
+  if ((int)threadIdx.x < n) {
+    if (traj_max_t) traj_max_t[threadIdx.x] = xn[threadIdx.x + (size_t)s_imax * n];
+    if (traj_mean_t) {
+      double acc = 0.0;
+      for (int q = 0; q < nchunk; ++q) acc += ws.pmean[(size_t)q * 8 + threadIdx.x];
+      traj_mean_t[threadIdx.x] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K2b  JacobianPhi3D (tools/JacobianPhi3D.m:29-64): Hessian of every basis function at
 // every point, J [3 x 3 x m x N].  Same separable structure as K2: per point and axis one
 // sin and one cos per distinct index (<= 3*RB_MAXTAB sincos calls instead of 6*m trig).

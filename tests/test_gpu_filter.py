@@ -77,7 +77,8 @@ def test_filter_teacher_forced(rbslam_lib, fam, N, kw):
 
 
 @pytest.mark.parametrize("fam,N,kw", [("radio", 100, {}), ("mag", 24, {"m": 64, "T": 24}),
-                                      ("sparse", 40, {"T": 60})])
+                                      ("sparse", 40, {"T": 60}),
+                                      ("mag", 33000, {"m": 5, "T": 3})])      # chunked normalisation, split scan / search
 def test_filter_free_running_injected(rbslam_lib, fam, N, kw):
     """Same injected uniforms/normals, device draws its own ancestors: bit-exact indices."""
     rb = rbslam_lib

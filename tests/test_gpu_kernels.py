@@ -56,7 +56,7 @@ def test_resample_frequencies(rbslam_lib):
     assert np.max(np.abs(freq - w)) < 5e-3
 
 
-@pytest.mark.parametrize("N", [1, 33, 5000])
+@pytest.mark.parametrize("N", [1, 33, 5000, 32768, 50001])   # >= 32768: the chunked multi-CTA form
 def test_normalize(rbslam_lib, N):
     rb = rbslam_lib
     pr, om, gm = _problem(rb, "radio")
