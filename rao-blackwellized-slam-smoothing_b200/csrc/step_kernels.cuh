@@ -24,7 +24,7 @@ k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__r
   // draws for particles i0 .. i0+n_draws-1 (uniform U[i] / Philox counter i, result ai[i]).
   // The scan runs chunk by chunk through shared memory: all threads stage a chunk, ONE thread
   // adds it up left to right (the rounding order is the contract), all threads write it back.
-  extern __shared__ double s_buf[];
+  extern __shared__ __align__(16) double s_buf[];
   __shared__ double s_carry;
   unsigned dyn;
   asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
@@ -35,14 +35,29 @@ k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__r
     for (int j = threadIdx.x; j < cn; j += blockDim.x) s_buf[j] = w[c0 + j];
     __syncthreads();
     if (threadIdx.x == 0) {
+      // the DADD chain is the critical path: the 16 addends of the NEXT block are loaded (as
+      // double2) while the chain of this block runs, results leave as double2 stores
       double acc = s_carry;
       int j = 0;
-      for (; j + 4 <= cn; j += 4) {
-        const double a0 = s_buf[j], a1 = s_buf[j + 1], a2 = s_buf[j + 2], a3 = s_buf[j + 3];
-        acc += a0; s_buf[j] = acc;
-        acc += a1; s_buf[j + 1] = acc;
-        acc += a2; s_buf[j + 2] = acc;
-        acc += a3; s_buf[j + 3] = acc;
+      double2 nx[8];
+      if (cn >= 16) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) nx[q] = reinterpret_cast<const double2 *>(s_buf)[q];
+      }
+      for (; j + 16 <= cn; j += 16) {
+        double2 cur[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cur[q] = nx[q];
+        if (j + 32 <= cn) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) nx[q] = reinterpret_cast<const double2 *>(s_buf + j + 16)[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          acc += cur[q].x; cur[q].x = acc;
+          acc += cur[q].y; cur[q].y = acc;
+          reinterpret_cast<double2 *>(s_buf + j)[q] = cur[q];
+        }
       }
       for (; j < cn; ++j) { acc += s_buf[j]; s_buf[j] = acc; }
       s_carry = acc;
