@@ -355,6 +355,242 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// k_chol_inv: the same left-looking factorisation with the two serial phases of k_chol_solve taken
+// off the per-matrix critical path (ncu source page of k_chol_solve, profiles/tuning_r2.md section 3:
+// 31 % of a CTA's time in the tensor-core loop, 35 % in the per-row forward substitution of the
+// panel, 20 % with three warps waiting for the one that factors the diagonal block in shared memory):
+//   * the C tile of a row tile never goes to global memory: accumulators -> shared memory in the
+//     A-operand layout of the next product;
+//   * the 32 x 32 diagonal block is factored by one warp IN REGISTERS (lane = row, right-looking,
+//     the column broadcast by shuffles: the same FMA sequence per element as the left-looking
+//     form), and inverted (lane = column of L11^-1, L11 read by broadcast from shared memory);
+//   * the panel solve L21 = C21 L11^-T is one more tensor-core product C21 * (L11^-1)' per row
+//     tile (K = 32), instead of 496 dependent FMAs per row;
+//   * the addends A1 / A2 of a tile are loaded before the operand loop and consumed after it.
+// A narrower last panel is padded with an identity block.  Same arguments and results as
+// k_chol_solve (which stays as the retry kernel of the across-the-batch path and as
+// RBSLAM_CHOL_KERNEL=solve).
+// ---------------------------------------------------------------------------
+// lane = row r of a 32 x 32 block (x[c], c <= r used).  Returns false if a pivot is not positive.
+// On return x = row r of L and invd = 1 / L(r, r).
+__device__ __forceinline__ bool warp_chol32_reg(double (&x)[32], double &invd, int lane) {
+  bool ok = true;
+  invd = 1.0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double dj = __shfl_sync(0xffffffffu, x[j], j);
+    if (!(dj > 0.0)) { ok = false; break; }
+    const double ljj = sqrt(dj);
+    x[j] = (lane == j) ? ljj : x[j] / ljj;
+    if (lane == j) invd = 1.0 / ljj;
+#pragma unroll
+    for (int k = j + 1; k < 32; ++k) {
+      const double lkj = __shfl_sync(0xffffffffu, x[j], k);   // L(k, j)
+      x[k] = fma(-x[j], lkj, x[k]);
+    }
+  }
+  return ok;
+}
+
+#define RB_CI_TR 64
+#define RB_CI_LDA (RB_CI_TR + 8)
+static inline size_t chol_inv_smem() {
+  return sizeof(double) * (2 * 32 * RB_CI_LDA + 2 * 32 * RB_CH_LDB + 32 * RB_CH_LDB + 32);
+}
+
+__global__ void __launch_bounds__(128, 3) k_chol_inv(CholArgs a) {
+  constexpr int TR = RB_CI_TR, LDA_T = RB_CI_LDA, NT = 128;
+  extern __shared__ __align__(16) double sm[];
+  double *As = sm;                           // [2][32][LDA_T] operand ring; buffer 0 doubles as the C tile
+  double *Bs = As + 2 * 32 * LDA_T;          // [2][32][RB_CH_LDB]; buffer 1 doubles as L11 (stride 33)
+  double *sX = Bs + 2 * 32 * RB_CH_LDB;      // [32][RB_CH_LDB]: L11^-1 as a B operand, X(j, c) at c*LDB + j
+  double *sInv = sX + 32 * RB_CH_LDB;        // [32] 1 / L11(k, k)
+  double *sD = Bs + 32 * RB_CH_LDB;
+  __shared__ int s_fail;
+  __shared__ double s_red[2][4];
+  const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double *A1 = a.A1 + (size_t)(a.slot1 ? a.slot1[b] : b) * a.strideA1;
+  double *L = a.L + (size_t)b * a.strideL;
+  const int ldl = a.ldl;
+  const int nr = n + 1;                      // rows incl. the right-hand-side row
+  const int gq = lane >> 2, tg = lane & 3;
+  const int wr = warp * 16;                  // warp tile: 16 rows x 32 columns = 2 x 4 DMMA tiles
+  bool ok = false;
+  for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
+    const double jit = attempt ? a.jitter : 0.0;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    for (int jb = 0; jb < n; jb += RB_CH_NB) {
+      const int nb = min(RB_CH_NB, n - jb);
+      for (int ti = jb; ti < nr; ti += TR) {
+        // addends of this tile: in flight during the operand loop
+        double c1[2][4][2], c2[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int gr = min(ti + wr + 8 * mi + gq, n - 1), gc = min(jb + 8 * nj + 2 * tg + e, n - 1);
+              c1[mi][nj][e] = A1[gr + (size_t)gc * a.lda1];
+              c2[mi][nj][e] = a.A2 ? a.A2[gr + (size_t)gc * a.lda2] : 0.0;
+            }
+        double acc[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+        __syncthreads();                         // ring + C tile + sX readers of the previous tile are done
+        if (jb > 0) {
+          stage_rows_k32<TR, LDA_T, NT>(As, L, ldl, ti, nr, tid);
+          stage_rows_k32<32, RB_CH_LDB, NT>(Bs, L, ldl, jb, n, tid);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          int buf = 0;
+          for (int k0 = 0; k0 < jb; k0 += 32, buf ^= 1) {
+            if (k0 + 32 < jb) {                  // next step's operands fly while this one is multiplied
+              stage_rows_k32<TR, LDA_T, NT>(As + (buf ^ 1) * 32 * LDA_T, L + (size_t)(k0 + 32) * ldl, ldl, ti, nr, tid);
+              stage_rows_k32<32, RB_CH_LDB, NT>(Bs + (buf ^ 1) * 32 * RB_CH_LDB, L + (size_t)(k0 + 32) * ldl, ldl, jb, n, tid);
+              asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;" ::: "memory");
+            } else {
+              asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            const double *Ab = As + buf * 32 * LDA_T, *Bb = Bs + buf * 32 * RB_CH_LDB;
+#pragma unroll
+            for (int kk = 0; kk < 32; kk += 4) {
+              double av[2], bv[4];
+#pragma unroll
+              for (int mi = 0; mi < 2; ++mi) av[mi] = Ab[(kk + tg) * LDA_T + wr + 8 * mi + gq];
+#pragma unroll
+              for (int nj = 0; nj < 4; ++nj) bv[nj] = Bb[(kk + tg) * RB_CH_LDB + 8 * nj + gq];
+#pragma unroll
+              for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], av[mi], bv[nj]);
+            }
+            __syncthreads();                     // buffer `buf` may be refilled two steps from now
+          }
+        }
+        // C = A1 + A2 [+ jitter I] - L L' (row n: the right-hand side), into shared memory as an A operand
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int lr = wr + 8 * mi + gq, lc = 8 * nj + 2 * tg + e;
+              const int gr = ti + lr, gc = jb + lc;
+              double v = c1[mi][nj][e] + c2[mi][nj][e] + (gr == gc ? jit : 0.0);
+              if (gr == n && gc < n) v = a.rhs[(size_t)b * a.stride_rhs + gc] + (a.rhs2 ? a.rhs2[gc] : 0.0);
+              v -= acc[mi][nj][e];
+              As[lc * LDA_T + lr] = (gc < n && gr >= gc && gr <= n) ? v : 0.0;
+            }
+        __syncthreads();
+        if (ti == jb) {
+          // diagonal block: rows 0..31 of this tile
+          if (warp == 0) {
+            double x[32], invd;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const double v = As[c * LDA_T + lane];
+              x[c] = (lane < nb) ? v : (c == lane ? 1.0 : 0.0);   // identity padding of a narrow last panel
+            }
+            const bool okw = warp_chol32_reg(x, invd, lane);
+            if (!okw) {
+              if (lane == 0) s_fail = 1;
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                sD[lane * 33 + c] = (c <= lane) ? x[c] : 0.0;
+                if (c <= lane && lane < nb) L[(jb + lane) + (size_t)(jb + c) * ldl] = x[c];
+              }
+              sInv[lane] = invd;
+              __syncwarp();
+              // column `lane` of X = L11^-1 (column-oriented forward substitution: the updates of one
+              // step are independent, the chain is 32 x (multiply + FMA))
+              double y[32];
+#pragma unroll
+              for (int r = 0; r < 32; ++r) y[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                y[k] *= sInv[k];
+#pragma unroll
+                for (int r = k + 1; r < 32; ++r) y[r] = fma(-sD[r * 33 + k], y[k], y[r]);
+              }
+#pragma unroll
+              for (int r = 0; r < 32; ++r) sX[lane * RB_CH_LDB + r] = y[r];
+            }
+          }
+          __syncthreads();
+          if (s_fail) break;
+        }
+        // L21 = C21 X' on the tensor cores; rows of the diagonal block itself are skipped at the store
+        double out[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj) out[mi][nj][0] = out[mi][nj][1] = 0.0;
+        if (ti + wr + 16 > jb + nb) {            // warp-uniform: this warp owns rows below the diagonal block
+#pragma unroll
+          for (int kk = 0; kk < 32; kk += 4) {
+            double av[2], bv[4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) av[mi] = As[(kk + tg) * LDA_T + wr + 8 * mi + gq];
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj) bv[nj] = sX[(kk + tg) * RB_CH_LDB + 8 * nj + gq];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+              for (int nj = 0; nj < 4; ++nj) dmma884(out[mi][nj][0], out[mi][nj][1], av[mi], bv[nj]);
+          }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int gr = ti + wr + 8 * mi + gq, gc = jb + 8 * nj + 2 * tg + e;
+                if (gr >= jb + nb && gr < nr && gc < n) L[gr + (size_t)gc * ldl] = out[mi][nj][e];
+              }
+        }
+      }
+      __syncthreads();
+      if (s_fail) break;
+    }
+    __syncthreads();
+    ok = !s_fail;
+    if (!ok && attempt == 0) {
+      if (a.jitter < 0.0) break;
+      if (tid == 0) atomicAdd(&a.status->used_jitter, 1);
+    }
+    __syncthreads();
+  }
+  if (!ok) {
+    if (tid == 0 && atomicCAS(&a.status->not_pd, 0, 1) == 0) {
+      a.status->not_pd_step = a.t;
+      a.status->not_pd_particle = b;
+    }
+    if (tid == 0) { a.sum_log_diag[b] = nan(""); a.vtv[b] = nan(""); }
+    return;
+  }
+  double ld = 0.0, vv = 0.0;
+  for (int r = tid; r < n; r += blockDim.x) {
+    ld += log(L[r + (size_t)r * ldl]);
+    const double v = L[n + (size_t)r * ldl];    // v = L \ rhs
+    vv = fma(v, v, vv);
+  }
+  ld = warp_sum(ld); vv = warp_sum(vv);
+  if (lane == 0) { s_red[0][warp] = ld; s_red[1][warp] = vv; }
+  __syncthreads();
+  if (tid == 0) {
+    double l2 = 0.0, v2 = 0.0;
+    for (int q = 0; q < 4; ++q) { l2 += s_red[0][q]; v2 += s_red[1][q]; }
+    a.sum_log_diag[b] = l2;
+    a.vtv[b] = v2;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Batched Cholesky, panel by panel ACROSS the batch (large batches: C5, N = 4096).
 // One CTA per matrix (k_chol_solve) keeps 3-4 matrices per SM in flight and is bound by the latency of
 // its own serial chain (operand loads, one warp on the diagonal block, barriers; ncu: issue slots 17 %

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstring>
 #include <thread>
 #include "engine_internal.h"
 #include "step_kernels.cuh"
@@ -602,8 +603,10 @@ static int launch_gemm(rbslam_ctx *ctx, bool ta, const GemmArgs &g, int batch) {
 static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
   static int nt = 0, panel_min = 0;
   if (!nt) {
-    nt = 128;
-    if (const char *e = getenv("RBSLAM_CHOL_THREADS")) nt = atoi(e) == 256 ? 256 : 128;
+    nt = 64;   // 64: k_chol_inv (default); 128 / 256: k_chol_solve with that many threads (RBSLAM_CHOL_KERNEL=solve)
+    if (const char *e = getenv("RBSLAM_CHOL_KERNEL"))
+      if (!strcmp(e, "solve")) nt = 128;
+    if (const char *e = getenv("RBSLAM_CHOL_THREADS")) nt = atoi(e) == 256 ? 256 : (atoi(e) == 128 ? 128 : nt);
     // batches at least this large go panel by panel across the batch.  Measured at C5 (N = 4096, M = 515):
     // 21.6 ms per step against 19.8 ms for one CTA per matrix (profiles/tuning_r2.md), so the path is
     // opt-in (RBSLAM_CHOL_PANEL_MIN=<batch size>) until its two kernels are tuned
@@ -612,6 +615,7 @@ static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
   }
   RB_OPTIN_SMEM(k_chol_solve<128>, chol_solve_smem(128));
   RB_OPTIN_SMEM(k_chol_solve<256>, chol_solve_smem(256));
+  RB_OPTIN_SMEM(k_chol_inv, chol_inv_smem());
   if (batch >= panel_min && c.n > RB_CP_NB) {
     // panel by panel across the batch (dense_kernels.cuh): thousands of independent tensor-core tiles
     // per launch instead of 3-4 latency-bound matrices per SM
@@ -644,6 +648,7 @@ static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
     return RBSLAM_OK;
   }
   if (nt == 256) k_chol_solve<256><<<batch, 256, chol_solve_smem(256), ctx->stream>>>(c);
+  else if (nt == 64) k_chol_inv<<<batch, 128, chol_inv_smem(), ctx->stream>>>(c);
   else k_chol_solve<128><<<batch, 128, chol_solve_smem(128), ctx->stream>>>(c);
   ctx->launches += 1;
   CK(cudaGetLastError());

@@ -35,25 +35,26 @@ k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__r
     for (int j = threadIdx.x; j < cn; j += blockDim.x) s_buf[j] = w[c0 + j];
     __syncthreads();
     if (threadIdx.x == 0) {
-      // the DADD chain is the critical path: the 16 addends of the NEXT block are loaded (as
-      // double2) while the chain of this block runs, results leave as double2 stores
+      // the DADD chain is the critical path: the 8 addends of the NEXT block are loaded (as double2)
+      // while the chain of this block runs, results leave as double2 stores.  (64 registers per
+      // thread at 1024 threads: blocks of 8, not more.)
       double acc = s_carry;
       int j = 0;
-      double2 nx[8];
-      if (cn >= 16) {
+      double2 nx[4];
+      if (cn >= 8) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) nx[q] = reinterpret_cast<const double2 *>(s_buf)[q];
+        for (int q = 0; q < 4; ++q) nx[q] = reinterpret_cast<const double2 *>(s_buf)[q];
       }
-      for (; j + 16 <= cn; j += 16) {
-        double2 cur[8];
+      for (; j + 8 <= cn; j += 8) {
+        double2 cur[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) cur[q] = nx[q];
-        if (j + 32 <= cn) {
+        for (int q = 0; q < 4; ++q) cur[q] = nx[q];
+        if (j + 16 <= cn) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) nx[q] = reinterpret_cast<const double2 *>(s_buf + j + 16)[q];
+          for (int q = 0; q < 4; ++q) nx[q] = reinterpret_cast<const double2 *>(s_buf + j + 8)[q];
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           acc += cur[q].x; cur[q].x = acc;
           acc += cur[q].y; cur[q].y = acc;
           reinterpret_cast<double2 *>(s_buf + j)[q] = cur[q];

@@ -119,3 +119,20 @@ def test_packed_is_filter_only_and_auto_mode(rbslam_lib):
     ref = oracle.particleFilter(om, *_args(pr), 8, pr["dt"], st)
     for a, b in zip(outs, ref):
         assert_close_norm(a, b, 1e-7)
+
+
+def test_packed_filter_is_bit_reproducible(rbslam_lib):
+    """The column-side tiles of the packed kernel travel from 15 consumer warps to the reducer lanes
+    through mbarrier-ordered shared-memory buffers and are added in fixed warp order: three runs on
+    the same inputs must agree in every bit (a stale or early read of a hand-off buffer would not),
+    with many more work items than SMs so that the schedule differs from run to run."""
+    rb = rbslam_lib
+    N, T = 600, 5
+    pr, om, gm = _setup(rb, "mag", N, m=253, T=T)
+    runs = []
+    for _ in range(3):
+        with rb.Context(gm, N, T, rng_mode=1, seed=11, kalman_variant=PT) as ctx:
+            runs.append(ctx.filter_run(*_args(pr), pr["dt"]))
+    for o in runs[1:]:
+        for k in ("traj_max", "traj_mean", "xl_max", "xl_mean", "P_max", "P_mean"):
+            assert np.array_equal(o[k], runs[0][k]), k

@@ -3,6 +3,7 @@
 # fetch-then-pass migration, the C5 smoother slice on all GPUs
 mkdir -p gpurun_out
 tag=c14
+export RBSLAM_CHOL_KERNEL=solve   # the verified K7 kernel: this call is about scaling
 nvidia-smi -L | wc -l
 run() { # name nproc env...
   name=$1; np=$2; shift 2
