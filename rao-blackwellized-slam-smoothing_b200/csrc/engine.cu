@@ -1026,7 +1026,7 @@ int rb_resample_phase(rbslam_ctx *ctx, int n_draws) {
   const int *forced = ctx->have_forced ? ctx->d_forced + soff : nullptr;
   size_t smem = sizeof(double) * (size_t)N;
   smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
-  if (N > 16384 && n_draws > 1024) {   // large populations: scan in one CTA, draws over the grid
+  if (N >= 4096 && n_draws > 1024) {   // scan in one CTA, draws over the grid (N = 10^4: 0.06 ms against 0.17 ms in one CTA)
     k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, -1, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
     k_resample_search<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(N, 0, n_draws, ctx->d_wc, rs, forced, ai, ctx->d_status);
     ctx->launches += 2;

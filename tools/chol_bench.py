@@ -21,6 +21,6 @@ with rbslam.Context(gm, N, Ts, rng_mode=1, seed=1, information_form=True) as ctx
 M = gm.M
 anc = ph["ancestor"] / (Ts - 1)
 fl = N * (M ** 3 / 3.0 + 4.0 * M * M)
-print(json.dumps({"N": N, "M": M, "threads": os.environ.get("RBSLAM_CHOL_THREADS", "128"), "ancestor_ms_per_step": anc,
+print(json.dumps({"N": N, "M": M, "kernel": os.environ.get("RBSLAM_CHOL_KERNEL", "inv"), "threads": os.environ.get("RBSLAM_CHOL_THREADS", "128"), "ancestor_ms_per_step": anc,
                   "tflops": fl / anc / 1e9, "frac_of_37.09": fl / anc / 1e9 / 37.09, "wall_s": wall,
                   "phases_ms": {k: round(v, 2) for k, v in ph.items() if v > 0}}))
