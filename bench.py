@@ -226,6 +226,23 @@ def fp64_peak():
         return 37.0, "fallback"
 
 
+def _c5_sweep_ms(ctx, a, dt, Ts):
+    """ms per time step of ONE sweep with ancestor weights (k > 0): wall time of an N_K = 3 call minus an N_K = 1
+    call, over two sweeps (the fixed costs of a call -- upload, first sweep, extraction -- cancel; a difference over
+    one sweep of a 24-step slice was within the noise of those costs).  Then the phase times of an N_K = 2 call."""
+    ctx.smoother_run(*a, dt, 2, 1)          # warm-up: every kernel of both kinds of sweep
+    t = {}
+    for nk in (1, 3):
+        t0 = time.perf_counter()
+        ctx.smoother_run(*a, dt, nk, 1)
+        t[nk] = time.perf_counter() - t0
+    ctx.phase_timing(True)
+    ctx.smoother_run(*a, dt, 2, 1)
+    ph = ctx.phase_times()
+    ctx.phase_timing(False)
+    return 1e3 * (t[3] - t[1]) / (2 * Ts), ph
+
+
 def smoother_block_multi(rbslam, world):
     """C5 (BASELINE.json configs[4]: information-form smoother, N = 4096, M = 515, T = 5000, "on 8xB200") on
     all GPUs of the job: rank 0 drives a replica group over devices 0..world-1 (rbslam_create_replicas: the
@@ -237,19 +254,10 @@ def smoother_block_multi(rbslam, world):
     a = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
     with rbslam.Context(gm, N5, Ts, rng_mode=1, seed=1, information_form=True, replicas=True,
                         devices=list(range(world))) as ctx:
-        ctx.smoother_run(*a, pr["dt"], 2, 1)          # warm-up
-        t0 = time.perf_counter()
-        ctx.smoother_run(*a, pr["dt"], 1, 1)
-        t_filter = time.perf_counter() - t0
-        ctx.phase_timing(True)
-        t0 = time.perf_counter()
-        ctx.smoother_run(*a, pr["dt"], 2, 1)
-        t_two = time.perf_counter() - t0
-        ph = ctx.phase_times()
-    ms_step = 1e3 * (t_two - t_filter) / Ts
+        ms_step, ph = _c5_sweep_ms(ctx, a, pr["dt"], Ts)
     return {"c5_ms_per_step": ms_step, "c5_s_per_sweep": ms_step * 5000 / 1e3, "n_gpus": world,
             "c5_ancestor_ms_per_step": ph["ancestor"] / (Ts - 1),
-            "c5": "information form, N=4096, M=515: sweep 2 of an N_K=2 run on a T=%d slice, extrapolated to T=5000; "
+            "c5": "information form, N=4096, M=515: one sweep with ancestor weights (N_K=3 call minus N_K=1 call, over 2) on a T=%d slice, extrapolated to T=5000; "
                   "%d GPUs as one replica group (every GPU runs the filter part, the ancestor weights are split "
                   "%d ways and all-gathered over peer memory)" % (Ts, world, world)}
 
@@ -277,27 +285,18 @@ def smoother_block(rbslam, device):
     gm = rbslam.models.from_problem(pr)
     a = (pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"])
     with rbslam.Context(gm, N5, Ts, device=device, rng_mode=1, seed=1, information_form=True) as ctx:
-        ctx.smoother_run(*a, pr["dt"], 1, 1)
-        t0 = time.perf_counter()
-        ctx.smoother_run(*a, pr["dt"], 1, 1)
-        t_filter = time.perf_counter() - t0
-        ctx.phase_timing(True)
-        t0 = time.perf_counter()
-        ctx.smoother_run(*a, pr["dt"], 2, 1)
-        t_two = time.perf_counter() - t0
-        ph = ctx.phase_times()
+        ms_step, ph = _c5_sweep_ms(ctx, a, pr["dt"], Ts)
     M = gm.M
-    ms_step = 1e3 * (t_two - t_filter) / Ts          # a sweep with ancestor weights
     anc_ms = ph["ancestor"] / (Ts - 1)
     flops = N5 * (M ** 3 / 3.0 + 4.0 * M * M)         # chol + solve + quadratic form
     peak, src = fp64_peak()
     out.update({
         "c5_ms_per_step": ms_step, "c5_s_per_sweep": ms_step * 5000 / 1e3,
-        "c5": "information form, N=4096, M=515: sweep 2 of an N_K=2 run on a T=%d slice, extrapolated to T=5000; one GPU" % Ts,
+        "c5": "information form, N=4096, M=515: one sweep with ancestor weights (N_K=3 call minus N_K=1 call, over 2) on a T=%d slice, extrapolated to T=5000; one GPU" % Ts,
         "c5_ancestor_ms_per_step": anc_ms,
         "fp64_tflops": flops / (anc_ms / 1e3) / 1e12, "fp64_peak_tflops": peak, "fp64_peak_source": src,
         "fp64_frac": flops / (anc_ms / 1e3) / 1e12 / peak,
-        "fp64_kernel": "k_chol_solve (K7: batched 515 x 515 Cholesky + solve), M^3/3 + 4 M^2 flop per particle-step"})
+        "fp64_kernel": "k_chol_inv (K7: batched 515 x 515 Cholesky + solve), M^3/3 + 4 M^2 flop per particle-step"})
     return out
 
 

@@ -5,6 +5,7 @@
 // SIMT fp64 (B200's fp64 FMA pipes); one CTA per output tile / per matrix.
 #pragma once
 #include "common.cuh"
+#include "kalman_stream.cuh"   // mbarrier + cp.async.bulk helpers
 
 namespace rb {
 
@@ -361,51 +362,50 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
 // panel, 20 % with three warps waiting for the one that factors the diagonal block in shared memory):
 //   * the C tile of a row tile never goes to global memory: accumulators -> shared memory in the
 //     A-operand layout of the next product;
-//   * the 32 x 32 diagonal block is factored by one warp IN REGISTERS (lane = row, right-looking,
-//     the column broadcast by shuffles: the same FMA sequence per element as the left-looking
-//     form), and inverted (lane = column of L11^-1, L11 read by broadcast from shared memory);
+//   * the 32 x 32 diagonal block is factored AND inverted by all four warps together, right-looking,
+//     one block barrier per column (a single warp in registers took 53 k cycles per block: 28 % of
+//     the kernel with three warps waiting, ncu source page of the first version);
 //   * the panel solve L21 = C21 L11^-T is one more tensor-core product C21 * (L11^-1)' per row
 //     tile (K = 32), instead of 496 dependent FMAs per row;
-//   * the addends A1 / A2 of a tile are loaded before the operand loop and consumed after it.
+//   * the addend tile of A1 is prefetched towards L2 before the operand loop and read after it;
+//   * operand ring of NS stages of KC columns, ONE block barrier per stage.
 // A narrower last panel is padded with an identity block.  Same arguments and results as
 // k_chol_solve (which stays as the retry kernel of the across-the-batch path and as
 // RBSLAM_CHOL_KERNEL=solve).
 // ---------------------------------------------------------------------------
-// lane = row r of a 32 x 32 block (x[c], c <= r used).  Returns false if a pivot is not positive.
-// On return x = row r of L and invd = 1 / L(r, r).
-__device__ __forceinline__ bool warp_chol32_reg(double (&x)[32], double &invd, int lane) {
-  bool ok = true;
-  invd = 1.0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const double dj = __shfl_sync(0xffffffffu, x[j], j);
-    if (!(dj > 0.0)) { ok = false; break; }
-    const double ljj = sqrt(dj);
-    x[j] = (lane == j) ? ljj : x[j] / ljj;
-    if (lane == j) invd = 1.0 / ljj;
-#pragma unroll
-    for (int k = j + 1; k < 32; ++k) {
-      const double lkj = __shfl_sync(0xffffffffu, x[j], k);   // L(k, j)
-      x[k] = fma(-x[j], lkj, x[k]);
-    }
-  }
-  return ok;
-}
-
 #define RB_CI_TR 64
 #define RB_CI_LDA (RB_CI_TR + 8)
-static inline size_t chol_inv_smem() {
-  return sizeof(double) * (2 * 32 * RB_CI_LDA + 2 * 32 * RB_CH_LDB + 32 * RB_CH_LDB + 32);
+// KC = columns of L per operand stage, NS = stages in the cp.async ring
+static inline size_t chol_inv_smem(int kc, int ns) {
+  return sizeof(double) * ((size_t)ns * kc * (RB_CI_LDA + RB_CH_LDB) + 32 * RB_CH_LDB);
+}
+// rows [row0, row0+ROWS) x KC columns of a column-major matrix into a [KC][LD] tile; rows >= nrows are zero
+template <int ROWS, int KC, int LD, int NT>
+__device__ __forceinline__ void stage_rows(double *tile, const double *__restrict__ src, int ld_src, int row0,
+                                           int nrows, int tid) {
+#pragma unroll
+  for (int q = 0; q < (ROWS / 2) * KC / NT; ++q) {
+    const int idx = tid + q * NT;
+    const int i2 = idx % (ROWS / 2), k = idx / (ROWS / 2);
+    const int r = row0 + 2 * i2;
+    const int valid = max(0, min(2, nrows - r));
+    const double *gp = src + (size_t)k * ld_src + (valid ? r : 0);
+    cp_async16(tile + k * LD + 2 * i2, gp, 8 * valid);
+  }
 }
 
-__global__ void __launch_bounds__(128, 3) k_chol_inv(CholArgs a) {
-  constexpr int TR = RB_CI_TR, LDA_T = RB_CI_LDA, NT = 128;
-  extern __shared__ __align__(16) double sm[];
-  double *As = sm;                           // [2][32][LDA_T] operand ring; buffer 0 doubles as the C tile
-  double *Bs = As + 2 * 32 * LDA_T;          // [2][32][RB_CH_LDB]; buffer 1 doubles as L11 (stride 33)
-  double *sX = Bs + 2 * 32 * RB_CH_LDB;      // [32][RB_CH_LDB]: L11^-1 as a B operand, X(j, c) at c*LDB + j
-  double *sInv = sX + 32 * RB_CH_LDB;        // [32] 1 / L11(k, k)
-  double *sD = Bs + 32 * RB_CH_LDB;
+// (A cp.async.bulk form of the ring -- one bulk copy per 512-byte operand column, mbarrier per stage -- was
+// measured at 18.2 ms against 12.5 ms for the cp.async form at the C5 shape: copies this small are bound by
+// the per-copy cost of the TMA unit.  profiles/tuning_r2.md section 3.)
+template <int KC, int NS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
+  constexpr int TR = RB_CI_TR, LDA_T = RB_CI_LDA, LDB = RB_CH_LDB, NT = 128;
+  static_assert(NS * KC >= 32, "the C tile lives in the first 32 columns of the A ring");
+  extern __shared__ __align__(128) double sm[];
+  double *As = sm;                           // [NS][KC][LDA_T] operand ring; its first 32 columns double as the C tile
+  double *Bs = As + NS * KC * LDA_T;         // [NS][KC][LDB]; doubles as the exchange line of the diagonal block
+  double *sX = Bs + NS * KC * LDB;           // [32][LDB]: L11^-1 as a B operand, X(j, c) at c*LDB + j
+  double *colb = Bs;
   __shared__ int s_fail;
   __shared__ double s_red[2][4];
   const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -415,143 +415,238 @@ __global__ void __launch_bounds__(128, 3) k_chol_inv(CholArgs a) {
   const int nr = n + 1;                      // rows incl. the right-hand-side row
   const int gq = lane >> 2, tg = lane & 3;
   const int wr = warp * 16;                  // warp tile: 16 rows x 32 columns = 2 x 4 DMMA tiles
+  const bool v1ok = ((a.lda1 & 1) == 0) && ((a.strideA1 & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.A1) & 15) == 0);
   bool ok = false;
   for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
     const double jit = attempt ? a.jitter : 0.0;
     if (tid == 0) s_fail = 0;
+    bool pre = false;
     __syncthreads();
     for (int jb = 0; jb < n; jb += RB_CH_NB) {
       const int nb = min(RB_CH_NB, n - jb);
       for (int ti = jb; ti < nr; ti += TR) {
-        // addends of this tile: in flight during the operand loop
-        double c1[2][4][2], c2[2][4][2];
+        // the addend tile of A1 towards L2 (one 64-byte piece per thread and half tile): it is read after
+        // the operand loop, registers stay free for a fourth CTA per SM
+        {
+          const int pc = tid >> 2, pr = (tid & 3) * 16;
+          const int gc = min(jb + pc, n - 1);
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int gr = min(ti + wr + 8 * mi + gq, n - 1), gc = min(jb + 8 * nj + 2 * tg + e, n - 1);
-              c1[mi][nj][e] = A1[gr + (size_t)gc * a.lda1];
-              c2[mi][nj][e] = a.A2 ? a.A2[gr + (size_t)gc * a.lda2] : 0.0;
-            }
+          for (int h = 0; h < 2; ++h) {
+            const int gr = min(ti + pr + 8 * h, n - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A1 + gr + (size_t)gc * a.lda1));
+          }
+        }
         double acc[2][4][2];
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
           for (int nj = 0; nj < 4; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+        // the last tile of a panel is ragged: a warp whose 16 rows lie past the right-hand-side row skips the
+        // products (with 64-row granularity 27 % of all tensor-core work of a 515 x 515 matrix would be padding,
+        // most of it in the late panels where K is largest)
+        const bool wact = ti + wr < nr;
         __syncthreads();                         // ring + C tile + sX readers of the previous tile are done
         if (jb > 0) {
-          stage_rows_k32<TR, LDA_T, NT>(As, L, ldl, ti, nr, tid);
-          stage_rows_k32<32, RB_CH_LDB, NT>(Bs, L, ldl, jb, n, tid);
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          int buf = 0;
-          for (int k0 = 0; k0 < jb; k0 += 32, buf ^= 1) {
-            if (k0 + 32 < jb) {                  // next step's operands fly while this one is multiplied
-              stage_rows_k32<TR, LDA_T, NT>(As + (buf ^ 1) * 32 * LDA_T, L + (size_t)(k0 + 32) * ldl, ldl, ti, nr, tid);
-              stage_rows_k32<32, RB_CH_LDB, NT>(Bs + (buf ^ 1) * 32 * RB_CH_LDB, L + (size_t)(k0 + 32) * ldl, ldl, jb, n, tid);
-              asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;" ::: "memory");
-            } else {
-              asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            __syncthreads();
-            const double *Ab = As + buf * 32 * LDA_T, *Bb = Bs + buf * 32 * RB_CH_LDB;
+          const int nk = jb / KC;
+          // stage i of this tile lives in buffer (sb + i) % NS.  pre: stage 0 was issued into the last buffer
+          // while the previous tile finished (its C tile occupies the first buffers of the ring)
+          const int sb = pre ? NS - 1 : 0;
 #pragma unroll
-            for (int kk = 0; kk < 32; kk += 4) {
+          for (int s0 = 0; s0 < NS - 1; ++s0)
+            if (s0 < nk && !(pre && s0 == 0)) {
+              const int bq = (sb + s0) % NS;
+              stage_rows<TR, KC, LDA_T, NT>(As + bq * KC * LDA_T, L + (size_t)(s0 * KC) * ldl, ldl, ti, nr, tid);
+              stage_rows<32, KC, LDB, NT>(Bs + bq * KC * LDB, L + (size_t)(s0 * KC) * ldl, ldl, jb, n, tid);
+              asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+          int buf = sb, nbuf = (sb + NS - 1) % NS;   // buffer of stage i, buffer stage i + NS - 1 goes to
+          for (int i = 0; i < nk; ++i) {
+            // stage i has landed when at most min(NS - 2, nk - 1 - i) younger groups are outstanding
+            if (NS >= 3 && i + 1 < nk) asm volatile("cp.async.wait_group %0;" ::"n"(NS >= 3 ? NS - 2 : 0) : "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                     // everyone's copies of stage i landed; stage i-1's buffer is free
+            if (i + NS - 1 < nk) {
+              const int k0 = (i + NS - 1) * KC;
+              stage_rows<TR, KC, LDA_T, NT>(As + nbuf * KC * LDA_T, L + (size_t)k0 * ldl, ldl, ti, nr, tid);
+              stage_rows<32, KC, LDB, NT>(Bs + nbuf * KC * LDB, L + (size_t)k0 * ldl, ldl, jb, n, tid);
+              asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            const double *Ab = As + buf * KC * LDA_T, *Bb = Bs + buf * KC * LDB;
+            if (wact)
+#pragma unroll
+            for (int kk = 0; kk < KC; kk += 4) {
               double av[2], bv[4];
 #pragma unroll
               for (int mi = 0; mi < 2; ++mi) av[mi] = Ab[(kk + tg) * LDA_T + wr + 8 * mi + gq];
 #pragma unroll
-              for (int nj = 0; nj < 4; ++nj) bv[nj] = Bb[(kk + tg) * RB_CH_LDB + 8 * nj + gq];
+              for (int nj = 0; nj < 4; ++nj) bv[nj] = Bb[(kk + tg) * LDB + 8 * nj + gq];
 #pragma unroll
               for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], av[mi], bv[nj]);
+                for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], bv[nj], av[mi]);   // transposed fragment
             }
-            __syncthreads();                     // buffer `buf` may be refilled two steps from now
+            buf = (buf + 1 == NS) ? 0 : buf + 1;
+            nbuf = (nbuf + 1 == NS) ? 0 : nbuf + 1;
+          }
+          __syncthreads();                       // the ring is free: its head becomes the C tile
+        }
+        // stage 0 of the NEXT tile into the last ring buffer: it lands while this tile's epilogue, diagonal
+        // block and panel product run.  Next tile: the next 64 rows of this panel, or the first tile of the
+        // next panel -- whose stage 0 (columns 0 .. KC-1) is final unless this is panel 0.
+        pre = false;
+        if (NS >= 3) {
+          const bool same = ti + TR < nr;
+          const int njb = same ? jb : jb + RB_CH_NB, nti = same ? ti + TR : jb + RB_CH_NB;
+          if (jb > 0 && njb < n) {
+            stage_rows<TR, KC, LDA_T, NT>(As + (NS - 1) * KC * LDA_T, L, ldl, nti, nr, tid);
+            stage_rows<32, KC, LDB, NT>(Bs + (NS - 1) * KC * LDB, L, ldl, njb, n, tid);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            pre = true;
           }
         }
-        // C = A1 + A2 [+ jitter I] - L L' (row n: the right-hand side), into shared memory as an A operand
+        // C = A1 + A2 [+ jitter I] - L L' (row n: the right-hand side), into shared memory as an A operand.
+        // The products run with the operands swapped, so a thread holds C(rows wr + 8 mi + 2 tg + {0, 1},
+        // column 8 nj + gq): two consecutive rows of a column -- 16-byte loads of the addend where its
+        // leading dimension allows, conflict-free 16-byte stores of the tile.
+        if (ti >= jb + RB_CH_NB && ti + TR <= n) {
+          // interior tile: all rows below the diagonal block and above the right-hand-side row
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+          for (int mi = 0; mi < 2; ++mi) {
+            double2 c1[4], c2[4];
 #pragma unroll
-          for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int lr = wr + 8 * mi + gq, lc = 8 * nj + 2 * tg + e;
-              const int gr = ti + lr, gc = jb + lc;
-              double v = c1[mi][nj][e] + c2[mi][nj][e] + (gr == gc ? jit : 0.0);
-              if (gr == n && gc < n) v = a.rhs[(size_t)b * a.stride_rhs + gc] + (a.rhs2 ? a.rhs2[gc] : 0.0);
-              v -= acc[mi][nj][e];
-              As[lc * LDA_T + lr] = (gc < n && gr >= gc && gr <= n) ? v : 0.0;
+            for (int nj = 0; nj < 4; ++nj) {
+              const int gr = ti + wr + 8 * mi + 2 * tg, gc = jb + 8 * nj + gq;
+              const double *p1 = A1 + gr + (size_t)gc * a.lda1;
+              if (v1ok) c1[nj] = *reinterpret_cast<const double2 *>(p1);
+              else c1[nj] = make_double2(p1[0], p1[1]);
+              if (a.A2) { const double *p2 = a.A2 + gr + (size_t)gc * a.lda2; c2[nj] = make_double2(p2[0], p2[1]); }
+              else c2[nj] = make_double2(0.0, 0.0);
             }
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj)
+              *reinterpret_cast<double2 *>(As + (8 * nj + gq) * LDA_T + wr + 8 * mi + 2 * tg) =
+                  make_double2((c1[nj].x + c2[nj].x) - acc[mi][nj][0], (c1[nj].y + c2[nj].y) - acc[mi][nj][1]);
+          }
+        } else {
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            double c1[4][2], c2[4][2];
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int gr = min(ti + wr + 8 * mi + 2 * tg + e, n - 1), gc = min(jb + 8 * nj + gq, n - 1);
+                c1[nj][e] = A1[gr + (size_t)gc * a.lda1];
+                c2[nj][e] = a.A2 ? a.A2[gr + (size_t)gc * a.lda2] : 0.0;
+              }
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj) {
+              double v2[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int gr = ti + wr + 8 * mi + 2 * tg + e, gc = jb + 8 * nj + gq;
+                double v = c1[nj][e] + c2[nj][e] + (gr == gc ? jit : 0.0);
+                if (gr == n && gc < n) v = a.rhs[(size_t)b * a.stride_rhs + gc] + (a.rhs2 ? a.rhs2[gc] : 0.0);
+                v -= acc[mi][nj][e];
+                v2[e] = (gc < n && gr >= gc && gr <= n) ? v : 0.0;
+              }
+              *reinterpret_cast<double2 *>(As + (8 * nj + gq) * LDA_T + wr + 8 * mi + 2 * tg) = make_double2(v2[0], v2[1]);
+            }
+          }
+        }
         __syncthreads();
         if (ti == jb) {
-          // diagonal block: rows 0..31 of this tile
-          if (warp == 0) {
-            double x[32], invd;
+          // diagonal block (rows 0..31 of this tile): Cholesky AND inverse by all four warps, right-looking,
+          // one __syncthreads per column.  Thread (lane, warp) holds A(lane, 4q + warp) and
+          // Y(4q + warp, lane), q = 0..7 (Y = L11^-1, built column-oriented alongside: as soon as column
+          // j of L is final, row j of Y is, and both update what is to their right / below).  Column j
+          // is owned by warp j & 3: pivot -> rsqrt (one Newton step for the square root), scaled column
+          // and row j of Y into the double-buffered exchange line, barrier, rank-1 updates by everybody.
+          {
+            double x[8], y[8];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
+            for (int q = 0; q < 8; ++q) {
+              const int c = 4 * q + warp;
               const double v = As[c * LDA_T + lane];
-              x[c] = (lane < nb) ? v : (c == lane ? 1.0 : 0.0);   // identity padding of a narrow last panel
+              x[q] = (lane < nb && c < nb) ? v : (c == lane ? 1.0 : 0.0);   // identity padding of a narrow last panel
+              y[q] = (c == lane) ? 1.0 : 0.0;
             }
-            const bool okw = warp_chol32_reg(x, invd, lane);
-            if (!okw) {
-              if (lane == 0) s_fail = 1;
-            } else {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                sD[lane * 33 + c] = (c <= lane) ? x[c] : 0.0;
-                if (c <= lane && lane < nb) L[(jb + lane) + (size_t)(jb + c) * ldl] = x[c];
+            for (int j = 0; j < 32; ++j) {
+              const int qj = j >> 2, buf = j & 1;
+              if (warp == (j & 3)) {
+                const double dj = __shfl_sync(0xffffffffu, x[qj], j);
+                if (!(dj > 0.0)) {
+                  if (lane == 0) s_fail = 1;
+                } else {
+                  const double r = rsqrt(dj);
+                  double ljj = dj * r;
+                  ljj = fma(fma(-ljj, ljj, dj), 0.5 * r, ljj);
+                  const double lj = (lane == j) ? ljj : (lane > j ? x[qj] * r : 0.0);
+                  const double yj = y[qj] * r;
+                  x[qj] = lj; y[qj] = yj;
+                  colb[buf * 64 + lane] = lj;
+                  colb[buf * 64 + 32 + lane] = yj;
+                }
               }
-              sInv[lane] = invd;
-              __syncwarp();
-              // column `lane` of X = L11^-1 (column-oriented forward substitution: the updates of one
-              // step are independent, the chain is 32 x (multiply + FMA))
-              double y[32];
+              __syncthreads();
+              if (s_fail) break;
+              const double lr = colb[buf * 64 + lane];        // L(lane, j)
+              const double yl = colb[buf * 64 + 32 + lane];   // Y(j, lane)
 #pragma unroll
-              for (int r = 0; r < 32; ++r) y[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                y[k] *= sInv[k];
-#pragma unroll
-                for (int r = k + 1; r < 32; ++r) y[r] = fma(-sD[r * 33 + k], y[k], y[r]);
+              for (int q = qj; q < 8; ++q) {
+                const int k = 4 * q + warp;
+                const double lk = (k > j) ? colb[buf * 64 + k] : 0.0;   // L(k, j)
+                x[q] = fma(-lr, lk, x[q]);       // A(lane, k) -= L(lane, j) L(k, j)
+                y[q] = fma(-lk, yl, y[q]);       // Y(k, lane) -= L(k, j) Y(j, lane)
               }
+            }
+            if (!s_fail) {
 #pragma unroll
-              for (int r = 0; r < 32; ++r) sX[lane * RB_CH_LDB + r] = y[r];
+              for (int q = 0; q < 8; ++q) {
+                const int c = 4 * q + warp;
+                if (c <= lane && lane < nb) L[(jb + lane) + (size_t)(jb + c) * ldl] = x[q];
+                sX[lane * LDB + c] = y[q];                   // X(row c, column lane) as a B operand
+              }
             }
           }
           __syncthreads();
           if (s_fail) break;
         }
         // L21 = C21 X' on the tensor cores; rows of the diagonal block itself are skipped at the store
-        double out[2][4][2];
+        if (ti + wr + 16 > jb + nb && wact) {    // warp-uniform: this warp owns rows below the diagonal block
+          double out[2][4][2];
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+          for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-          for (int nj = 0; nj < 4; ++nj) out[mi][nj][0] = out[mi][nj][1] = 0.0;
-        if (ti + wr + 16 > jb + nb) {            // warp-uniform: this warp owns rows below the diagonal block
+            for (int nj = 0; nj < 4; ++nj) out[mi][nj][0] = out[mi][nj][1] = 0.0;
 #pragma unroll
           for (int kk = 0; kk < 32; kk += 4) {
             double av[2], bv[4];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) av[mi] = As[(kk + tg) * LDA_T + wr + 8 * mi + gq];
 #pragma unroll
-            for (int nj = 0; nj < 4; ++nj) bv[nj] = sX[(kk + tg) * RB_CH_LDB + 8 * nj + gq];
+            for (int nj = 0; nj < 4; ++nj) bv[nj] = sX[(kk + tg) * LDB + 8 * nj + gq];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-              for (int nj = 0; nj < 4; ++nj) dmma884(out[mi][nj][0], out[mi][nj][1], av[mi], bv[nj]);
+              for (int nj = 0; nj < 4; ++nj) dmma884(out[mi][nj][0], out[mi][nj][1], bv[nj], av[mi]);
           }
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int gr = ti + wr + 8 * mi + gq, gc = jb + 8 * nj + 2 * tg + e;
-                if (gr >= jb + nb && gr < nr && gc < n) L[gr + (size_t)gc * ldl] = out[mi][nj][e];
+            for (int nj = 0; nj < 4; ++nj) {
+              const int gr = ti + wr + 8 * mi + 2 * tg, gc = jb + 8 * nj + gq;
+              if (gc < n) {
+                double *dst = L + gr + (size_t)gc * ldl;
+                if (gr >= jb + nb && gr + 1 < nr) {
+                  *reinterpret_cast<double2 *>(dst) = make_double2(out[mi][nj][0], out[mi][nj][1]);
+                } else {
+                  if (gr >= jb + nb && gr < nr) dst[0] = out[mi][nj][0];
+                  if (gr + 1 >= jb + nb && gr + 1 < nr) dst[1] = out[mi][nj][1];
+                }
               }
+            }
         }
       }
       __syncthreads();
@@ -565,6 +660,7 @@ __global__ void __launch_bounds__(128, 3) k_chol_inv(CholArgs a) {
     }
     __syncthreads();
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");   // a prefetch may be in flight after a failed attempt
   if (!ok) {
     if (tid == 0 && atomicCAS(&a.status->not_pd, 0, 1) == 0) {
       a.status->not_pd_step = a.t;
