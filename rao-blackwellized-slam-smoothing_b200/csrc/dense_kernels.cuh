@@ -133,6 +133,116 @@ __global__ void __launch_bounds__(256, 2) k_dgemm(GemmArgs g) {
 }
 
 // ---------------------------------------------------------------------------
+// k_dgemm_pipe<AK>: the same product with the operands staged by cp.async (16-byte copies) into a
+// double-buffered ring, so the loads of K-step i+1 fly while step i is multiplied.  k_dgemm above stages
+// with synchronous scalar loads and is kept for operands whose leading dimensions / addresses are not
+// 16-byte friendly (launch_gemm checks).
+//   A: AK = false  stored [m x k] (row index contiguous)  -> tile [32 k][RB_LDA], as k_dgemm
+//      AK = true   stored [k x m] (k contiguous)          -> tile [128 m][RB_LDK]
+//   B: stored [k x n] (k contiguous)                      -> tile [64 n][RB_LDK]
+// RB_LDK = 36 = 4 (mod 16) doubles: a fragment read (8 rows x 4 k) touches every 8-byte bank pair exactly
+// twice, the minimum for 256 bytes.
+// ---------------------------------------------------------------------------
+#define RB_LDK 36
+static inline size_t dgemm_pipe_smem(bool ak) {
+  return sizeof(double) * 2 * ((ak ? 128 * RB_LDK : 32 * RB_LDA) + 64 * RB_LDK);
+}
+// rows [r0, r0+ROWS) x k [k0, k0+32) of a k-contiguous operand X(k, r) = X[k + r*ld] into tile[r][RB_LDK]
+template <int ROWS>
+__device__ __forceinline__ void stage_kmajor(double *tile, const double *__restrict__ X, int ld, int r0, int nrows,
+                                             int k0, int K, int tid) {
+#pragma unroll
+  for (int q = 0; q < ROWS * 16 / 256; ++q) {
+    const int idx = tid + q * 256;
+    const int k2 = idx & 15, r = idx >> 4;
+    const int gk = k0 + 2 * k2, gr = r0 + r;
+    const int valid = gr < nrows ? max(0, min(2, K - gk)) : 0;
+    const double *gp = X + (valid ? gk + (size_t)gr * ld : 0);
+    cp_async16(tile + r * RB_LDK + 2 * k2, gp, 8 * valid);
+  }
+}
+// rows [r0, r0+128) x k [k0, k0+32) of a row-contiguous operand X(r, k) = X[r + k*ld] into tile[k][RB_LDA]
+__device__ __forceinline__ void stage_mmajor(double *tile, const double *__restrict__ X, int ld, int r0, int nrows,
+                                             int k0, int K, int tid) {
+#pragma unroll
+  for (int q = 0; q < 64 * 32 / 256; ++q) {
+    const int idx = tid + q * 256;
+    const int i2 = idx & 63, k = idx >> 6;
+    const int gr = r0 + 2 * i2, gk = k0 + k;
+    const int valid = gk < K ? max(0, min(2, nrows - gr)) : 0;
+    const double *gp = X + (valid ? gr + (size_t)gk * ld : 0);
+    cp_async16(tile + k * RB_LDA + 2 * i2, gp, 8 * valid);
+  }
+}
+
+template <bool AK>
+__global__ void __launch_bounds__(256, 2) k_dgemm_pipe(GemmArgs g) {
+  extern __shared__ __align__(16) double sm_gemm[];
+  constexpr int ASZ = AK ? 128 * RB_LDK : 32 * RB_LDA, BSZ = 64 * RB_LDK;
+  double *As = sm_gemm;                  // [2][ASZ]
+  double *Bs = sm_gemm + 2 * ASZ;        // [2][BSZ]
+  const int b = blockIdx.z;
+  const double *A = g.A + (size_t)(g.slotA ? g.slotA[b] : b) * g.strideA;
+  const double *B = g.B + (size_t)b * g.strideB;
+  double *C = g.C + (size_t)b * g.strideC;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+  const int gq = lane >> 2, tg = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  auto stage = [&](int buf, int k0) {
+    if (AK) stage_kmajor<128>(As + buf * ASZ, A, g.lda, m0, g.m, k0, g.k, tid);
+    else stage_mmajor(As + buf * ASZ, A, g.lda, m0, g.m, k0, g.k, tid);
+    stage_kmajor<64>(Bs + buf * BSZ, B, g.ldb, n0, g.n, k0, g.k, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int nk = (g.k + 31) / 32;
+  stage(0, 0);
+  for (int i = 0; i < nk; ++i) {
+    const int buf = i & 1;
+    if (i + 1 < nk) {
+      stage(buf ^ 1, (i + 1) * 32);      // its buffer was released by the barrier that closed step i-1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const double *Ab = As + buf * ASZ, *Bb = Bs + buf * BSZ;
+#pragma unroll
+    for (int kk = 0; kk < 32; kk += 4) {
+      double a[4], bv[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+        a[mi] = AK ? Ab[(wr + 8 * mi + gq) * RB_LDK + kk + tg] : Ab[(kk + tg) * RB_LDA + wr + 8 * mi + gq];
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj) bv[nj] = Bb[(wc + 8 * nj + gq) * RB_LDK + kk + tg];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], bv[nj]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gi = m0 + wr + 8 * mi + gq, gj = n0 + wc + 8 * nj + 2 * tg + e;
+        if (gi < g.m && gj < g.n) {
+          double v = acc[mi][nj][e];
+          if (g.Rblk && (gi / g.d) == (gj / g.d)) v += g.Rblk[(gi % g.d) + (gj % g.d) * g.d];
+          C[gi + (size_t)gj * g.ldc] = v;
+        }
+      }
+}
+
+// ---------------------------------------------------------------------------
 // batched Cholesky + forward solve, one CTA (256 threads) per matrix
 // ---------------------------------------------------------------------------
 struct CholArgs {
@@ -397,6 +507,28 @@ __device__ __forceinline__ void stage_rows(double *tile, const double *__restric
 // (A cp.async.bulk form of the ring -- one bulk copy per 512-byte operand column, mbarrier per stage -- was
 // measured at 18.2 ms against 12.5 ms for the cp.async form at the C5 shape: copies this small are bound by
 // the per-copy cost of the TMA unit.  profiles/tuning_r2.md section 3.)
+// one operand stage of the panel update for a 16 x 32 warp tile; MASK selects the 8 x 8 tiles (bit 4 mi + nj).
+// Operands swapped: the thread ends up with C(rows 8 mi + 2 tg + {0, 1}, column 8 nj + gq).
+template <int KC, int MASK>
+__device__ __forceinline__ void chol_kstep(const double *__restrict__ Ab, const double *__restrict__ Bb,
+                                           double (&acc)[2][4][2]) {
+#pragma unroll
+  for (int kk = 0; kk < KC; kk += 4) {
+    double av[2], bv[4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+      if ((MASK >> (4 * mi)) & 0xf) av[mi] = Ab[kk * RB_CI_LDA + 8 * mi];
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj)
+      if ((MASK >> nj) & 0x11) bv[nj] = Bb[kk * RB_CH_LDB + 8 * nj];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+        if ((MASK >> (4 * mi + nj)) & 1) dmma884(acc[mi][nj][0], acc[mi][nj][1], bv[nj], av[mi]);
+  }
+}
+
 template <int KC, int NS, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
   constexpr int TR = RB_CI_TR, LDA_T = RB_CI_LDA, LDB = RB_CH_LDB, NT = 128;
@@ -445,6 +577,8 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
         // products (with 64-row granularity 27 % of all tensor-core work of a 515 x 515 matrix would be padding,
         // most of it in the late panels where K is largest)
         const bool wact = ti + wr < nr;
+        // tiles (mi, nj) of this warp that are multiplied: bit 4 mi + nj
+        const int tmask = !wact ? 0 : (ti != jb || warp > 1) ? 0xff : (warp == 0 ? 0x31 : 0xf7);
         __syncthreads();                         // ring + C tile + sX readers of the previous tile are done
         if (jb > 0) {
           const int nk = jb / KC;
@@ -471,20 +605,12 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
               stage_rows<32, KC, LDB, NT>(Bs + nbuf * KC * LDB, L + (size_t)k0 * ldl, ldl, jb, n, tid);
               asm volatile("cp.async.commit_group;" ::: "memory");
             }
-            const double *Ab = As + buf * KC * LDA_T, *Bb = Bs + buf * KC * LDB;
-            if (wact)
-#pragma unroll
-            for (int kk = 0; kk < KC; kk += 4) {
-              double av[2], bv[4];
-#pragma unroll
-              for (int mi = 0; mi < 2; ++mi) av[mi] = Ab[(kk + tg) * LDA_T + wr + 8 * mi + gq];
-#pragma unroll
-              for (int nj = 0; nj < 4; ++nj) bv[nj] = Bb[(kk + tg) * LDB + 8 * nj + gq];
-#pragma unroll
-              for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], bv[nj], av[mi]);   // transposed fragment
-            }
+            const double *Ab = As + buf * KC * LDA_T + wr + gq + tg * LDA_T, *Bb = Bs + buf * KC * LDB + gq + tg * LDB;
+            // the 8 x 8 tiles strictly above the diagonal of the diagonal block are never read: warps 0 and 1
+            // of a panel's first tile skip them (6 of their 16 tiles)
+            if (tmask == 0xff) chol_kstep<KC, 0xff>(Ab, Bb, acc);
+            else if (tmask == 0x31) chol_kstep<KC, 0x31>(Ab, Bb, acc);
+            else if (tmask == 0xf7) chol_kstep<KC, 0xf7>(Ab, Bb, acc);
             buf = (buf + 1 == NS) ? 0 : buf + 1;
             nbuf = (nbuf + 1 == NS) ? 0 : nbuf + 1;
           }
@@ -509,24 +635,34 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
         // column 8 nj + gq): two consecutive rows of a column -- 16-byte loads of the addend where its
         // leading dimension allows, conflict-free 16-byte stores of the tile.
         if (ti >= jb + RB_CH_NB && ti + TR <= n) {
-          // interior tile: all rows below the diagonal block and above the right-hand-side row
+          // interior tile: all rows below the diagonal block and above the right-hand-side row; all 24 loads of
+          // a thread in flight together (the A1 tile was prefetched towards L2, A2 is shared by every matrix)
+          double2 c1[2][4], c2[2][4];
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
-            double2 c1[4], c2[4];
+          for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj) {
-              const int gr = ti + wr + 8 * mi + 2 * tg, gc = jb + 8 * nj + gq;
-              const double *p1 = A1 + gr + (size_t)gc * a.lda1;
-              if (v1ok) c1[nj] = *reinterpret_cast<const double2 *>(p1);
-              else c1[nj] = make_double2(p1[0], p1[1]);
-              if (a.A2) { const double *p2 = a.A2 + gr + (size_t)gc * a.lda2; c2[nj] = make_double2(p2[0], p2[1]); }
-              else c2[nj] = make_double2(0.0, 0.0);
+              const double *p1 = A1 + (ti + wr + 8 * mi + 2 * tg) + (size_t)(jb + 8 * nj + gq) * a.lda1;
+              if (v1ok) c1[mi][nj] = *reinterpret_cast<const double2 *>(p1);
+              else c1[mi][nj] = make_double2(p1[0], p1[1]);
             }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj) {
+              if (a.A2) {
+                const double *p2 = a.A2 + (ti + wr + 8 * mi + 2 * tg) + (size_t)(jb + 8 * nj + gq) * a.lda2;
+                c2[mi][nj] = make_double2(p2[0], p2[1]);
+              } else {
+                c2[mi][nj] = make_double2(0.0, 0.0);
+              }
+            }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj)
               *reinterpret_cast<double2 *>(As + (8 * nj + gq) * LDA_T + wr + 8 * mi + 2 * tg) =
-                  make_double2((c1[nj].x + c2[nj].x) - acc[mi][nj][0], (c1[nj].y + c2[nj].y) - acc[mi][nj][1]);
-          }
+                  make_double2((c1[mi][nj].x + c2[mi][nj].x) - acc[mi][nj][0], (c1[mi][nj].y + c2[mi][nj].y) - acc[mi][nj][1]);
         } else {
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
@@ -557,54 +693,71 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
         __syncthreads();
         if (ti == jb) {
           // diagonal block (rows 0..31 of this tile): Cholesky AND inverse by all four warps, right-looking,
-          // one __syncthreads per column.  Thread (lane, warp) holds A(lane, 4q + warp) and
-          // Y(4q + warp, lane), q = 0..7 (Y = L11^-1, built column-oriented alongside: as soon as column
-          // j of L is final, row j of Y is, and both update what is to their right / below).  Column j
-          // is owned by warp j & 3: pivot -> rsqrt (one Newton step for the square root), scaled column
-          // and row j of Y into the double-buffered exchange line, barrier, rank-1 updates by everybody.
+          // TWO columns per block barrier.  Columns 2P, 2P+1 belong to warp P & 3; thread (lane, warp) holds
+          // A(lane, c) and Y(c, lane) for its 8 columns c = 8q + 2 warp + e (Y = L11^-1, built column-oriented
+          // alongside: as soon as column j of L is final, row j of Y is, and both update what is to their
+          // right / below).  Owner: pivot -> rsqrt (one Newton step for the square root) -> column j, its
+          // effect on column j+1 inside the warp (shuffles), pivot j+1, both columns and both rows of Y into
+          // the double-buffered exchange line; barrier; rank-2 updates by everybody.
           {
             double x[8], y[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const int c = 4 * q + warp;
+              const int c = 8 * (q >> 1) + 2 * warp + (q & 1);
               const double v = As[c * LDA_T + lane];
               x[q] = (lane < nb && c < nb) ? v : (c == lane ? 1.0 : 0.0);   // identity padding of a narrow last panel
               y[q] = (c == lane) ? 1.0 : 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int qj = j >> 2, buf = j & 1;
-              if (warp == (j & 3)) {
-                const double dj = __shfl_sync(0xffffffffu, x[qj], j);
-                if (!(dj > 0.0)) {
+            for (int P = 0; P < 16; ++P) {
+              const int j = 2 * P, qj = 2 * (P >> 2), buf = P & 1;
+              double *cb = colb + buf * 128;     // [4][32]: L(:, j), L(:, j+1), Y(j, :), Y(j+1, :)
+              if (warp == (P & 3)) {
+                const double d0 = __shfl_sync(0xffffffffu, x[qj], j);
+                double l0 = 0.0, l1 = 0.0, y0 = 0.0, y1 = 0.0;
+                bool bad = !(d0 > 0.0);
+                if (!bad) {
+                  const double r0 = rsqrt(d0);
+                  double s0 = d0 * r0;
+                  s0 = fma(fma(-s0, s0, d0), 0.5 * r0, s0);
+                  l0 = (lane == j) ? s0 : (lane > j ? x[qj] * r0 : 0.0);
+                  y0 = y[qj] * r0;
+                  const double l10 = __shfl_sync(0xffffffffu, l0, j + 1);   // L(j+1, j)
+                  const double x1 = fma(-l0, l10, x[qj + 1]);
+                  const double d1 = __shfl_sync(0xffffffffu, x1, j + 1);
+                  bad = !(d1 > 0.0);
+                  if (!bad) {
+                    const double r1 = rsqrt(d1);
+                    double s1 = d1 * r1;
+                    s1 = fma(fma(-s1, s1, d1), 0.5 * r1, s1);
+                    l1 = (lane == j + 1) ? s1 : (lane > j + 1 ? x1 * r1 : 0.0);
+                    y1 = fma(-l10, y0, y[qj + 1]) * r1;
+                  }
+                }
+                if (bad) {
                   if (lane == 0) s_fail = 1;
                 } else {
-                  const double r = rsqrt(dj);
-                  double ljj = dj * r;
-                  ljj = fma(fma(-ljj, ljj, dj), 0.5 * r, ljj);
-                  const double lj = (lane == j) ? ljj : (lane > j ? x[qj] * r : 0.0);
-                  const double yj = y[qj] * r;
-                  x[qj] = lj; y[qj] = yj;
-                  colb[buf * 64 + lane] = lj;
-                  colb[buf * 64 + 32 + lane] = yj;
+                  x[qj] = l0; x[qj + 1] = l1; y[qj] = y0; y[qj + 1] = y1;
+                  cb[lane] = l0; cb[32 + lane] = l1; cb[64 + lane] = y0; cb[96 + lane] = y1;
                 }
               }
               __syncthreads();
               if (s_fail) break;
-              const double lr = colb[buf * 64 + lane];        // L(lane, j)
-              const double yl = colb[buf * 64 + 32 + lane];   // Y(j, lane)
+              const double lr0 = cb[lane], lr1 = cb[32 + lane];          // L(lane, j), L(lane, j+1)
+              const double yl0 = cb[64 + lane], yl1 = cb[96 + lane];     // Y(j, lane), Y(j+1, lane)
 #pragma unroll
               for (int q = qj; q < 8; ++q) {
-                const int k = 4 * q + warp;
-                const double lk = (k > j) ? colb[buf * 64 + k] : 0.0;   // L(k, j)
-                x[q] = fma(-lr, lk, x[q]);       // A(lane, k) -= L(lane, j) L(k, j)
-                y[q] = fma(-lk, yl, y[q]);       // Y(k, lane) -= L(k, j) Y(j, lane)
+                const int k = 8 * (q >> 1) + 2 * warp + (q & 1);
+                const bool upd = k > j + 1;
+                const double lk0 = upd ? cb[k] : 0.0, lk1 = upd ? cb[32 + k] : 0.0;   // L(k, j), L(k, j+1)
+                x[q] = fma(-lr1, lk1, fma(-lr0, lk0, x[q]));     // A(lane, k) -= L(lane, j) L(k, j) + L(lane, j+1) L(k, j+1)
+                y[q] = fma(-lk1, yl1, fma(-lk0, yl0, y[q]));     // Y(k, lane) -= L(k, j) Y(j, lane) + L(k, j+1) Y(j+1, lane)
               }
             }
             if (!s_fail) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const int c = 4 * q + warp;
+                const int c = 8 * (q >> 1) + 2 * warp + (q & 1);
                 if (c <= lane && lane < nb) L[(jb + lane) + (size_t)(jb + c) * ldl] = x[q];
                 sX[lane * LDB + c] = y[q];                   // X(row c, column lane) as a B operand
               }

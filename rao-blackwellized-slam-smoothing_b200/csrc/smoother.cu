@@ -175,7 +175,7 @@ __global__ void k_future_resid(int M, int ntau, const double *__restrict__ Dt, i
 __global__ void k_sparse_future(ModelConsts mc, int nobs, const int *__restrict__ obs_t,
                                 const int *__restrict__ obs_l, const double *__restrict__ xnk,
                                 const double *__restrict__ y, const double *__restrict__ xl, int i0,
-                                double *__restrict__ Dti, size_t strideD, double *__restrict__ e,
+                                double *__restrict__ Dti, int ldd, size_t strideD, double *__restrict__ e,
                                 size_t stride_e) {
   const int b = blockIdx.y;
   const int M = mc.M;
@@ -192,9 +192,9 @@ __global__ void k_sparse_future(ModelConsts mc, int nobs, const int *__restrict_
     const double yhat = (mc.cam_f * lx + mc.cam_fp * ly) / ly;
     const double dv = m2 * c - p2 * c - m1 * s + p1 * s;
     const double div = dv * dv;
-    for (int r = 0; r < M; ++r) D[r + (size_t)j * M] = 0.0;
-    D[2 * l + (size_t)j * M] = (mc.cam_f * (m2 - p2)) / div;
-    D[2 * l + 1 + (size_t)j * M] = -(mc.cam_f * (m1 - p1)) / div;
+    for (int r = 0; r < M; ++r) D[r + (size_t)j * ldd] = 0.0;
+    D[2 * l + (size_t)j * ldd] = (mc.cam_f * (m2 - p2)) / div;
+    D[2 * l + 1 + (size_t)j * ldd] = -(mc.cam_f * (m1 - p1)) / div;
     e[(size_t)b * stride_e + j] = y[(size_t)ti * mc.d + l] - yhat;
   }
 }
@@ -590,11 +590,24 @@ int rb_info_kalman_phase(rbslam_ctx *ctx, const double *y_t_dev, const double *y
 // ---------------------------------------------------------------------------
 static int launch_gemm(rbslam_ctx *ctx, bool ta, const GemmArgs &g, int batch) {
   dim3 grid((g.m + 127) / 128, (g.n + 63) / 64, batch);
-  const size_t smem = sizeof(double) * 32 * (RB_LDA + RB_LDB);
-  RB_OPTIN_SMEM(k_dgemm<true>, smem);
-  RB_OPTIN_SMEM(k_dgemm<false>, smem);
-  if (ta) k_dgemm<true><<<grid, 256, smem, ctx->stream>>>(g);
-  else k_dgemm<false><<<grid, 256, smem, ctx->stream>>>(g);
+  // cp.async-pipelined kernel when every 16-byte copy is aligned (the sweeps allocate their operands that way);
+  // otherwise the synchronous-staging kernel
+  static int force_sync = -1;
+  if (force_sync < 0) { const char *e = getenv("RBSLAM_GEMM_SYNC"); force_sync = (e && atoi(e)) ? 1 : 0; }
+  const bool aligned = !force_sync && (g.lda % 2 == 0) && (g.ldb % 2 == 0) && (g.strideA % 2 == 0) && (g.strideB % 2 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B)) & 15) == 0;
+  if (aligned) {
+    RB_OPTIN_SMEM(k_dgemm_pipe<true>, dgemm_pipe_smem(true));
+    RB_OPTIN_SMEM(k_dgemm_pipe<false>, dgemm_pipe_smem(false));
+    if (ta) k_dgemm_pipe<true><<<grid, 256, dgemm_pipe_smem(true), ctx->stream>>>(g);
+    else k_dgemm_pipe<false><<<grid, 256, dgemm_pipe_smem(false), ctx->stream>>>(g);
+  } else {
+    const size_t smem = sizeof(double) * 32 * (RB_LDA + RB_LDB);
+    RB_OPTIN_SMEM(k_dgemm<true>, smem);
+    RB_OPTIN_SMEM(k_dgemm<false>, smem);
+    if (ta) k_dgemm<true><<<grid, 256, smem, ctx->stream>>>(g);
+    else k_dgemm<false><<<grid, 256, smem, ctx->stream>>>(g);
+  }
   ctx->launches += 1;
   CK(cudaGetLastError());
   return RBSLAM_OK;
@@ -678,7 +691,8 @@ static int ancestor_weights_cov(rbslam_ctx *ctx, int t, bool use_default_dyn) {
   const int ne = sparse ? (w->n_obs - w->obs_off[t]) : d * (T - t);
   const double *xl_old = ctx->d_xl[ctx->cx];
   const int *slot_old = ctx->d_slot[ctx->cs];
-  const size_t sW = (size_t)M * w->ntau_max, sS = w->ntau_max * w->ntau_max;
+  const int ldw = ctx->ld;   // W and Dti: leading dimension padded like the slabs (16-byte aligned columns)
+  const size_t sW = (size_t)ldw * w->ntau_max, sS = w->ntau_max * w->ntau_max;
   const size_t sLw = (size_t)chol_ldl((int)w->ntau_max) * w->ntau_max;
   int blo, bhi;
   rep_block(ctx, N, blo, bhi);
@@ -689,18 +703,18 @@ static int ancestor_weights_cov(rbslam_ctx *ctx, int t, bool use_default_dyn) {
       GemmArgs g1{};   // W = P_i * D'
       g1.m = M; g1.n = ne; g1.k = M;
       g1.A = ctx->d_P; g1.lda = ctx->ld; g1.strideA = ctx->slab; g1.slotA = slot_old + b0;
-      g1.C = w->W; g1.ldc = M; g1.strideC = sW; g1.Rblk = nullptr; g1.d = 1;
+      g1.C = w->W; g1.ldc = ldw; g1.strideC = sW; g1.Rblk = nullptr; g1.d = 1;
       GemmArgs g2{};   // SS = D * W (+ kron(I,R))
       g2.m = ne; g2.n = ne; g2.k = M; g2.slotA = nullptr;
-      g2.B = w->W; g2.ldb = M; g2.strideB = sW;
+      g2.B = w->W; g2.ldb = ldw; g2.strideB = sW;
       g2.C = w->SS; g2.ldc = ne; g2.strideC = sS;
       if (sparse) {
         const int o0 = w->obs_off[t];
         k_sparse_future<<<dim3((ne + 127) / 128, cnt), 128, 0, ctx->stream>>>(
-            ctx->mc, ne, w->obs_t + o0, w->obs_l + o0, w->xnk, ctx->d_y, xl_old, b0, w->Dti, sW, w->e, w->ntau_max);
+            ctx->mc, ne, w->obs_t + o0, w->obs_l + o0, w->xnk, ctx->d_y, xl_old, b0, w->Dti, ldw, sW, w->e, w->ntau_max);
         ctx->launches += 1;
-        g1.B = w->Dti; g1.ldb = M; g1.strideB = sW;
-        g2.A = w->Dti; g2.lda = M; g2.strideA = sW; g2.Rblk = nullptr; g2.d = 1;
+        g1.B = w->Dti; g1.ldb = ldw; g1.strideB = sW;
+        g2.A = w->Dti; g2.lda = ldw; g2.strideA = sW; g2.Rblk = nullptr; g2.d = 1;
       } else {
         const double *Dt = w->Hk + (size_t)t * d * ctx->ldh;
         g1.B = Dt; g1.ldb = ctx->ldh; g1.strideB = 0;
@@ -860,8 +874,8 @@ static int smoother_run_impl(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N
       }
       const size_t per = ((size_t)M * w->ntau_max * (sparse ? 2 : 1) + 2 * w->ntau_max * w->ntau_max + w->ntau_max) * 8;
       w->batch = std::max<size_t>(1, std::min<size_t>(N, ((size_t)6 << 30) / per));
-      RB_ALLOC(w->W, w->batch * M * w->ntau_max);
-      if (sparse) RB_ALLOC(w->Dti, w->batch * M * w->ntau_max);
+      RB_ALLOC(w->W, w->batch * ctx->ld * w->ntau_max);
+      if (sparse) RB_ALLOC(w->Dti, w->batch * ctx->ld * w->ntau_max);
       RB_ALLOC(w->SS, w->batch * w->ntau_max * w->ntau_max);
       RB_ALLOC(w->Lw, w->batch * (size_t)chol_ldl((int)w->ntau_max) * w->ntau_max);
       RB_ALLOC(w->e, w->batch * w->ntau_max);
@@ -1055,36 +1069,46 @@ extern "C" int rbslam_op_ancestor_weights(rbslam_ctx *ctx, int32_t form, int32_t
     return RBSLAM_OK;
   };
   const size_t MM = (size_t)M * M, ldl = chol_ldl(n);
-  if ((rc = alloc(bA, MM * N * 8)) || (rc = alloc(bv, (size_t)M * N * 8)) || (rc = alloc(bsl, (size_t)N * 8)) ||
+  // form 0: the covariances and D' get the slabs' padded leading dimension, as in the sweeps (the cp.async
+  // staging of k_dgemm_pipe needs 16-byte aligned columns)
+  const size_t ldp = form == 0 ? (size_t)ctx->ld : (size_t)M;
+  if ((rc = alloc(bA, ldp * M * N * 8)) || (rc = alloc(bv, (size_t)M * N * 8)) || (rc = alloc(bsl, (size_t)N * 8)) ||
       (rc = alloc(bvv, (size_t)N * 8)) || (rc = alloc(bo, (size_t)N * 8)) || (rc = alloc(bL, ldl * n * N * 8)))
     return rc;
-  if ((rc = rb_h2d(ctx, bA.p, A, MM * N * 8)) || (rc = rb_h2d(ctx, bv.p, v, (size_t)M * N * 8))) return rc;
+  if (form == 0) {
+    CK(cudaMemsetAsync(bA.p, 0, ldp * M * N * 8, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy2D(bA.p, ldp * 8, A, (size_t)M * 8, (size_t)M * 8, (size_t)M * N, cudaMemcpyHostToDevice));
+  } else if ((rc = rb_h2d(ctx, bA.p, A, MM * N * 8))) {
+    return rc;
+  }
+  if ((rc = rb_h2d(ctx, bv.p, v, (size_t)M * N * 8))) return rc;
   CholArgs c{};
   c.n = n; c.L = (double *)bL.p; c.ldl = (int)ldl; c.strideL = ldl * n; c.jitter = jitter;
   c.sum_log_diag = (double *)bsl.p; c.vtv = (double *)bvv.p; c.status = ctx->d_status; c.t = 0;
   CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(DevStatus), ctx->stream));
   if (form == 0) {
     // S = D [ne x M] (MATLAB layout) -> Dt [M x ne]; r = stacked future measurements
-    std::vector<double> Dt((size_t)M * ne);
+    std::vector<double> Dt(ldp * ne, 0.0);
     for (int j = 0; j < ne; ++j)
-      for (int cidx = 0; cidx < M; ++cidx) Dt[cidx + (size_t)j * M] = S[j + (size_t)cidx * ne];
+      for (int cidx = 0; cidx < M; ++cidx) Dt[cidx + (size_t)j * ldp] = S[j + (size_t)cidx * ne];
     if ((rc = alloc(bS, Dt.size() * 8)) || (rc = alloc(br, (size_t)ne * 8)) || (rc = alloc(bR, (size_t)d * d * 8)) ||
-        (rc = alloc(bW, (size_t)M * ne * N * 8)) || (rc = alloc(bSS, (size_t)ne * ne * N * 8)) ||
+        (rc = alloc(bW, ldp * ne * N * 8)) || (rc = alloc(bSS, (size_t)ne * ne * N * 8)) ||
         (rc = alloc(be, (size_t)ne * N * 8)))
       return rc;
     if ((rc = rb_h2d(ctx, bS.p, Dt.data(), Dt.size() * 8)) || (rc = rb_h2d(ctx, br.p, r, (size_t)ne * 8)) ||
         (rc = rb_h2d(ctx, bR.p, R, (size_t)d * d * 8)))
       return rc;
-    k_future_resid<<<dim3((ne + 3) / 4, N), 128, 0, ctx->stream>>>(M, ne, (const double *)bS.p, M, (const double *)br.p,
+    k_future_resid<<<dim3((ne + 3) / 4, N), 128, 0, ctx->stream>>>(M, ne, (const double *)bS.p, (int)ldp, (const double *)br.p,
                                                                   (const double *)bv.p, 0, (double *)be.p, ne);
     ctx->launches += 1;
     GemmArgs g1{};   // W = P_i * D'
-    g1.m = M; g1.n = ne; g1.k = M; g1.A = (const double *)bA.p; g1.lda = M; g1.strideA = MM; g1.slotA = nullptr;
-    g1.B = (const double *)bS.p; g1.ldb = M; g1.strideB = 0;
-    g1.C = (double *)bW.p; g1.ldc = M; g1.strideC = (size_t)M * ne; g1.Rblk = nullptr; g1.d = 1;
+    g1.m = M; g1.n = ne; g1.k = M; g1.A = (const double *)bA.p; g1.lda = (int)ldp; g1.strideA = ldp * M; g1.slotA = nullptr;
+    g1.B = (const double *)bS.p; g1.ldb = (int)ldp; g1.strideB = 0;
+    g1.C = (double *)bW.p; g1.ldc = (int)ldp; g1.strideC = ldp * ne; g1.Rblk = nullptr; g1.d = 1;
     GemmArgs g2{};   // SS = D * W + kron(I, R)
-    g2.m = ne; g2.n = ne; g2.k = M; g2.A = (const double *)bS.p; g2.lda = M; g2.strideA = 0; g2.slotA = nullptr;
-    g2.B = (const double *)bW.p; g2.ldb = M; g2.strideB = (size_t)M * ne;
+    g2.m = ne; g2.n = ne; g2.k = M; g2.A = (const double *)bS.p; g2.lda = (int)ldp; g2.strideA = 0; g2.slotA = nullptr;
+    g2.B = (const double *)bW.p; g2.ldb = (int)ldp; g2.strideB = ldp * ne;
     g2.C = (double *)bSS.p; g2.ldc = ne; g2.strideC = (size_t)ne * ne; g2.Rblk = (const double *)bR.p; g2.d = d;
     if ((rc = launch_gemm(ctx, false, g1, N)) || (rc = launch_gemm(ctx, true, g2, N))) return rc;
     c.A1 = (const double *)bSS.p; c.lda1 = ne; c.strideA1 = (size_t)ne * ne; c.slot1 = nullptr; c.A2 = nullptr; c.lda2 = 0;
