@@ -227,20 +227,25 @@ def fp64_peak():
 
 
 def _c5_sweep_ms(ctx, a, dt, Ts):
-    """ms per time step of ONE sweep with ancestor weights (k > 0): wall time of an N_K = 3 call minus an N_K = 1
-    call, over two sweeps (the fixed costs of a call -- upload, first sweep, extraction -- cancel; a difference over
-    one sweep of a 24-step slice was within the noise of those costs).  Then the phase times of an N_K = 2 call."""
+    """ms per time step of ONE sweep with ancestor weights (k > 0), measured INSIDE one N_K = 3 call: the library's
+    per-sweep callback (the reference's makePlots hook, t == T) fires when a sweep's outputs are written; the time
+    between the ends of sweeps 2 and 3 is a whole sweep including its initialisation and read-out.  (Differences of
+    whole-call wall times were useless on a replica group: a call's fixed costs vary by +-0.3 s there.)  Then the
+    phase times of an N_K = 2 call without the callback."""
     ctx.smoother_run(*a, dt, 2, 1)          # warm-up: every kernel of both kinds of sweep
-    t = {}
-    for nk in (1, 3):
-        t0 = time.perf_counter()
-        ctx.smoother_run(*a, dt, nk, 1)
-        t[nk] = time.perf_counter() - t0
+    marks = {}
+
+    def cb(k, t):
+        if t == Ts:
+            marks[k] = time.perf_counter()
+    ctx.set_step_callback(cb)
+    ctx.smoother_run(*a, dt, 3, 1)
+    ctx.set_step_callback(None)
     ctx.phase_timing(True)
     ctx.smoother_run(*a, dt, 2, 1)
     ph = ctx.phase_times()
     ctx.phase_timing(False)
-    return 1e3 * (t[3] - t[1]) / (2 * Ts), ph
+    return 1e3 * (marks[2] - marks[1]) / Ts, ph
 
 
 def smoother_block_multi(rbslam, world):
@@ -257,7 +262,7 @@ def smoother_block_multi(rbslam, world):
         ms_step, ph = _c5_sweep_ms(ctx, a, pr["dt"], Ts)
     return {"c5_ms_per_step": ms_step, "c5_s_per_sweep": ms_step * 5000 / 1e3, "n_gpus": world,
             "c5_ancestor_ms_per_step": ph["ancestor"] / (Ts - 1),
-            "c5": "information form, N=4096, M=515: one sweep with ancestor weights (N_K=3 call minus N_K=1 call, over 2) on a T=%d slice, extrapolated to T=5000; "
+            "c5": "information form, N=4096, M=515: one whole sweep with ancestor weights (between the sweep-end callbacks of sweeps 2 and 3 of an N_K=3 call) on a T=%d slice, extrapolated to T=5000; "
                   "%d GPUs as one replica group (every GPU runs the filter part, the ancestor weights are split "
                   "%d ways and all-gathered over peer memory)" % (Ts, world, world)}
 
@@ -292,7 +297,7 @@ def smoother_block(rbslam, device):
     peak, src = fp64_peak()
     out.update({
         "c5_ms_per_step": ms_step, "c5_s_per_sweep": ms_step * 5000 / 1e3,
-        "c5": "information form, N=4096, M=515: one sweep with ancestor weights (N_K=3 call minus N_K=1 call, over 2) on a T=%d slice, extrapolated to T=5000; one GPU" % Ts,
+        "c5": "information form, N=4096, M=515: one whole sweep with ancestor weights (between the sweep-end callbacks of sweeps 2 and 3 of an N_K=3 call) on a T=%d slice, extrapolated to T=5000; one GPU" % Ts,
         "c5_ancestor_ms_per_step": anc_ms,
         "fp64_tflops": flops / (anc_ms / 1e3) / 1e12, "fp64_peak_tflops": peak, "fp64_peak_source": src,
         "fp64_frac": flops / (anc_ms / 1e3) / 1e12 / peak,

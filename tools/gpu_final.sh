@@ -4,8 +4,8 @@ mkdir -p gpurun_out
 tag=${1:-fin}
 timeout 2400 python -m pytest tests -q -m gpu --timeout 1200 > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$?"
 tail -6 gpurun_out/${tag}_tests.log
-for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_small.py all > gpurun_out/${tag}_san_$tool.log 2>&1; echo "sanitizer $tool rc=$?"
+for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_small.py ${SAN_WHAT:-all} > gpurun_out/${tag}_san_$tool.log 2>&1; echo "sanitizer $tool rc=$?"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|ok " gpurun_out/${tag}_san_$tool.log | tail -12
 done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-smoother --e2e-steps 8 > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "launch list rc=$?"
