@@ -614,8 +614,22 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
             buf = (buf + 1 == NS) ? 0 : buf + 1;
             nbuf = (nbuf + 1 == NS) ? 0 : nbuf + 1;
           }
-          __syncthreads();                       // the ring is free: its head becomes the C tile
         }
+        // the addends of this tile (A1 was prefetched towards L2, A2 is shared by every matrix): all loads of a
+        // thread are issued BEFORE the barrier that frees the ring, so their latency overlaps the barrier and the
+        // prefetch below.  A thread owns C(rows wr + 8 mi + 2 tg + {0, 1}, column 8 nj + gq) (swapped operands).
+        const bool interior = ti >= jb + RB_CH_NB && ti + TR <= n;   // all rows below the diagonal block, above row n
+        double2 c1[2][4];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj) {
+            const int gr = ti + wr + 8 * mi + 2 * tg, gc = min(jb + 8 * nj + gq, n - 1);
+            const double *p1 = A1 + (size_t)gc * a.lda1;
+            if (interior && v1ok) c1[mi][nj] = *reinterpret_cast<const double2 *>(p1 + gr);
+            else c1[mi][nj] = make_double2(p1[min(gr, n - 1)], p1[min(gr + 1, n - 1)]);
+          }
+        if (jb > 0) __syncthreads();             // the ring is free: its head becomes the C tile
         // stage 0 of the NEXT tile into the last ring buffer: it lands while this tile's epilogue, diagonal
         // block and panel product run.  Next tile: the next 64 rows of this panel, or the first tile of the
         // next panel -- whose stage 0 (columns 0 .. KC-1) is final unless this is panel 0.
@@ -630,65 +644,42 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
             pre = true;
           }
         }
-        // C = A1 + A2 [+ jitter I] - L L' (row n: the right-hand side), into shared memory as an A operand.
-        // The products run with the operands swapped, so a thread holds C(rows wr + 8 mi + 2 tg + {0, 1},
-        // column 8 nj + gq): two consecutive rows of a column -- 16-byte loads of the addend where its
-        // leading dimension allows, conflict-free 16-byte stores of the tile.
-        if (ti >= jb + RB_CH_NB && ti + TR <= n) {
-          // interior tile: all rows below the diagonal block and above the right-hand-side row; all 24 loads of
-          // a thread in flight together (the A1 tile was prefetched towards L2, A2 is shared by every matrix)
-          double2 c1[2][4], c2[2][4];
+        if (a.A2) {
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj) {
-              const double *p1 = A1 + (ti + wr + 8 * mi + 2 * tg) + (size_t)(jb + 8 * nj + gq) * a.lda1;
-              if (v1ok) c1[mi][nj] = *reinterpret_cast<const double2 *>(p1);
-              else c1[mi][nj] = make_double2(p1[0], p1[1]);
+              const int gr = ti + wr + 8 * mi + 2 * tg, gc = min(jb + 8 * nj + gq, n - 1);
+              const double *p2 = a.A2 + (size_t)gc * a.lda2;
+              c1[mi][nj].x += p2[min(gr, n - 1)];
+              c1[mi][nj].y += p2[min(gr + 1, n - 1)];
             }
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-            for (int nj = 0; nj < 4; ++nj) {
-              if (a.A2) {
-                const double *p2 = a.A2 + (ti + wr + 8 * mi + 2 * tg) + (size_t)(jb + 8 * nj + gq) * a.lda2;
-                c2[mi][nj] = make_double2(p2[0], p2[1]);
-              } else {
-                c2[mi][nj] = make_double2(0.0, 0.0);
-              }
-            }
+        }
+        // C = A1 + A2 [+ jitter I] - L L' (row n: the right-hand side), into shared memory as an A operand:
+        // conflict-free 16-byte stores (two consecutive rows of a column per thread)
+        if (interior) {
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj)
               *reinterpret_cast<double2 *>(As + (8 * nj + gq) * LDA_T + wr + 8 * mi + 2 * tg) =
-                  make_double2((c1[mi][nj].x + c2[mi][nj].x) - acc[mi][nj][0], (c1[mi][nj].y + c2[mi][nj].y) - acc[mi][nj][1]);
+                  make_double2(c1[mi][nj].x - acc[mi][nj][0], c1[mi][nj].y - acc[mi][nj][1]);
         } else {
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
-            double c1[4][2], c2[4][2];
-#pragma unroll
-            for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int gr = min(ti + wr + 8 * mi + 2 * tg + e, n - 1), gc = min(jb + 8 * nj + gq, n - 1);
-                c1[nj][e] = A1[gr + (size_t)gc * a.lda1];
-                c2[nj][e] = a.A2 ? a.A2[gr + (size_t)gc * a.lda2] : 0.0;
-              }
+          for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj) {
               double v2[2];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int gr = ti + wr + 8 * mi + 2 * tg + e, gc = jb + 8 * nj + gq;
-                double v = c1[nj][e] + c2[nj][e] + (gr == gc ? jit : 0.0);
+                double v = (e ? c1[mi][nj].y : c1[mi][nj].x) + (gr == gc ? jit : 0.0);
                 if (gr == n && gc < n) v = a.rhs[(size_t)b * a.stride_rhs + gc] + (a.rhs2 ? a.rhs2[gc] : 0.0);
                 v -= acc[mi][nj][e];
                 v2[e] = (gc < n && gr >= gc && gr <= n) ? v : 0.0;
               }
               *reinterpret_cast<double2 *>(As + (8 * nj + gq) * LDA_T + wr + 8 * mi + 2 * tg) = make_double2(v2[0], v2[1]);
             }
-          }
         }
         __syncthreads();
         if (ti == jb) {
@@ -773,17 +764,20 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
           for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj) out[mi][nj][0] = out[mi][nj][1] = 0.0;
+          // X = L11^-1 is lower triangular: X(j, c) = 0 for c > j, so column tile nj only needs c < 8 (nj + 1)
 #pragma unroll
           for (int kk = 0; kk < 32; kk += 4) {
             double av[2], bv[4];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) av[mi] = As[(kk + tg) * LDA_T + wr + 8 * mi + gq];
 #pragma unroll
-            for (int nj = 0; nj < 4; ++nj) bv[nj] = sX[(kk + tg) * LDB + 8 * nj + gq];
+            for (int nj = 0; nj < 4; ++nj)
+              if (kk < 8 * (nj + 1)) bv[nj] = sX[(kk + tg) * LDB + 8 * nj + gq];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-              for (int nj = 0; nj < 4; ++nj) dmma884(out[mi][nj][0], out[mi][nj][1], bv[nj], av[mi]);
+              for (int nj = 0; nj < 4; ++nj)
+                if (kk < 8 * (nj + 1)) dmma884(out[mi][nj][0], out[mi][nj][1], bv[nj], av[mi]);
           }
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi)
