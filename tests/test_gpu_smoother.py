@@ -226,6 +226,70 @@ def test_ancestor_weights_info_c5_size(rbslam_lib):
     assert np.all(np.abs(got - ref) <= 1e-8 * np.maximum(1.0, np.abs(ref))), (got, ref)
 
 
+@pytest.mark.parametrize("m,nfut", [(5, 1), (29, 2), (30, 11), (61, 21), (62, 22), (93, 32), (125, 43), (126, 5)])
+def test_ancestor_weights_panel_edges(rbslam_lib, m, nfut):
+    """The blocked factorisation at orders around its block sizes (panels of 32 columns, row tiles of 64, the
+    right-hand side as an extra row): K7 with n = M = m + 3 in {8, 32, 33, 64, 65, 96, 128, 129} and K6 with
+    n = 3 nfut in {3, 6, 33, 63, 66, 96, 129, 15}: single narrow panel, exact multiples (the right-hand-side row
+    opens a new tile), one past a multiple (one-column last panel)."""
+    rb = rbslam_lib
+    N = 5
+    pr, om, P, xl, Imat, ivec = _c1_state(rb, m, max(8, nfut + 2), N, seed=100 + m)
+    gm = rb.models.from_problem(pr)
+    rng = np.random.default_rng(m)
+    M = m + 3
+    xnk = np.repeat(pr["x0_nonLin"][:, None], nfut, axis=1) + 0.2 * rng.standard_normal((7, nfut))
+    Hk = om.measModel(xnk)
+    Ri = np.linalg.inv(pr["R"])
+    yk = pr["y"][1:1 + nfut]
+    # information form
+    ImatAddt = sum(Hk[j].T @ Ri @ Hk[j] for j in range(nfut))
+    ivecAddt = sum(Hk[j].T @ Ri @ yk[j] for j in range(nfut))
+    q2 = np.array([ivec[:, i] @ P[i] @ ivec[:, i] for i in range(N)])
+    hld = np.array([0.5 * np.linalg.slogdet(P[i])[1] for i in range(N)])
+    ref1 = np.zeros(N)
+    for i in range(N):
+        cI = np.linalg.cholesky(Imat[i] + ImatAddt)
+        vI = np.linalg.solve(cI, ivec[:, i] + ivecAddt)
+        ref1[i] = -0.5 * q2[i] - hld[i] - np.sum(np.log(np.diag(cI))) + 0.5 * (vI @ vI)
+    with rb.Context(gm, N, 4, information_form=True) as ctx:
+        got1 = ctx.op_ancestor_weights(1, Imat.transpose(1, 2, 0), ivec, ImatAddt, ivecAddt, q2=q2, hld=hld, jitter=-1.0)
+    assert np.all(np.abs(got1 - ref1) <= 1e-8 * np.maximum(1.0, np.abs(ref1))), (got1, ref1)
+    # covariance form
+    D = Hk.reshape(-1, M)
+    yfut = yk.reshape(-1)
+    ne = D.shape[0]
+    RR = np.kron(np.eye(nfut), pr["R"])
+    ref0 = np.zeros(N)
+    for i in range(N):
+        cS = np.linalg.cholesky(D @ P[i] @ D.T + RR)
+        v = np.linalg.solve(cS, yfut - D @ xl[:, i])
+        ref0[i] = -np.sum(np.log(np.diag(cS))) - 0.5 * (v @ v) - ne / 2 * np.log(2 * np.pi)
+    with rb.Context(gm, N, 4) as ctx:
+        got0 = ctx.op_ancestor_weights(0, P.transpose(1, 2, 0), xl, D, yfut, R=pr["R"], jitter=1e-2)
+    assert np.all(np.abs(got0 - ref0) <= 1e-8 * np.maximum(1.0, np.abs(ref0))), (got0, ref0)
+
+
+def test_ancestor_weights_not_positive_definite_is_reported(rbslam_lib):
+    """An indefinite matrix in the batch: the information form raises (quirk Q7: no retry), with the particle
+    named; the others in the batch are unaffected by it on the next call."""
+    rb = rbslam_lib
+    N, m = 4, 61
+    pr, om, P, xl, Imat, ivec = _c1_state(rb, m, 8, N, seed=7)
+    gm = rb.models.from_problem(pr)
+    M = m + 3
+    bad = Imat.copy()
+    bad[2, 40, 40] = -5.0                      # a negative pivot in the second panel of particle 2
+    q2, hld = np.zeros(N), np.zeros(N)
+    with rb.Context(gm, N, 4, information_form=True) as ctx:
+        with pytest.raises(rb.RbslamError, match="particle 2"):
+            ctx.op_ancestor_weights(1, bad.transpose(1, 2, 0), ivec, np.zeros((M, M)), np.zeros(M), q2=q2, hld=hld, jitter=-1.0)
+        ok = ctx.op_ancestor_weights(1, Imat.transpose(1, 2, 0), ivec, np.zeros((M, M)), np.zeros(M), q2=q2, hld=hld, jitter=-1.0)
+    ref = np.array([-np.sum(np.log(np.diag(np.linalg.cholesky(Imat[i])))) +
+                    0.5 * np.sum(np.linalg.solve(np.linalg.cholesky(Imat[i]), ivec[:, i]) ** 2) for i in range(N)])
+    assert np.all(np.abs(ok - ref) <= 1e-8 * np.maximum(1.0, np.abs(ref)))
+
+
 def test_particlesmoother_makeplots_and_progress(rbslam_lib, capsys):
     """The smoother drop-in calls makePlots(xnk,xlk,k,XNK,XLK,PK) and prints the progress line once
     per sweep, when that sweep's outputs exist (src/particleSmoother.m:359-365)."""
