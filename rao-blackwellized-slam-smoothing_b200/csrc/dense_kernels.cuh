@@ -74,6 +74,7 @@ struct GemmArgs {
   const double *B; int ldb; size_t strideB;   // k x n
   double *C; int ldc; size_t strideC;         // m x n
   const double *Rblk; int d;                  // optional: C += kron(I, R) (d x d blocks)
+  int lower = 0;                              // C is symmetric and only read below the diagonal: tiles above it are skipped
 };
 
 template <bool TA>
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256, 2) k_dgemm(GemmArgs g) {
   const double *B = g.B + (size_t)b * g.strideB;
   double *C = g.C + (size_t)b * g.strideC;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
+  if (g.lower && n0 >= m0 + 128) return;   // tile entirely above the diagonal of a symmetric result
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
   double acc[4][4][2];
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(256, 2) k_dgemm_pipe(GemmArgs g) {
   const double *B = g.B + (size_t)b * g.strideB;
   double *C = g.C + (size_t)b * g.strideC;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
+  if (g.lower && n0 >= m0 + 128) return;   // tile entirely above the diagonal of a symmetric result
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
   const int gq = lane >> 2, tg = lane & 3;

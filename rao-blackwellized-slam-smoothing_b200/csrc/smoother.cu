@@ -708,6 +708,7 @@ static int ancestor_weights_cov(rbslam_ctx *ctx, int t, bool use_default_dyn) {
       g2.m = ne; g2.n = ne; g2.k = M; g2.slotA = nullptr;
       g2.B = w->W; g2.ldb = ldw; g2.strideB = sW;
       g2.C = w->SS; g2.ldc = ne; g2.strideC = sS;
+      g2.lower = 1;    // S = D P D' + R is symmetric and the factorisation reads its lower triangle only
       if (sparse) {
         const int o0 = w->obs_off[t];
         k_sparse_future<<<dim3((ne + 127) / 128, cnt), 128, 0, ctx->stream>>>(
@@ -1110,6 +1111,7 @@ extern "C" int rbslam_op_ancestor_weights(rbslam_ctx *ctx, int32_t form, int32_t
     g2.m = ne; g2.n = ne; g2.k = M; g2.A = (const double *)bS.p; g2.lda = (int)ldp; g2.strideA = 0; g2.slotA = nullptr;
     g2.B = (const double *)bW.p; g2.ldb = (int)ldp; g2.strideB = ldp * ne;
     g2.C = (double *)bSS.p; g2.ldc = ne; g2.strideC = (size_t)ne * ne; g2.Rblk = (const double *)bR.p; g2.d = d;
+    g2.lower = 1;
     if ((rc = launch_gemm(ctx, false, g1, N)) || (rc = launch_gemm(ctx, true, g2, N))) return rc;
     c.A1 = (const double *)bSS.p; c.lda1 = ne; c.strideA1 = (size_t)ne * ne; c.slot1 = nullptr; c.A2 = nullptr; c.lda2 = 0;
     c.rhs = (const double *)be.p; c.stride_rhs = ne; c.rhs2 = nullptr;
