@@ -489,16 +489,18 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
 #define RB_CI_TR 64
 #define RB_CI_LDA (RB_CI_TR + 8)
 // KC = columns of L per operand stage, NS = stages in the cp.async ring
-static inline size_t chol_inv_smem(int kc, int ns) {
-  return sizeof(double) * ((size_t)ns * kc * (RB_CI_LDA + RB_CH_LDB) + 32 * RB_CH_LDB);
+static inline size_t chol_inv_smem(int kc, int ns, int nt = 128) {
+  return sizeof(double) * ((size_t)ns * kc * (nt / 2 + 8 + RB_CH_LDB) + 32 * RB_CH_LDB);
 }
 // rows [row0, row0+ROWS) x KC columns of a column-major matrix into a [KC][LD] tile; rows >= nrows are zero
 template <int ROWS, int KC, int LD, int NT>
 __device__ __forceinline__ void stage_rows(double *tile, const double *__restrict__ src, int ld_src, int row0,
                                            int nrows, int tid) {
+  constexpr int TOTAL = (ROWS / 2) * KC;     // 16-byte copies
 #pragma unroll
-  for (int q = 0; q < (ROWS / 2) * KC / NT; ++q) {
+  for (int q = 0; q < (TOTAL + NT - 1) / NT; ++q) {
     const int idx = tid + q * NT;
+    if (TOTAL % NT != 0 && idx >= TOTAL) break;
     const int i2 = idx % (ROWS / 2), k = idx / (ROWS / 2);
     const int r = row0 + 2 * i2;
     const int valid = max(0, min(2, nrows - r));
@@ -512,7 +514,7 @@ __device__ __forceinline__ void stage_rows(double *tile, const double *__restric
 // the per-copy cost of the TMA unit.  profiles/tuning_r2.md section 3.)
 // one operand stage of the panel update for a 16 x 32 warp tile; MASK selects the 8 x 8 tiles (bit 4 mi + nj).
 // Operands swapped: the thread ends up with C(rows 8 mi + 2 tg + {0, 1}, column 8 nj + gq).
-template <int KC, int MASK>
+template <int KC, int MASK, int LDA_T>
 __device__ __forceinline__ void chol_kstep(const double *__restrict__ Ab, const double *__restrict__ Bb,
                                            double (&acc)[2][4][2]) {
 #pragma unroll
@@ -520,7 +522,7 @@ __device__ __forceinline__ void chol_kstep(const double *__restrict__ Ab, const 
     double av[2], bv[4];
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
-      if ((MASK >> (4 * mi)) & 0xf) av[mi] = Ab[kk * RB_CI_LDA + 8 * mi];
+      if ((MASK >> (4 * mi)) & 0xf) av[mi] = Ab[kk * LDA_T + 8 * mi];
 #pragma unroll
     for (int nj = 0; nj < 4; ++nj)
       if ((MASK >> nj) & 0x11) bv[nj] = Bb[kk * RB_CH_LDB + 8 * nj];
@@ -532,9 +534,15 @@ __device__ __forceinline__ void chol_kstep(const double *__restrict__ Ab, const 
   }
 }
 
-template <int KC, int NS, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
-  constexpr int TR = RB_CI_TR, LDA_T = RB_CI_LDA, LDB = RB_CH_LDB, NT = 128;
+// NT threads per matrix: 128 (row tiles of 64, 4 CTAs/SM: large batches) or 512 (row tiles of 256, one
+// CTA per SM: batches that leave SMs idle anyway -- the C1 example has 100 particles -- get a whole SM's
+// warps per matrix, which shortens the serial chain of row tiles per panel 4x)
+template <int KC, int NS, int MINB, int NT>
+__global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
+  constexpr int NW = NT / 32, TR = 16 * NW, LDA_T = TR + 8, LDB = RB_CH_LDB;
+  constexpr int NQ = 32 / NW;                // columns of the diagonal block per thread (pairs: NQ even)
+  static_assert(NW >= 4 && NW <= 16 && (NQ % 2) == 0, "4, 8 or 16 warps");
+  static_assert(NS >= 2 && NS <= 5, "wait_group cases below");
   static_assert(NS * KC >= 32, "the C tile lives in the first 32 columns of the A ring");
   extern __shared__ __align__(128) double sm[];
   double *As = sm;                           // [NS][KC][LDA_T] operand ring; its first 32 columns double as the C tile
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
   double *sX = Bs + NS * KC * LDB;           // [32][LDB]: L11^-1 as a B operand, X(j, c) at c*LDB + j
   double *colb = Bs;
   __shared__ int s_fail;
-  __shared__ double s_red[2][4];
+  __shared__ double s_red[2][NW];
   const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double *A1 = a.A1 + (size_t)(a.slot1 ? a.slot1[b] : b) * a.strideA1;
   double *L = a.L + (size_t)b * a.strideL;
@@ -563,11 +571,10 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
         // the addend tile of A1 towards L2 (one 64-byte piece per thread and half tile): it is read after
         // the operand loop, registers stay free for a fourth CTA per SM
         {
-          const int pc = tid >> 2, pr = (tid & 3) * 16;
-          const int gc = min(jb + pc, n - 1);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int gr = min(ti + pr + 8 * h, n - 1);
+          for (int h = 0; h < 2; ++h) {        // 32 columns x TR / 8 pieces of 64 bytes = 2 per thread
+            const int pc = (tid + h * NT) & 31, pr = ((tid + h * NT) >> 5) * 8;
+            const int gc = min(jb + pc, n - 1), gr = min(ti + pr, n - 1);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(A1 + gr + (size_t)gc * a.lda1));
           }
         }
@@ -599,8 +606,13 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
           int buf = sb, nbuf = (sb + NS - 1) % NS;   // buffer of stage i, buffer stage i + NS - 1 goes to
           for (int i = 0; i < nk; ++i) {
             // stage i has landed when at most min(NS - 2, nk - 1 - i) younger groups are outstanding
-            if (NS >= 3 && i + 1 < nk) asm volatile("cp.async.wait_group %0;" ::"n"(NS >= 3 ? NS - 2 : 0) : "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            {
+              const int rem = nk - 1 - i;
+              if (NS >= 3 && rem >= NS - 2) asm volatile("cp.async.wait_group %0;" ::"n"(NS >= 3 ? NS - 2 : 0) : "memory");
+              else if (NS >= 5 && rem == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+              else if (NS >= 4 && rem == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+              else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
             __syncthreads();                     // everyone's copies of stage i landed; stage i-1's buffer is free
             if (i + NS - 1 < nk) {
               const int k0 = (i + NS - 1) * KC;
@@ -611,9 +623,9 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
             const double *Ab = As + buf * KC * LDA_T + wr + gq + tg * LDA_T, *Bb = Bs + buf * KC * LDB + gq + tg * LDB;
             // the 8 x 8 tiles strictly above the diagonal of the diagonal block are never read: warps 0 and 1
             // of a panel's first tile skip them (6 of their 16 tiles)
-            if (tmask == 0xff) chol_kstep<KC, 0xff>(Ab, Bb, acc);
-            else if (tmask == 0x31) chol_kstep<KC, 0x31>(Ab, Bb, acc);
-            else if (tmask == 0xf7) chol_kstep<KC, 0xf7>(Ab, Bb, acc);
+            if (tmask == 0xff) chol_kstep<KC, 0xff, LDA_T>(Ab, Bb, acc);
+            else if (tmask == 0x31) chol_kstep<KC, 0x31, LDA_T>(Ab, Bb, acc);
+            else if (tmask == 0xf7) chol_kstep<KC, 0xf7, LDA_T>(Ab, Bb, acc);
             buf = (buf + 1 == NS) ? 0 : buf + 1;
             nbuf = (nbuf + 1 == NS) ? 0 : nbuf + 1;
           }
@@ -687,26 +699,26 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
         __syncthreads();
         if (ti == jb) {
           // diagonal block (rows 0..31 of this tile): Cholesky AND inverse by all four warps, right-looking,
-          // TWO columns per block barrier.  Columns 2P, 2P+1 belong to warp P & 3; thread (lane, warp) holds
-          // A(lane, c) and Y(c, lane) for its 8 columns c = 8q + 2 warp + e (Y = L11^-1, built column-oriented
+          // TWO columns per block barrier.  Columns 2P, 2P+1 belong to warp P % NW; thread (lane, warp) holds
+          // A(lane, c) and Y(c, lane) for its 32 / NW columns c = 2 NW q' + 2 warp + e (Y = L11^-1, built column-oriented
           // alongside: as soon as column j of L is final, row j of Y is, and both update what is to their
           // right / below).  Owner: pivot -> rsqrt (one Newton step for the square root) -> column j, its
           // effect on column j+1 inside the warp (shuffles), pivot j+1, both columns and both rows of Y into
           // the double-buffered exchange line; barrier; rank-2 updates by everybody.
           {
-            double x[8], y[8];
+            double x[NQ], y[NQ];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int c = 8 * (q >> 1) + 2 * warp + (q & 1);
+            for (int q = 0; q < NQ; ++q) {
+              const int c = 2 * NW * (q >> 1) + 2 * warp + (q & 1);
               const double v = As[c * LDA_T + lane];
               x[q] = (lane < nb && c < nb) ? v : (c == lane ? 1.0 : 0.0);   // identity padding of a narrow last panel
               y[q] = (c == lane) ? 1.0 : 0.0;
             }
 #pragma unroll
             for (int P = 0; P < 16; ++P) {
-              const int j = 2 * P, qj = 2 * (P >> 2), buf = P & 1;
+              const int j = 2 * P, qj = 2 * (P / NW), buf = P & 1;
               double *cb = colb + buf * 128;     // [4][32]: L(:, j), L(:, j+1), Y(j, :), Y(j+1, :)
-              if (warp == (P & 3)) {
+              if (warp == (P % NW)) {
                 const double d0 = __shfl_sync(0xffffffffu, x[qj], j);
                 double l0 = 0.0, l1 = 0.0, y0 = 0.0, y1 = 0.0;
                 bool bad = !(d0 > 0.0);
@@ -740,8 +752,8 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
               const double lr0 = cb[lane], lr1 = cb[32 + lane];          // L(lane, j), L(lane, j+1)
               const double yl0 = cb[64 + lane], yl1 = cb[96 + lane];     // Y(j, lane), Y(j+1, lane)
 #pragma unroll
-              for (int q = qj; q < 8; ++q) {
-                const int k = 8 * (q >> 1) + 2 * warp + (q & 1);
+              for (int q = qj; q < NQ; ++q) {
+                const int k = 2 * NW * (q >> 1) + 2 * warp + (q & 1);
                 const bool upd = k > j + 1;
                 const double lk0 = upd ? cb[k] : 0.0, lk1 = upd ? cb[32 + k] : 0.0;   // L(k, j), L(k, j+1)
                 x[q] = fma(-lr1, lk1, fma(-lr0, lk0, x[q]));     // A(lane, k) -= L(lane, j) L(k, j) + L(lane, j+1) L(k, j+1)
@@ -750,8 +762,8 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
             }
             if (!s_fail) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int c = 8 * (q >> 1) + 2 * warp + (q & 1);
+              for (int q = 0; q < NQ; ++q) {
+                const int c = 2 * NW * (q >> 1) + 2 * warp + (q & 1);
                 if (c <= lane && lane < nb) L[(jb + lane) + (size_t)(jb + c) * ldl] = x[q];
                 sX[lane * LDB + c] = y[q];                   // X(row c, column lane) as a B operand
               }
@@ -830,7 +842,7 @@ __global__ void __launch_bounds__(128, MINB) k_chol_inv(CholArgs a) {
   __syncthreads();
   if (tid == 0) {
     double l2 = 0.0, v2 = 0.0;
-    for (int q = 0; q < 4; ++q) { l2 += s_red[0][q]; v2 += s_red[1][q]; }
+    for (int q = 0; q < NW; ++q) { l2 += s_red[0][q]; v2 += s_red[1][q]; }
     a.sum_log_diag[b] = l2;
     a.vtv[b] = v2;
   }

@@ -628,8 +628,9 @@ static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
   }
   RB_OPTIN_SMEM(k_chol_solve<128>, chol_solve_smem(128));
   RB_OPTIN_SMEM(k_chol_solve<256>, chol_solve_smem(256));
-  RB_OPTIN_SMEM((k_chol_inv<16, 3, 4>), chol_inv_smem(16, 3));
-  RB_OPTIN_SMEM((k_chol_inv<32, 2, 3>), chol_inv_smem(32, 2));
+  RB_OPTIN_SMEM((k_chol_inv<16, 3, 4, 128>), chol_inv_smem(16, 3));
+  RB_OPTIN_SMEM((k_chol_inv<32, 2, 3, 128>), chol_inv_smem(32, 2));
+  RB_OPTIN_SMEM((k_chol_inv<16, 3, 1, 512>), chol_inv_smem(16, 3, 512));
   if (batch >= panel_min && c.n > RB_CP_NB) {
     // panel by panel across the batch (dense_kernels.cuh): thousands of independent tensor-core tiles
     // per launch instead of 3-4 latency-bound matrices per SM
@@ -666,8 +667,12 @@ static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
     // operand ring: columns per stage x stages, CTAs per SM (tuning: RBSLAM_CHOL_CFG, profiles/tuning_r2.md section 3)
     static int cfg = -1;
     if (cfg < 0) { cfg = 0; if (const char *e = getenv("RBSLAM_CHOL_CFG")) cfg = atoi(e) & 1; }
-    if (cfg == 0) k_chol_inv<16, 3, 4><<<batch, 128, chol_inv_smem(16, 3), ctx->stream>>>(c);
-    else k_chol_inv<32, 2, 3><<<batch, 128, chol_inv_smem(32, 2), ctx->stream>>>(c);
+    // small batches (fewer matrices than SMs x 1.1: the C1 example) get 512 threads per matrix
+    int wide_max = 160;   // read per call: the tests switch between the two shapes inside one process
+    if (const char *e = getenv("RBSLAM_CHOL_WIDE_MAX")) wide_max = atoi(e);
+    if (cfg == 0 && batch <= wide_max) k_chol_inv<16, 3, 1, 512><<<batch, 512, chol_inv_smem(16, 3, 512), ctx->stream>>>(c);
+    else if (cfg == 0) k_chol_inv<16, 3, 4, 128><<<batch, 128, chol_inv_smem(16, 3), ctx->stream>>>(c);
+    else k_chol_inv<32, 2, 3, 128><<<batch, 128, chol_inv_smem(32, 2), ctx->stream>>>(c);
   }
   else k_chol_solve<128><<<batch, 128, chol_solve_smem(128), ctx->stream>>>(c);
   ctx->launches += 1;

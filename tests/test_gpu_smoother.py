@@ -91,7 +91,7 @@ def test_smoother_cov_free_running(rbslam_lib, fam, N, K, kw):
 
 @pytest.mark.parametrize("fam,N,K,kw", [("radio", 20, 3, {"m": 40}), ("radio", 12, 2, {}),
                                         ("mag", 8, 2, {"m": 40, "T": 8}), ("mag", 6, 2, {"m": 253, "T": 6})])
-def test_smoother_information_form(rbslam_lib, fam, N, K, kw):
+def test_smoother_information_form(rbslam_lib, chol_shape, fam, N, K, kw):
     rb = rbslam_lib
     pr, om, gm = _setup(rb, fam, N, **kw)
     T = pr["y"].shape[0]
@@ -174,7 +174,18 @@ def _c1_state(rb, m, T, N, seed):
     return pr, om, P, xl, Imat, ivec
 
 
-def test_ancestor_weights_cov_c1_size(rbslam_lib):
+@pytest.fixture(params=["wide", "narrow"])
+def chol_shape(request, monkeypatch):
+    """The factorisation kernel runs with 512 threads per matrix for small batches and with 128 for large ones
+    (launch_chol); every kernel-level case below runs with both."""
+    if request.param == "narrow":
+        monkeypatch.setenv("RBSLAM_CHOL_WIDE_MAX", "0")
+    else:
+        monkeypatch.delenv("RBSLAM_CHOL_WIDE_MAX", raising=False)
+    return request.param
+
+
+def test_ancestor_weights_cov_c1_size(rbslam_lib, chol_shape):
     """K6 at the C1 shape: M = 515, the full future system of T = 192 steps (d tau = 576)."""
     rb = rbslam_lib
     N, m, T = 8, 512, 193
@@ -199,7 +210,7 @@ def test_ancestor_weights_cov_c1_size(rbslam_lib):
     assert np.all(np.abs(got - ref) <= 1e-8 * np.maximum(1.0, np.abs(ref))), (got, ref)
 
 
-def test_ancestor_weights_info_c5_size(rbslam_lib):
+def test_ancestor_weights_info_c5_size(rbslam_lib, chol_shape):
     """K7 at the C1 / C5 shape: batched 515 x 515 Cholesky of Imat_i + ImatAddt, forward solve,
     quadratic forms (src/particleSmootherInformationForm.m:225-236)."""
     rb = rbslam_lib
@@ -227,7 +238,7 @@ def test_ancestor_weights_info_c5_size(rbslam_lib):
 
 
 @pytest.mark.parametrize("m,nfut", [(5, 1), (29, 2), (30, 11), (61, 21), (62, 22), (93, 32), (125, 43), (126, 5)])
-def test_ancestor_weights_panel_edges(rbslam_lib, m, nfut):
+def test_ancestor_weights_panel_edges(rbslam_lib, chol_shape, m, nfut):
     """The blocked factorisation at orders around its block sizes (panels of 32 columns, row tiles of 64, the
     right-hand side as an extra row): K7 with n = M = m + 3 in {8, 32, 33, 64, 65, 96, 128, 129} and K6 with
     n = 3 nfut in {3, 6, 33, 63, 66, 96, 129, 15}: single narrow panel, exact multiples (the right-hand-side row
@@ -270,7 +281,7 @@ def test_ancestor_weights_panel_edges(rbslam_lib, m, nfut):
     assert np.all(np.abs(got0 - ref0) <= 1e-8 * np.maximum(1.0, np.abs(ref0))), (got0, ref0)
 
 
-def test_ancestor_weights_not_positive_definite_is_reported(rbslam_lib):
+def test_ancestor_weights_not_positive_definite_is_reported(rbslam_lib, chol_shape):
     """An indefinite matrix in the batch: the information form raises (quirk Q7: no retry), with the particle
     named; the others in the batch are unaffected by it on the next call."""
     rb = rbslam_lib
