@@ -2,7 +2,7 @@
 # 8-GPU box: scaling of the sharded filter (strong: 10^4 particles in total, weak: 10^4 per GPU), fused vs
 # fetch-then-pass migration, the C5 smoother slice on all GPUs
 mkdir -p gpurun_out
-tag=c14
+tag=ab
 export RBSLAM_CHOL_KERNEL=solve   # the verified K7 kernel: this call is about scaling
 nvidia-smi -L | wc -l
 run() { # name nproc env...
