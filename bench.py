@@ -477,7 +477,10 @@ def run_cuda(args):
                             "phases_ms_per_step": {("plan" if k == "info" else k): v / K
                                                    for k, v in weak["phases"].items() if v > 0}}
         if world == 1 and not args.no_smoother:
-            line["smoother"] = smoother_block(rbslam, local_rank)
+            try:
+                line["smoother"] = smoother_block(rbslam, local_rank)
+            except Exception as e:      # the filter line must survive a smoother problem
+                line["smoother"] = {"error": str(e)[:200]}
         elif world > 1 and not args.no_smoother:
             try:
                 line["smoother"] = smoother_block_multi(rbslam, world)
