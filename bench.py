@@ -3,7 +3,7 @@
 
 Workload (config C4 of BASELINE.json, the one the metric and the >=70 % target are
 quoted on): dense-mag 3-D SLAM, N = 10^4 particles, m = 1024 basis functions
-(M = 1027 linear states, 84.8 GB of fp64 covariance slabs), synthetic bean-6D
+(M = 1027 linear states, 42.9 GB of packed symmetric fp64 covariance slabs), synthetic bean-6D
 trajectory.  One "step" is one time step of the filter recursion over all N
 particles (resample + propagate + basis/Jacobian + fused gather/log-weight/Kalman
 update + normalise).
@@ -272,7 +272,7 @@ def smoother_block(rbslam, device):
     C1 = the reference's dense-mag example (N_P = 100, m = 512 -> M = 515, T = 192,
     run_dense3D_magfield.m:85,124; N_K = 10, slam-dense-mag/main.m:26) in both forms, whole runs;
     C5 = BASELINE.json configs[4] (information form, N = 4096, M = 515, T = 5000) on a stated T-slice:
-    sweep 2 of an N_K = 2 run, ms per step of the slice times 5000."""
+    one whole sweep with ancestor weights (see _c5_sweep_ms), ms per step of the slice times 5000."""
     out = {}
     pr = rbslam.synth.dense_mag_problem(N_T=192, m=512, seed=1, n_laps=3, m_sim=2000)
     gm = rbslam.models.from_problem(pr)
