@@ -475,19 +475,21 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
 // panel, 20 % with three warps waiting for the one that factors the diagonal block in shared memory):
 //   * the C tile of a row tile never goes to global memory: accumulators -> shared memory in the
 //     A-operand layout of the next product;
-//   * the 32 x 32 diagonal block is factored AND inverted by all four warps together, right-looking,
-//     one block barrier per column (a single warp in registers took 53 k cycles per block: 28 % of
-//     the kernel with three warps waiting, ncu source page of the first version);
+//   * the 32 x 32 diagonal block is factored AND inverted by all warps together, right-looking, two
+//     columns per block barrier (a single warp in registers took 53 k cycles per block: 28 % of the
+//     kernel with three warps waiting, ncu source page of the first version);
 //   * the panel solve L21 = C21 L11^-T is one more tensor-core product C21 * (L11^-1)' per row
-//     tile (K = 32), instead of 496 dependent FMAs per row;
+//     tile (K <= 32: the zero half of the triangular inverse is skipped), instead of 496 dependent
+//     FMAs per row;
 //   * the addend tile of A1 is prefetched towards L2 before the operand loop and read after it;
-//   * operand ring of NS stages of KC columns, ONE block barrier per stage.
+//   * operand ring of NS stages of KC columns, ONE block barrier per stage, stage 0 of the next tile
+//     issued before the epilogue of the current one;
+//   * products with swapped operands (a thread owns two consecutive rows of a column: 16-byte
+//     accesses), ragged tiles skip padded warps and the tiles above the diagonal.
 // A narrower last panel is padded with an identity block.  Same arguments and results as
 // k_chol_solve (which stays as the retry kernel of the across-the-batch path and as
 // RBSLAM_CHOL_KERNEL=solve).
 // ---------------------------------------------------------------------------
-#define RB_CI_TR 64
-#define RB_CI_LDA (RB_CI_TR + 8)
 // KC = columns of L per operand stage, NS = stages in the cp.async ring
 static inline size_t chol_inv_smem(int kc, int ns, int nt = 128) {
   return sizeof(double) * ((size_t)ns * kc * (nt / 2 + 8 + RB_CH_LDB) + 32 * RB_CH_LDB);

@@ -29,6 +29,7 @@ struct SmootherWs {
   std::vector<int> obs_off;     // first row of step t in the obs list
   int n_obs = 0;
   size_t batch = 0, ntau_max = 0;
+  std::vector<double> Rinv_h;   // host copy of inv(R): the per-step R^-1 y needs no device round trip
   // information form
   double *ImatAddt = nullptr, *ivecAddt = nullptr, *NHR4 = nullptr, *HRy = nullptr, *q2 = nullptr;
   double *Rinv = nullptr;
@@ -315,7 +316,7 @@ struct InnovInfoArgs {
   const double *hld_old;
   double *hld_new;
   double *q2;              // [N] ivec' P ivec after the update
-  const double *Riy;       // [d] R^-1 y
+  double Riy[4];           // R^-1 y, by value (a kernel argument: no copy, no synchronisation)
   double yRy_const;        // -1/2*y/R*y' - 1/2*log((2*pi)^d*det(R))
   double half_logdetR;
 };
@@ -499,15 +500,12 @@ static int info_kalman_phase_d(rbslam_ctx *ctx, const double *y_t_dev, const dou
   const int *anc = resampled ? ctx->d_Ahist + (size_t)(ctx->t % ctx->T_hist) * N : nullptr;
   // R^-1 y and the constant of the weight (:303-304)
   double Riy[4] = {0, 0, 0, 0}, yRy = 0.0;
-  std::vector<double> Rinv_h((size_t)d * d);
-  CK(cudaMemcpyAsync(Rinv_h.data(), w->Rinv, sizeof(double) * d * d, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if ((int)w->Rinv_h.size() != d * d) return ctx->fail(RBSLAM_EARG, "information form: inv(R) is set by the smoother run");
+  const std::vector<double> &Rinv_h = w->Rinv_h;   // no stream synchronisation inside the step loop
   for (int a = 0; a < d; ++a) {
     for (int b = 0; b < d; ++b) Riy[a] += Rinv_h[a + b * d] * y_t_host[b];
   }
   for (int a = 0; a < d; ++a) yRy += y_t_host[a] * Riy[a];
-  double *Riy_dev = ctx->d_scratch + 16;
-  CK(cudaMemcpyAsync(Riy_dev, Riy, sizeof(double) * 4, cudaMemcpyHostToDevice, ctx->stream));
   k_info_prep<<<N, 128, 0, ctx->stream>>>(M, ld, d, ctx->d_H, w->Rinv, y_t_dev, ctx->d_ivec[ctx->cx],
                                           anc, w->NHR4, w->HRy);
   ctx->launches += 1;
@@ -564,7 +562,7 @@ static int info_kalman_phase_d(rbslam_ctx *ctx, const double *y_t_dev, const dou
   ia.base.status = ctx->d_status; ia.base.t = ctx->t;
   ia.HRy = w->HRy; ia.ivec_old = ctx->d_ivec[ctx->cx]; ia.ivec_new = ctx->d_ivec[1 - ctx->cx];
   ia.hld_old = ctx->d_hld[ctx->cx]; ia.hld_new = ctx->d_hld[1 - ctx->cx]; ia.q2 = w->q2;
-  ia.Riy = Riy_dev;
+  for (int a = 0; a < 4; ++a) ia.Riy[a] = Riy[a];
   ia.half_logdetR = w->half_logdetR;
   ia.yRy_const = -0.5 * yRy - 0.5 * (d * RB_LOG2PI + 2.0 * w->half_logdetR);
   k_innov4_info<D><<<N, 128, sizeof(double) * 8 * ld, ctx->stream>>>(ia);
@@ -919,6 +917,7 @@ static int smoother_run_impl(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N
     if (!(det > 0)) return ctx->fail(RBSLAM_EARG, "R must be positive definite");
     w->half_logdetR = 0.5 * std::log(det);
     if ((rc = rb_h2d(ctx, w->Rinv, Ri.data(), sizeof(double) * d * d))) return rc;
+    w->Rinv_h = Ri;
   }
 
   std::vector<int> h_ak(N_K, 0);
