@@ -539,6 +539,28 @@ __device__ __forceinline__ void chol_kstep(const double *__restrict__ Ab, const 
 // NT threads per matrix: 128 (row tiles of 64, 4 CTAs/SM: large batches) or 512 (row tiles of 256, one
 // CTA per SM: batches that leave SMs idle anyway -- the C1 example has 100 particles -- get a whole SM's
 // warps per matrix, which shortens the serial chain of row tiles per panel 4x)
+// warp 0 of a panel's first tile when the panel's few last rows ("tail": at most 8 rows, staged into rows
+// TR .. TR+7 of the A stages) ride along: its own three tiles (mask 0x31) plus the four tiles of the tail rows,
+// kept in the accumulators of the tiles it skips: tail column tile nj -> acc[0][1], acc[0][2], acc[0][3], acc[1][2].
+template <int KC, int LDA_T, int TR>
+__device__ __forceinline__ void chol_kstep_tail(const double *__restrict__ Ab, const double *__restrict__ Bb,
+                                                double (&acc)[2][4][2]) {
+#pragma unroll
+  for (int kk = 0; kk < KC; kk += 4) {
+    const double a0 = Ab[kk * LDA_T], a1 = Ab[kk * LDA_T + 8], at = Ab[kk * LDA_T + TR];
+    double bv[4];
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj) bv[nj] = Bb[kk * RB_CH_LDB + 8 * nj];
+    dmma884(acc[0][0][0], acc[0][0][1], bv[0], a0);
+    dmma884(acc[1][0][0], acc[1][0][1], bv[0], a1);
+    dmma884(acc[1][1][0], acc[1][1][1], bv[1], a1);
+    dmma884(acc[0][1][0], acc[0][1][1], bv[0], at);
+    dmma884(acc[0][2][0], acc[0][2][1], bv[1], at);
+    dmma884(acc[0][3][0], acc[0][3][1], bv[2], at);
+    dmma884(acc[1][2][0], acc[1][2][1], bv[3], at);
+  }
+}
+
 template <int KC, int NS, int MINB, int NT>
 __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
   constexpr int NW = NT / 32, TR = 16 * NW, LDA_T = TR + 8, LDB = RB_CH_LDB;
@@ -569,7 +591,16 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
     __syncthreads();
     for (int jb = 0; jb < n; jb += RB_CH_NB) {
       const int nb = min(RB_CH_NB, n - jb);
-      for (int ti = jb; ti < nr; ti += TR) {
+      // A panel whose row count leaves a remainder of at most 8 rows (n = 515: the last three rows and the
+      // right-hand side, on every second panel) would spend a whole operand loop on a 64-row tile with one
+      // useful 8-row slice.  Those "tail" rows ride with the panel's FIRST tile instead: they are staged into
+      // the 8 padding rows of the A stages, warp 0 -- which skips five of its eight tiles there -- multiplies
+      // them, and their C values and panel product use the padding rows of the C tile.
+      const int trem = (nr - jb) % TR;
+      const bool tail = NT == 128 && nr - jb > TR && trem > 0 && trem <= 8;
+      const int trow0 = nr - trem;             // first tail row (even: jb + a multiple of TR)
+      const int nr_t = tail ? trow0 : nr;      // rows covered by regular tiles
+      for (int ti = jb; ti < nr_t; ti += TR) {
         // the addend tile of A1 towards L2 (one 64-byte piece per thread and half tile): it is read after
         // the operand loop, registers stay free for a fourth CTA per SM
         {
@@ -590,7 +621,18 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
         // most of it in the late panels where K is largest)
         const bool wact = ti + wr < nr;
         // tiles (mi, nj) of this warp that are multiplied: bit 4 mi + nj
-        const int tmask = !wact ? 0 : (ti != jb || warp > 1) ? 0xff : (warp == 0 ? 0x31 : 0xf7);
+        const bool tile0 = ti == jb;
+        const bool tailw = tail && tile0 && warp == 0;
+        const int tmask = !wact ? 0 : (!tile0 || warp > 1) ? 0xff : (warp == 0 ? (tail ? 0x131 : 0x31) : 0xf7);
+        // tail rows of this panel into rows TR .. TR+7 of an A stage (4 row pairs x KC columns)
+        auto stage_tail = [&](double *Astage, int k0, int row0) {
+          if (tid < 4 * KC) {
+            const int i2 = tid & 3, kc = tid >> 2;
+            const int r = row0 + 2 * i2;
+            const int valid = max(0, min(2, nr - r));
+            cp_async16(Astage + kc * LDA_T + TR + 2 * i2, L + (size_t)(k0 + kc) * ldl + (valid ? r : 0), 8 * valid);
+          }
+        };
         __syncthreads();                         // ring + C tile + sX readers of the previous tile are done
         if (jb > 0) {
           const int nk = jb / KC;
@@ -603,6 +645,7 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
               const int bq = (sb + s0) % NS;
               stage_rows<TR, KC, LDA_T, NT>(As + bq * KC * LDA_T, L + (size_t)(s0 * KC) * ldl, ldl, ti, nr, tid);
               stage_rows<32, KC, LDB, NT>(Bs + bq * KC * LDB, L + (size_t)(s0 * KC) * ldl, ldl, jb, n, tid);
+              if (tail && tile0) stage_tail(As + bq * KC * LDA_T, s0 * KC, trow0);
               asm volatile("cp.async.commit_group;" ::: "memory");
             }
           int buf = sb, nbuf = (sb + NS - 1) % NS;   // buffer of stage i, buffer stage i + NS - 1 goes to
@@ -620,6 +663,7 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
               const int k0 = (i + NS - 1) * KC;
               stage_rows<TR, KC, LDA_T, NT>(As + nbuf * KC * LDA_T, L + (size_t)k0 * ldl, ldl, ti, nr, tid);
               stage_rows<32, KC, LDB, NT>(Bs + nbuf * KC * LDB, L + (size_t)k0 * ldl, ldl, jb, n, tid);
+              if (tail && tile0) stage_tail(As + nbuf * KC * LDA_T, k0, trow0);
               asm volatile("cp.async.commit_group;" ::: "memory");
             }
             const double *Ab = As + buf * KC * LDA_T + wr + gq + tg * LDA_T, *Bb = Bs + buf * KC * LDB + gq + tg * LDB;
@@ -628,6 +672,7 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
             if (tmask == 0xff) chol_kstep<KC, 0xff, LDA_T>(Ab, Bb, acc);
             else if (tmask == 0x31) chol_kstep<KC, 0x31, LDA_T>(Ab, Bb, acc);
             else if (tmask == 0xf7) chol_kstep<KC, 0xf7, LDA_T>(Ab, Bb, acc);
+            else if (tmask == 0x131) chol_kstep_tail<KC, LDA_T, TR>(Ab, Bb, acc);
             buf = (buf + 1 == NS) ? 0 : buf + 1;
             nbuf = (nbuf + 1 == NS) ? 0 : nbuf + 1;
           }
@@ -652,11 +697,15 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
         // next panel -- whose stage 0 (columns 0 .. KC-1) is final unless this is panel 0.
         pre = false;
         if (NS >= 3) {
-          const bool same = ti + TR < nr;
+          const bool same = ti + TR < nr_t;
           const int njb = same ? jb : jb + RB_CH_NB, nti = same ? ti + TR : jb + RB_CH_NB;
           if (jb > 0 && njb < n) {
             stage_rows<TR, KC, LDA_T, NT>(As + (NS - 1) * KC * LDA_T, L, ldl, nti, nr, tid);
             stage_rows<32, KC, LDB, NT>(Bs + (NS - 1) * KC * LDB, L, ldl, njb, n, tid);
+            if (!same) {                         // the next panel's first tile: its tail rows, if it has a tail
+              const int nrem = (nr - njb) % TR;
+              if (NT == 128 && nr - njb > TR && nrem > 0 && nrem <= 8) stage_tail(As + (NS - 1) * KC * LDA_T, 0, nr - nrem);
+            }
             asm volatile("cp.async.commit_group;" ::: "memory");
             pre = true;
           }
@@ -697,6 +746,24 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
               }
               *reinterpret_cast<double2 *>(As + (8 * nj + gq) * LDA_T + wr + 8 * mi + 2 * tg) = make_double2(v2[0], v2[1]);
             }
+        }
+        if (tailw) {
+          // C values of the tail rows into the padding rows TR .. TR+7 of the C tile
+          const double (*ts[4])[2] = {&acc[0][1], &acc[0][2], &acc[0][3], &acc[1][2]};
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj) {
+            double v2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int gr = trow0 + 2 * tg + e, gc = jb + 8 * nj + gq;   // gr > gc always (rows below the panel)
+              const int cr = min(gr, n - 1), cc = min(gc, n - 1);
+              double v = A1[cr + (size_t)cc * a.lda1] + (a.A2 ? a.A2[cr + (size_t)cc * a.lda2] : 0.0);
+              if (gr == n && gc < n) v = a.rhs[(size_t)b * a.stride_rhs + gc] + (a.rhs2 ? a.rhs2[gc] : 0.0);
+              v -= (*ts[nj])[e];
+              v2[e] = (gc < n && gr <= n) ? v : 0.0;
+            }
+            *reinterpret_cast<double2 *>(As + (8 * nj + gq) * LDA_T + TR + 2 * tg) = make_double2(v2[0], v2[1]);
+          }
         }
         __syncthreads();
         if (ti == jb) {
@@ -811,6 +878,30 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
                 }
               }
             }
+        } else if (tailw) {
+          // the tail rows' part of the panel: warp 0 has no rows below the diagonal block in this tile
+          double outt[4][2];
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj) outt[nj][0] = outt[nj][1] = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 32; kk += 4) {
+            const double at = As[(kk + tg) * LDA_T + TR + gq];
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj)
+              if (kk < 8 * (nj + 1)) dmma884(outt[nj][0], outt[nj][1], sX[(kk + tg) * LDB + 8 * nj + gq], at);
+          }
+#pragma unroll
+          for (int nj = 0; nj < 4; ++nj) {
+            const int gr = trow0 + 2 * tg, gc = jb + 8 * nj + gq;
+            if (gc < n) {
+              double *dst = L + gr + (size_t)gc * ldl;
+              if (gr + 1 < nr) {
+                *reinterpret_cast<double2 *>(dst) = make_double2(outt[nj][0], outt[nj][1]);
+              } else if (gr < nr) {
+                dst[0] = outt[nj][0];
+              }
+            }
+          }
         }
       }
       __syncthreads();
