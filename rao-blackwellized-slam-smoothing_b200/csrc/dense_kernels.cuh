@@ -583,6 +583,7 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
   const int gq = lane >> 2, tg = lane & 3;
   const int wr = warp * 16;                  // warp tile: 16 rows x 32 columns = 2 x 4 DMMA tiles
   const bool v1ok = ((a.lda1 & 1) == 0) && ((a.strideA1 & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.A1) & 15) == 0);
+  const bool v2ok = ((a.lda2 & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.A2) & 15) == 0);
   bool ok = false;
   for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
     const double jit = attempt ? a.jitter : 0.0;
@@ -711,15 +712,20 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
           }
         }
         if (a.A2) {
+          double2 c2[2][4];
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int nj = 0; nj < 4; ++nj) {
               const int gr = ti + wr + 8 * mi + 2 * tg, gc = min(jb + 8 * nj + gq, n - 1);
               const double *p2 = a.A2 + (size_t)gc * a.lda2;
-              c1[mi][nj].x += p2[min(gr, n - 1)];
-              c1[mi][nj].y += p2[min(gr + 1, n - 1)];
+              if (interior && v2ok) c2[mi][nj] = *reinterpret_cast<const double2 *>(p2 + gr);
+              else c2[mi][nj] = make_double2(p2[min(gr, n - 1)], p2[min(gr + 1, n - 1)]);
             }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj) { c1[mi][nj].x += c2[mi][nj].x; c1[mi][nj].y += c2[mi][nj].y; }
         }
         // C = A1 + A2 [+ jitter I] - L L' (row n: the right-hand side), into shared memory as an A operand:
         // conflict-free 16-byte stores (two consecutive rows of a column per thread)
@@ -792,14 +798,17 @@ __global__ void __launch_bounds__(NT, MINB) k_chol_inv(CholArgs a) {
                 double l0 = 0.0, l1 = 0.0, y0 = 0.0, y1 = 0.0;
                 bool bad = !(d0 > 0.0);
                 if (!bad) {
+                  // critical chain: rsqrt -> scaled column -> L(j+1, j) -> column j+1 -> its pivot -> rsqrt.
+                  // The square roots themselves (one Newton step each) and the diagonal selects hang off it.
                   const double r0 = rsqrt(d0);
+                  const double lo0 = x[qj] * r0;                             // column j below the diagonal (lanes > j)
+                  const double l10 = __shfl_sync(0xffffffffu, lo0, j + 1);   // L(j+1, j)
+                  const double x1 = fma(-lo0, l10, x[qj + 1]);               // column j+1 (lanes > j)
+                  const double d1 = __shfl_sync(0xffffffffu, x1, j + 1);
                   double s0 = d0 * r0;
                   s0 = fma(fma(-s0, s0, d0), 0.5 * r0, s0);
-                  l0 = (lane == j) ? s0 : (lane > j ? x[qj] * r0 : 0.0);
+                  l0 = (lane == j) ? s0 : (lane > j ? lo0 : 0.0);
                   y0 = y[qj] * r0;
-                  const double l10 = __shfl_sync(0xffffffffu, l0, j + 1);   // L(j+1, j)
-                  const double x1 = fma(-l0, l10, x[qj + 1]);
-                  const double d1 = __shfl_sync(0xffffffffu, x1, j + 1);
                   bad = !(d1 > 0.0);
                   if (!bad) {
                     const double r1 = rsqrt(d1);

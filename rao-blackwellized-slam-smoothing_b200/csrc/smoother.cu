@@ -261,10 +261,10 @@ __global__ void k_info_init_vec(int N, int M, const double *__restrict__ P0, con
 // (...InformationForm.m:132-146): ImatAddt = sum_jj H_jj'/R*H_jj, ivecAddt = sum_jj H_jj'/R*y_jj
 __global__ void k_addt(int M, int d, int T0, int T1, double sign, const double *__restrict__ Hk,
                        int ldh, const double *__restrict__ Rinv, const double *__restrict__ y,
-                       double *__restrict__ ImatAddt, double *__restrict__ ivecAddt, int init) {
+                       double *__restrict__ ImatAddt, int lda, double *__restrict__ ivecAddt, int init) {
   const int c = blockIdx.x;
   for (int r = threadIdx.x; r < M; r += blockDim.x) {
-    double acc = init ? 0.0 : ImatAddt[r + (size_t)c * M];
+    double acc = init ? 0.0 : ImatAddt[r + (size_t)c * lda];
     double av = (init || c != 0) ? 0.0 : ivecAddt[r];
     for (int jj = T0; jj < T1; ++jj) {
       const double *H = Hk + (size_t)jj * d * ldh;
@@ -278,7 +278,7 @@ __global__ void k_addt(int M, int d, int T0, int T1, double sign, const double *
       acc += sign * term;
       av += sign * tv;
     }
-    ImatAddt[r + (size_t)c * M] = acc;
+    ImatAddt[r + (size_t)c * lda] = acc;
     if (c == 0) ivecAddt[r] = av;
   }
 }
@@ -758,7 +758,7 @@ static int ancestor_weights_info(rbslam_ctx *ctx, int t, bool use_default_dyn) {
   const int N = ctx->N, M = ctx->M, d = ctx->d, n = ctx->n;
   int rc;
   // the suffix sums lose the term of step t-1 (:192-201)
-  k_addt<<<M, 128, 0, ctx->stream>>>(M, d, t - 1, t, -1.0, w->Hk, ctx->ldh, w->Rinv, ctx->d_y, w->ImatAddt,
+  k_addt<<<M, 128, 0, ctx->stream>>>(M, d, t - 1, t, -1.0, w->Hk, ctx->ldh, w->Rinv, ctx->d_y, w->ImatAddt, ctx->ld,
                                      w->ivecAddt, 0);
   ctx->launches += 1;
   const double *xn_old = ctx->d_Xhist + (size_t)((t - 1) % ctx->T_hist) * N * n;
@@ -775,7 +775,7 @@ static int ancestor_weights_info(rbslam_ctx *ctx, int t, bool use_default_dyn) {
     const int cnt = std::min<int>((int)w->batch, bhi - b0);
     CholArgs c{};
     c.n = M; c.A1 = ctx->d_Imat; c.lda1 = ctx->ld; c.strideA1 = ctx->slab; c.slot1 = ctx->d_slot[ctx->cs] + b0;
-    c.A2 = w->ImatAddt; c.lda2 = M; c.L = w->Lw; c.ldl = chol_ldl(M); c.strideL = sL;
+    c.A2 = w->ImatAddt; c.lda2 = ctx->ld; c.L = w->Lw; c.ldl = chol_ldl(M); c.strideL = sL;
     c.rhs = ctx->d_ivec[ctx->cx] + (size_t)b0 * M; c.stride_rhs = M; c.rhs2 = w->ivecAddt;
     c.jitter = -1.0;   // quirk Q7: the reference's retry branch is broken and would raise
     c.sum_log_diag = w->sumlog; c.vtv = w->vtv; c.status = ctx->d_status; c.t = t;
@@ -891,7 +891,7 @@ static int smoother_run_impl(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N
     RB_ALLOC(w->sumlog, w->batch); RB_ALLOC(w->vtv, w->batch);
   }
   if (form == 1) {
-    RB_ALLOC(w->ImatAddt, (size_t)M * M); RB_ALLOC(w->ivecAddt, M);
+    RB_ALLOC(w->ImatAddt, (size_t)ctx->ld * M); RB_ALLOC(w->ivecAddt, M);   // padded leading dimension: 16-byte loads in K7
     RB_ALLOC(w->NHR4, (size_t)N * ctx->ld * 4); RB_ALLOC(w->HRy, (size_t)N * ctx->ld);
     RB_ALLOC(w->q2, N); RB_ALLOC(w->Rinv, (size_t)d * d);
     // R^-1 and log det R on the host (d <= 3)
@@ -936,7 +936,7 @@ static int smoother_run_impl(rbslam_ctx *ctx, const rbslam_inputs *in, int32_t N
         ctx->launches += 1;
       }
       if (form == 1) {
-        k_addt<<<M, 128, 0, ctx->stream>>>(M, d, 0, T, 1.0, w->Hk, ctx->ldh, w->Rinv, ctx->d_y, w->ImatAddt,
+        k_addt<<<M, 128, 0, ctx->stream>>>(M, d, 0, T, 1.0, w->Hk, ctx->ldh, w->Rinv, ctx->d_y, w->ImatAddt, ctx->ld,
                                            w->ivecAddt, 1);
         ctx->launches += 1;
       }
