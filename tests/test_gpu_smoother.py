@@ -301,6 +301,54 @@ def test_ancestor_weights_not_positive_definite_is_reported(rbslam_lib, chol_sha
     assert np.all(np.abs(ok - ref) <= 1e-8 * np.maximum(1.0, np.abs(ref)))
 
 
+def test_ancestor_weights_cov_jitter_retry(rbslam_lib, chol_shape):
+    """K6 with a system matrix that is not positive definite until the reference's retry adds jitter * I
+    (src/particleSmoother.m:221-226): one particle's covariance gets a small negative direction; the batch
+    must factor that matrix in the second attempt (same result as the oracle's chol_jitter) and the others
+    in the first."""
+    rb = rbslam_lib
+    N, m, nfut = 4, 61, 30                       # n = 90: three panels, the last one ragged
+    pr, om, P, xl, _, _ = _c1_state(rb, m, nfut + 2, N, seed=31)
+    gm = rb.models.from_problem(pr)
+    rng = np.random.default_rng(5)
+    M = m + 3
+    xnk = np.repeat(pr["x0_nonLin"][:, None], nfut, axis=1) + 0.2 * rng.standard_normal((7, nfut))
+    D = om.measModel(xnk).reshape(-1, M)
+    yfut = pr["y"][1:1 + nfut].reshape(-1)
+    ne = D.shape[0]
+    R = 1e-3 * np.eye(3)                         # small measurement noise: the perturbation below decides the sign
+    RR = np.kron(np.eye(nfut), R)
+    # particle 1: P1 <- P1 - alpha v v' with D v = z (a unit vector), i.e. S <- S - alpha z z'; alpha by bisection
+    # so that the smallest eigenvalue of S lands at -0.3 * jitter
+    jitter = 1e-2
+    U, sv, Vt = np.linalg.svd(D, full_matrices=False)
+    v = Vt[0] / sv[0]
+    S1 = D @ P[1] @ D.T + RR
+    lo, hi = 0.0, 10.0 * np.linalg.eigvalsh(S1)[-1]
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        if np.linalg.eigvalsh(S1 - mid * np.outer(U[:, 0], U[:, 0]))[0] > -0.3 * jitter:
+            lo = mid
+        else:
+            hi = mid
+    P = P.copy()
+    P[1] = P[1] - lo * np.outer(v, v)
+    lam = np.linalg.eigvalsh(D @ P[1] @ D.T + RR)
+    assert lam[0] < 0 and lam[0] > -jitter, lam[:3]
+    ref = np.zeros(N)
+    used = []
+    for i in range(N):
+        SS = D @ P[i] @ D.T + RR
+        cS, uj = oracle.tools.chol_jitter(SS, jitter)
+        used.append(uj)
+        v = np.linalg.solve(cS, yfut - D @ xl[:, i])
+        ref[i] = -np.sum(np.log(np.diag(cS))) - 0.5 * (v @ v) - ne / 2 * np.log(2 * np.pi)
+    assert used == [False, True, False, False]
+    with rb.Context(gm, N, 4) as ctx:
+        got = ctx.op_ancestor_weights(0, P.transpose(1, 2, 0), xl, D, yfut, R=R, jitter=jitter)
+    assert np.all(np.abs(got - ref) <= 1e-7 * np.maximum(1.0, np.abs(ref))), (got, ref)
+
+
 def test_particlesmoother_makeplots_and_progress(rbslam_lib, capsys):
     """The smoother drop-in calls makePlots(xnk,xlk,k,XNK,XLK,PK) and prints the progress line once
     per sweep, when that sweep's outputs exist (src/particleSmoother.m:359-365)."""
