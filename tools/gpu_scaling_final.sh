@@ -1,7 +1,7 @@
 #!/bin/bash
 # final build on an 8-GPU box: the driver's scaling runs (N = 8, 4, 2), reference arm under torchrun, multi-rank tests over NVLink
 mkdir -p gpurun_out
-tag=c28
+tag=sf
 nvidia-smi -L | wc -l
 run() { # name nproc
   name=$1; np=$2
