@@ -133,6 +133,8 @@ k_apply_pending_pt(double *__restrict__ P, size_t slab, int ld, const int *__res
 struct PtArgs {
   SrcTab st;
   int M, ld, nb, nsplit;
+  int rev;                        // families are walked from the last to the first (sharded filter: migrants, whose
+                                  // slabs come over NVLink, have the highest source keys and start first)
   int ts, ns;                     // tiles per stage, ring slots
   int psplit[RB_PT_MAXSPLIT + 1]; // item sp streams the panels [psplit[sp], psplit[sp+1])
   size_t slab;                    // doubles per slab
@@ -180,7 +182,8 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
   double *s_gpre = s_colp + (size_t)NBUF * NW * 64;                             // [NW][2][32] G fragments, prefetched
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
-  const int n_items = (*f.n_fam) * a.nsplit;
+  const int n_fam = *f.n_fam;
+  const int n_items = n_fam * a.nsplit;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
     for (int s = 0; s < NBUF; ++s) { mbar_init(&colfull[s], NW); mbar_init(&colfree[s], 1); }
@@ -205,7 +208,7 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
         mbar_arrive(&full[slot]);
         break;
       }
-      const int fam = it / a.nsplit, sp = it % a.nsplit;
+      const int fam = a.rev ? n_fam - 1 - it / a.nsplit : it / a.nsplit, sp = it % a.nsplit;
       if (fresh) {
         p = s_psplit[sp]; j = p;
         t_cur = (int)pt_panel_off(nb, p); t_end = (int)pt_panel_off(nb, s_psplit[sp + 1]);
@@ -319,7 +322,7 @@ k_stream_fam_pt(PtArgs a, FamLists f) {
     if (d_item < 0) break;
     if (d_item != s_bat.item || s_desc[slot].b0 != s_bat.b0) {   // a new batch starts (uniform over the consumers)
       if (s_bat.item >= 0) flush_rows();
-      const int fam = d_item / a.nsplit, b0 = s_desc[slot].b0;
+      const int fam = a.rev ? n_fam - 1 - d_item / a.nsplit : d_item / a.nsplit, b0 = s_desc[slot].b0;
       const int first = f.first[fam], nv = min(CB, f.cnt[fam] - b0);
       const int ch0 = f.child[first + b0], ch1 = nv > 1 ? f.child[first + b0 + 1] : -1;
       const double *Ga = src_base(a.st, a.st.G4, a.G4prev, f.anc[fam], (size_t)ld * 4);
