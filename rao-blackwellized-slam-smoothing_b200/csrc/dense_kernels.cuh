@@ -283,7 +283,7 @@ struct CholArgs {
 // more CTAs per SM overlap one matrix's serial panel phases with another's tensor-core phase)
 template <int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) k_chol_solve(CholArgs a) {
-  constexpr int TR = NT / 2, LDA_T = TR + 8, NWARP = NT / 32;
+  constexpr int TR = NT / 2, LDA_T = TR + 8;
   extern __shared__ double sm[];
   double *sD = sm;                           // [32][33] (+ pad to a 16-byte boundary)
   double *As = sD + 32 * 34;                 // [2][32][LDA_T] rows of the row tile, columns k0 .. k0+31

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) k_ekf_predict_meas(EkfArgs a) {
   __shared__ double s_sin[3][RB_MAXTAB], s_cos[3][RB_MAXTAB];     // eigenfun_dx tables, domain [-L, L]
   __shared__ double s_sj[3][RB_MAXTAB], s_cj[3][RB_MAXTAB];       // JacobianPhi3D tables, domain [lo, hi]
   __shared__ double s_red[4];
-  __shared__ double s_q[4], s_R[3][3], s_v[3], s_J[9];
+  __shared__ double s_R[3][3], s_v[3], s_J[9];
   const ModelConsts &mc = a.mc;
   const int M = mc.M, m = mc.m, tid = threadIdx.x;
   if (tid == 0) {
@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(128) k_ekf_predict_meas(EkfArgs a) {
           a.P[r + (size_t)c * a.ld] += s;
         }
     }
-    for (int j = 0; j < 4; ++j) s_q[j] = q[j];
     double Rq[3][3];
     quat2rmat(q, Rq);
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) s_R[r][c] = Rq[r][c];

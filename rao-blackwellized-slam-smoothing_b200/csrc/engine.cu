@@ -888,8 +888,7 @@ static int launch_pt_q(rbslam_ctx *ctx, const KalmanArgs &a, bool resampled) {
     // sharded filter, fused migration: RBSLAM_MIGRANTS_FIRST=1 starts with the families whose slab comes from a
     // peer (highest source keys).  Measured SLOWER on 4 GPUs (weak 15.31 vs 15.11 ms/step, strong 4.57 vs 4.45:
     // every rank would open its pass with NVLink reads), so the default keeps them last (profiles/tuning_r2.md 5)
-    static int mig_first = -1;
-    if (mig_first < 0) { const char *e = getenv("RBSLAM_MIGRANTS_FIRST"); mig_first = (e && atoi(e)) ? 1 : 0; }
+    static const int mig_first = [] { const char *e = getenv("RBSLAM_MIGRANTS_FIRST"); return (e && atoi(e)) ? 1 : 0; }();
     pa.rev = (ctx->st_nloc > 0 && mig_first) ? 1 : 0;
   }
   auto fkern = k_stream_fam_pt<NW, MAXQ>;

@@ -328,7 +328,6 @@ __global__ void __launch_bounds__(128) k_innov4_info(InnovInfoArgs ia) {
   const Innov4Args &a = ia.base;
   const int M = a.M, ld = a.ld;
   double *sPH = sm;              // [ld][4]: P H' (0..D-1) and P ivec (D)
-  double *sG = sm + (size_t)ld * 4;   // [ld][4] gain
   __shared__ double s_red[4][D * D + D + 1];
   __shared__ double s_red2[4][2 * D + 1];
   __shared__ double s_L[D * D], s_SS[D * D], s_e[D];
@@ -590,8 +589,7 @@ static int launch_gemm(rbslam_ctx *ctx, bool ta, const GemmArgs &g, int batch) {
   dim3 grid((g.m + 127) / 128, (g.n + 63) / 64, batch);
   // cp.async-pipelined kernel when every 16-byte copy is aligned (the sweeps allocate their operands that way);
   // otherwise the synchronous-staging kernel
-  static int force_sync = -1;
-  if (force_sync < 0) { const char *e = getenv("RBSLAM_GEMM_SYNC"); force_sync = (e && atoi(e)) ? 1 : 0; }
+  static const int force_sync = [] { const char *e = getenv("RBSLAM_GEMM_SYNC"); return (e && atoi(e)) ? 1 : 0; }();
   const bool aligned = !force_sync && (g.lda % 2 == 0) && (g.ldb % 2 == 0) && (g.strideA % 2 == 0) && (g.strideB % 2 == 0) &&
                        ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B)) & 15) == 0;
   if (aligned) {
@@ -611,19 +609,31 @@ static int launch_gemm(rbslam_ctx *ctx, bool ta, const GemmArgs &g, int batch) {
   return RBSLAM_OK;
 }
 
-static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
-  static int nt = 0, panel_min = 0;
-  if (!nt) {
-    nt = 64;   // 64: k_chol_inv (default); 128 / 256: k_chol_solve with that many threads (RBSLAM_CHOL_KERNEL=solve)
+// tuning switches of the factorisation, read once (thread-safe: the replica group calls this from one host
+// thread per device at the same time)
+struct CholTuning { int nt, panel_min, cfg; };
+static const CholTuning &chol_tuning() {
+  static const CholTuning t = [] {
+    CholTuning v;
+    v.nt = 64;   // 64: k_chol_inv (default); 128 / 256: k_chol_solve with that many threads (RBSLAM_CHOL_KERNEL=solve)
     if (const char *e = getenv("RBSLAM_CHOL_KERNEL"))
-      if (!strcmp(e, "solve")) nt = 128;
-    if (const char *e = getenv("RBSLAM_CHOL_THREADS")) nt = atoi(e) == 256 ? 256 : (atoi(e) == 128 ? 128 : nt);
+      if (!strcmp(e, "solve")) v.nt = 128;
+    if (const char *e = getenv("RBSLAM_CHOL_THREADS")) v.nt = atoi(e) == 256 ? 256 : (atoi(e) == 128 ? 128 : v.nt);
     // batches at least this large go panel by panel across the batch.  Measured at C5 (N = 4096, M = 515):
-    // 21.6 ms per step against 19.8 ms for one CTA per matrix (profiles/tuning_r2.md), so the path is
-    // opt-in (RBSLAM_CHOL_PANEL_MIN=<batch size>) until its two kernels are tuned
-    panel_min = 1 << 30;
-    if (const char *e = getenv("RBSLAM_CHOL_PANEL_MIN")) panel_min = std::max(1, atoi(e));
-  }
+    // 21.6 ms per step against 19.8 ms for k_chol_solve and 10.6 ms for k_chol_inv (profiles/tuning_r2.md), so the
+    // path is opt-in (RBSLAM_CHOL_PANEL_MIN=<batch size>)
+    v.panel_min = 1 << 30;
+    if (const char *e = getenv("RBSLAM_CHOL_PANEL_MIN")) v.panel_min = std::max(1, atoi(e));
+    // operand ring of k_chol_inv: columns per stage x stages, CTAs per SM (profiles/tuning_r2.md section 3)
+    v.cfg = 0;
+    if (const char *e = getenv("RBSLAM_CHOL_CFG")) v.cfg = atoi(e) & 1;
+    return v;
+  }();
+  return t;
+}
+
+static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
+  const int nt = chol_tuning().nt, panel_min = chol_tuning().panel_min;
   RB_OPTIN_SMEM(k_chol_solve<128>, chol_solve_smem(128));
   RB_OPTIN_SMEM(k_chol_solve<256>, chol_solve_smem(256));
   RB_OPTIN_SMEM((k_chol_inv<16, 3, 4, 128>), chol_inv_smem(16, 3));
@@ -662,9 +672,7 @@ static int launch_chol(rbslam_ctx *ctx, const CholArgs &c, int batch) {
   }
   if (nt == 256) k_chol_solve<256><<<batch, 256, chol_solve_smem(256), ctx->stream>>>(c);
   else if (nt == 64) {
-    // operand ring: columns per stage x stages, CTAs per SM (tuning: RBSLAM_CHOL_CFG, profiles/tuning_r2.md section 3)
-    static int cfg = -1;
-    if (cfg < 0) { cfg = 0; if (const char *e = getenv("RBSLAM_CHOL_CFG")) cfg = atoi(e) & 1; }
+    const int cfg = chol_tuning().cfg;
     // small batches (fewer matrices than SMs x 1.1: the C1 example) get 512 threads per matrix
     int wide_max = 160;   // read per call: the tests switch between the two shapes inside one process
     if (const char *e = getenv("RBSLAM_CHOL_WIDE_MAX")) wide_max = atoi(e);
