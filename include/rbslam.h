@@ -217,6 +217,12 @@ RBSLAM_API int rbslam_read_information(rbslam_ctx *ctx, double *ivec, double *Im
 /* counters since context creation: kernels launched by this library, bytes copied */
 RBSLAM_API int rbslam_counters(rbslam_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes,
                     int64_t *d2h_bytes);
+/* diagnostic counters of the device status word since the last rbslam_filter_begin / smoother sweep / op call:
+   chol retries with jitter (src/particleFilter.m:145-148), draws u > wc(end) that were clamped (tools/sample.m
+   would raise an index error), and how many resampling steps needed the exact sequential scan after the
+   parallel fast path could not prove a draw independent of the rounding order.  Synchronises the stream. */
+RBSLAM_API int rbslam_status_counters(rbslam_ctx *ctx, int32_t *used_jitter, int32_t *clamped_draws,
+                           int32_t *exact_scan_runs);
 /* CUDA-event timing on the context's own stream (torch.cuda.Event cannot see it).
    rbslam_event_record marks slot 0..15; rbslam_event_elapsed syncs and returns ms. */
 RBSLAM_API int rbslam_event_record(rbslam_ctx *ctx, int32_t slot);

@@ -26,6 +26,9 @@ struct DevStatus {
   int used_jitter;   // count of jitter retries (informational)
   int clamp_sample;  // count of u > wc(end) clamps (reference would index-error)
   int peer_timeout;  // sharded filter: a peer never reached the barrier (it failed or died)
+  int scan_ambig;    // fast resampling path: a draw could depend on the rounding order of the scan -> exact path
+  int clamp_fast;    // clamps counted by the fast path (added to clamp_sample when it stands)
+  int scan_fallbacks;   // how often the exact path had to run (informational)
 };
 
 // ---------------------------------------------------------------------------

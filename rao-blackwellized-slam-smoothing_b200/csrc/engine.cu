@@ -195,6 +195,11 @@ void rb_phase_end(rbslam_ctx *ctx) {
   ctx->ph_events.push_back(e);
 }
 
+bool rb_fast_scan() {
+  static const bool on = [] { const char *e = getenv("RBSLAM_EXACT_SCAN"); return !(e && atoi(e)); }();
+  return on;
+}
+
 int rb_check_status(rbslam_ctx *ctx) {
   DevStatus st;
   CK(cudaMemcpyAsync(&st, ctx->d_status, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
@@ -538,6 +543,19 @@ extern "C" int rbslam_sync(rbslam_ctx *ctx) {
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));
   return rb_check_status(ctx);
+}
+
+extern "C" int rbslam_status_counters(rbslam_ctx *ctx, int32_t *used_jitter, int32_t *clamped_draws,
+                                      int32_t *exact_scan_runs) {
+  if (!ctx) return RBSLAM_EARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  DevStatus st;
+  CK(cudaMemcpyAsync(&st, ctx->d_status, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (used_jitter) *used_jitter = st.used_jitter;
+  if (clamped_draws) *clamped_draws = st.clamp_sample;
+  if (exact_scan_runs) *exact_scan_runs = st.scan_fallbacks;
+  return RBSLAM_OK;
 }
 
 extern "C" int rbslam_counters(rbslam_ctx *ctx, int64_t *kl, int64_t *h2d, int64_t *d2h) {
@@ -1034,8 +1052,16 @@ int rb_resample_phase(rbslam_ctx *ctx, int n_draws) {
   size_t smem = sizeof(double) * (size_t)N;
   smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
   if (N >= 4096 && n_draws > 1024) {   // scan in one CTA, draws over the grid (N = 10^4: 0.06 ms against 0.17 ms in one CTA)
-    k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, -1, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);
-    k_resample_search<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(N, 0, n_draws, ctx->d_wc, rs, forced, ai, ctx->d_status);
+    // fast path first: parallel prefix sum + draws that prove themselves independent of the rounding order; the
+    // exact pair runs only if a draw could not (step_kernels.cuh).  RBSLAM_EXACT_SCAN=1: exact pair always.
+    const int fast = rb_fast_scan() ? 1 : 0;
+    if (fast) {
+      k_scan_approx<<<1, 1024, 0, ctx->stream>>>(N, ctx->d_w, ctx->d_wc, ctx->d_status);
+      k_search_checked<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(N, 0, n_draws, ctx->d_wc, rs, forced, ai, ctx->d_status);
+      ctx->launches += 2;
+    }
+    k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, -1, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status, fast);
+    k_resample_search<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(N, 0, n_draws, ctx->d_wc, rs, forced, ai, ctx->d_status, fast);
     ctx->launches += 2;
   } else {
     k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, n_draws, ctx->d_w, ctx->d_wc, rs, forced, ai, ctx->d_status);

@@ -42,6 +42,7 @@ static inline int dev_alloc(rbslam_ctx *c, T **p, size_t count) {
     }                                                                                           \
   } while (0)
 
+bool rb_fast_scan();   // resampling: provably exact parallel path first (RBSLAM_EXACT_SCAN=1 turns it off)
 int rb_h2d(rbslam_ctx *ctx, void *dst, const void *src, size_t bytes);
 int rb_d2h(rbslam_ctx *ctx, void *dst, const void *src, size_t bytes);
 void rb_phase_begin(rbslam_ctx *ctx, int id);

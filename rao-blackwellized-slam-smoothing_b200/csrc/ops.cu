@@ -40,8 +40,19 @@ extern "C" int rbslam_op_resample(rbslam_ctx *ctx, int32_t N, const double *w, i
   rs.U = d_u; rs.seed = 0; rs.sweep = 0; rs.t = 0;
   size_t smem = sizeof(double) * (size_t)N;
   smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
-  k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, n_draws, d_w, d_wc, rs, nullptr, d_ai, ctx->d_status);
-  ctx->launches += 1;
+  if (N >= 4096 && n_draws > 1024) {   // the launch sequence of rb_resample_phase for large populations
+    const int fast = rb_fast_scan() ? 1 : 0;
+    if (fast) {
+      k_scan_approx<<<1, 1024, 0, ctx->stream>>>(N, d_w, d_wc, ctx->d_status);
+      k_search_checked<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(N, 0, n_draws, d_wc, rs, nullptr, d_ai, ctx->d_status);
+    }
+    k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, -1, d_w, d_wc, rs, nullptr, d_ai, ctx->d_status, fast);
+    k_resample_search<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(N, 0, n_draws, d_wc, rs, nullptr, d_ai, ctx->d_status, fast);
+    ctx->launches += 2 + 2 * fast;
+  } else {
+    k_resample<<<1, 1024, smem, ctx->stream>>>(N, 0, n_draws, d_w, d_wc, rs, nullptr, d_ai, ctx->d_status);
+    ctx->launches += 1;
+  }
   CK(cudaGetLastError());
   return rb_d2h(ctx, ai, d_ai, sizeof(int) * n_draws);
 }

@@ -410,8 +410,14 @@ int rb_shard_step(rbslam_ctx *ctx) {
     rs.U = nullptr; rs.seed = ctx->cfg.seed; rs.sweep = 0; rs.t = t;
     size_t smem = sizeof(double) * (size_t)gN;
     smem = std::min(smem, std::min(ctx->smem_resample_max, (size_t)(96 << 10)));
-    k_resample<<<1, 1024, smem, ctx->stream>>>(gN, 0, -1, s->g_w, s->g_wc, rs, nullptr, ai, ctx->d_status);
-    k_resample_search<<<(gN + 255) / 256, 256, 0, ctx->stream>>>(gN, 0, gN, s->g_wc, rs, nullptr, ai, ctx->d_status);
+    const int fast = (rb_fast_scan() && gN >= 4096) ? 1 : 0;   // see rb_resample_phase
+    if (fast) {
+      k_scan_approx<<<1, 1024, 0, ctx->stream>>>(gN, s->g_w, s->g_wc, ctx->d_status);
+      k_search_checked<<<(gN + 255) / 256, 256, 0, ctx->stream>>>(gN, 0, gN, s->g_wc, rs, nullptr, ai, ctx->d_status);
+      ctx->launches += 2;
+    }
+    k_resample<<<1, 1024, smem, ctx->stream>>>(gN, 0, -1, s->g_w, s->g_wc, rs, nullptr, ai, ctx->d_status, fast);
+    k_resample_search<<<(gN + 255) / 256, 256, 0, ctx->stream>>>(gN, 0, gN, s->g_wc, rs, nullptr, ai, ctx->d_status, fast);
     ctx->launches += 2;
     rb_phase_end(ctx);
     rb_phase_begin(ctx, RB_PH_INFO);   // reported as the "plan" phase of the sharded filter

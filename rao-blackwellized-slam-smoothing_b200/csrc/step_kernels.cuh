@@ -20,7 +20,8 @@ struct RngSrc {
 __global__ void __launch_bounds__(1024)
 k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__restrict__ wc,
            RngSrc rng, const int *__restrict__ forced, int *__restrict__ ai,
-           DevStatus *status) {
+           DevStatus *status, int only_if_ambiguous = 0) {
+  if (only_if_ambiguous && !status->scan_ambig) return;   // the fast path of this step stands (k_scan_approx)
   // draws for particles i0 .. i0+n_draws-1 (uniform U[i] / Philox counter i, result ai[i]).
   // The scan runs chunk by chunk through shared memory: all threads stage a chunk, ONE thread
   // adds it up left to right (the rounding order is the contract), all threads write it back.
@@ -94,7 +95,15 @@ k_resample(int N, int i0, int n_draws, const double *__restrict__ w, double *__r
 // the draws alone, one thread per draw over the whole grid (large N: the single scanning CTA
 // would otherwise also do N binary searches)
 __global__ void k_resample_search(int N, int i0, int n_draws, const double *__restrict__ wc, RngSrc rng,
-                                  const int *__restrict__ forced, int *__restrict__ ai, DevStatus *status) {
+                                  const int *__restrict__ forced, int *__restrict__ ai, DevStatus *status,
+                                  int only_if_ambiguous = 0) {
+  if (only_if_ambiguous) {
+    if (!status->scan_ambig) {          // the fast path stands: its clamp count becomes the step's
+      if (blockIdx.x == 0 && threadIdx.x == 0 && status->clamp_fast) atomicAdd(&status->clamp_sample, status->clamp_fast);
+      return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&status->scan_fallbacks, 1);
+  }
   const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= i0 + n_draws) return;
   int idx;
@@ -111,6 +120,77 @@ __global__ void k_resample_search(int N, int i0, int n_draws, const double *__re
     if (idx >= N) { idx = N - 1; atomicAdd(&status->clamp_sample, 1); }
   }
   ai[i] = idx;
+}
+
+// ---------------------------------------------------------------------------
+// K5a, fast path for large populations.  The strict left-to-right scan is one dependent fp64 add per weight
+// (0.41 ms at 80 000 weights: the contract of `cumsum`, not parallelisable).  But an ancestor index is
+// count(wc < u), and it can only depend on the rounding order of the sums if u lies within the rounding error
+// of some wc(j).  So: (1) k_scan_approx -- a PARALLEL prefix sum wc' (blocked: per-thread segments + a tree over the threads);
+// (2) k_search_checked -- idx = count(wc' < u) and the proof that the sequential scan gives the same index:
+// wc'(idx-1) + delta < u <= wc'(idx) - delta, delta = eps ((idx+2) wc'(idx) + depth sum(w)) bounding both
+// summations (wc is non-decreasing, so the two neighbours decide for all j); a draw that cannot prove itself sets scan_ambig; (3) the exact pair
+// k_resample / k_resample_search runs ONLY IF the flag is set (a few per cent of the steps at N = 80 000; always for
+// adversarial draws placed on a boundary, NaN weights, ...).  The ancestors are bit-identical to the sequential
+// path in every case.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_scan_approx(int N, const double *__restrict__ w, double *__restrict__ wc, DevStatus *status) {
+  __shared__ double s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { status->scan_ambig = 0; status->clamp_fast = 0; }
+  const int per = (N + 1023) / 1024;
+  const int b = min(N, tid * per), e = min(N, b + per);
+  double s = 0.0;
+  for (int i = b; i < e; ++i) s += w[i];
+  double x = s;                                   // inclusive scan over the threads
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    double t = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
+    }
+    s_warp[lane] = t;
+  }
+  __syncthreads();
+  double excl = __shfl_up_sync(0xffffffffu, x, 1);          // exclusive prefix of this thread's segment
+  if (lane == 0) excl = 0.0;
+  double run = (wid ? s_warp[wid - 1] : 0.0) + excl;
+  for (int i = b; i < e; ++i) { run += w[i]; wc[i] = run; }
+}
+
+__global__ void k_search_checked(int N, int i0, int n_draws, const double *__restrict__ wc, RngSrc rng,
+                                 const int *__restrict__ forced, int *__restrict__ ai, DevStatus *status) {
+  const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i0 + n_draws) return;
+  if (forced != nullptr) { ai[i] = forced[i]; return; }
+  const double u = rng.U ? rng.U[i] : philox_uniform(rng.seed, rng.sweep, rng.t, i);
+  int lo = 0, hi = N;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (wc[mid] < u) lo = mid + 1; else hi = mid;
+  }
+  const int idx = lo;
+  // |sequential wc(j) - exact| <= eps * sum_{i<=j} wc(i) <= eps (j+1) wc(j)   (non-negative terms, non-decreasing sums);
+  // |wc'(j) - exact| <= depth * eps * sum(w), depth <= 2 ceil(N/1024) + 12 additions on any path of k_scan_approx.
+  // Both neighbours use the bound at the larger index; 5 % for the second-order terms.
+  const double per = (double)((N + 1023) / 1024);
+  const double delta = 1.05 * 1.1102230246251565e-16 *
+                       ((double)(idx + 2) * wc[min(idx, N - 1)] + (2.0 * per + 16.0) * wc[N - 1]);
+  // written so that any NaN makes the draw ambiguous
+  const bool below = idx == 0 || (wc[idx - 1] + delta < u);
+  const bool above = idx == N || (wc[idx] - delta >= u);
+  if (!(below && above && delta >= 0.0)) status->scan_ambig = 1;
+  if (idx >= N) { ai[i] = N - 1; atomicAdd(&status->clamp_fast, 1); }
+  else ai[i] = idx;
 }
 
 // ---------------------------------------------------------------------------

@@ -85,6 +85,7 @@ SYMBOLS = {
     "rbslam_read_information": (C.c_int, [_ctx, c_double_p, c_double_p, c_double_p]),
     "rbslam_counters": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),
+    "rbslam_status_counters": (C.c_int, [_ctx, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rbslam_event_record": (C.c_int, [_ctx, C.c_int32]),
     "rbslam_event_elapsed": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "rbslam_phase_timing": (C.c_int, [_ctx, C.c_int32]),

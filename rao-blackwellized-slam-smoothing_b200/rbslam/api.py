@@ -331,6 +331,12 @@ class Context:
         self._ck(self._lib.rbslam_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
 
+    def status_counters(self):
+        """Device status word: jitter retries, clamped draws, resampling steps that needed the exact scan."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self._lib.rbslam_status_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(used_jitter=a.value, clamped_draws=b.value, exact_scan_runs=c.value)
+
     # -- kernel-level ops (parity tests) --------------------------------------
     def op_resample(self, w, u):
         w = np.ascontiguousarray(w, dtype=np.float64)

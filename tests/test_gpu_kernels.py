@@ -43,6 +43,34 @@ def test_resample_bit_exact(rbslam_lib, N):
     assert np.array_equal(ai, ref)
 
 
+@pytest.mark.parametrize("N", [4096, 10000, 80000])
+def test_resample_fast_path_is_exact_and_usually_stands(rbslam_lib, N):
+    """Large populations: a parallel prefix sum first; every draw must PROVE that the strict left-to-right
+    cumsum would give the same ancestor (error bounds of both summations), else the exact scan runs.
+    (1) random draws: bit-exact against the sequential oracle, and the exact scan is (almost) never needed;
+    (2) draws placed ON the boundaries wc(j) and one ulp beside them: still bit-exact -- through the exact path."""
+    rb = rbslam_lib
+    pr, om, gm = _problem(rb, "radio")
+    rng = np.random.default_rng(N + 1)
+    w = rng.random(N) ** 4
+    w[rng.random(N) < 0.2] = 0.0
+    w = w / w.sum()
+    wc = np.cumsum(w)
+    with rb.Context(gm, 8, 4) as ctx:
+        runs = 0
+        for rep in range(8):
+            u = rng.random(N)
+            ai = ctx.op_resample(w, u)
+            assert np.array_equal(ai, oracle.tools.sample_many(w, u))
+            runs = ctx.status_counters()["exact_scan_runs"]
+        assert runs <= 2, runs                       # expected: ~0.04 ambiguous steps per 8 at N = 80 000
+        j = rng.integers(0, N, 400)
+        u = np.concatenate([rng.random(N), wc[j], np.nextafter(wc[j], 2.0), np.nextafter(wc[j], -1.0)])
+        ai = ctx.op_resample(w, u)
+        assert np.array_equal(ai, oracle.tools.sample_many(w, u))
+        assert ctx.status_counters()["exact_scan_runs"] == runs + 1
+
+
 def test_resample_frequencies(rbslam_lib):
     """The reference's own (commented-out) self-test of sample: tools/sample.m:36-64."""
     rb = rbslam_lib
