@@ -224,6 +224,14 @@ int rb_check_status(rbslam_ctx *ctx) {
 // ---------------------------------------------------------------------------
 // life cycle
 // ---------------------------------------------------------------------------
+// CUDA loads kernels lazily by default, and the first launch of a kernel may have to synchronise the device.
+// A single-process group whose shards SHARE a GPU enqueues shard 0's step -- including a peer barrier kernel that
+// spins until shard 1 arrives -- before shard 1's; if one of shard 1's kernels is launched for the first time at
+// that point, its load waits for the spinning kernel and the barrier only ends by its time-out.  (Seen as a
+// 20 s "peer did not reach the barrier" when a group on one GPU was the first thing a process ran.)  Eager
+// module loading removes the hazard; it is requested when the library is loaded, unless the user chose a mode.
+__attribute__((constructor)) static void rb_request_eager_module_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+
 extern "C" int rbslam_version(void) { return RBSLAM_VERSION; }
 
 extern "C" int rbslam_device_count(void) {

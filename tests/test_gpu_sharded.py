@@ -165,7 +165,8 @@ def test_device_planner_equals_host_planner(rbslam_lib, world):
             owner, lslot = ho.copy(), hl.copy()
 
 
-@pytest.mark.parametrize("world,N,m,T,variant", [(2, 32, 64, 10, 2), (2, 64, 253, 8, 7), (4, 64, 64, 8, 2)])
+@pytest.mark.parametrize("world,N,m,T,variant", [(2, 32, 64, 10, 2), (2, 64, 253, 8, 7), (4, 64, 64, 8, 2),
+                                                  (2, 4096, 64, 4, 2)])   # N >= 4096: the parallel resampling path
 def test_group_single_process_matches_single_gpu(rbslam_lib, world, N, m, T, variant):
     """rbslam_create_group: the same sharded filter driven from ONE process (what a MATLAB caller
     has).  Shards sit on devices 0..n-1 cyclically (all on device 0 on a 1-GPU box); outputs must
@@ -203,3 +204,26 @@ def test_group_rejects_what_it_cannot_do(rbslam_lib):
         with pytest.raises(rb.RbslamError):
             ctx.smoother_run(pr["odometry"], pr["y"], pr["x0_nonLin"], pr["x0_lin"], pr["P0_lin"], pr["Q"], pr["R"],
                              pr["dt"], 2)
+
+
+def test_group_on_one_gpu_as_the_first_thing_a_process_does():
+    """Cold start: a fresh process whose FIRST device work is a single-process group with both shards on
+    one GPU.  Shard 0's peer barrier spins until shard 1's step is enqueued; with lazy module loading the
+    first launch of one of shard 1's kernels waited for that spinning kernel (a 20 s barrier time-out:
+    'a peer rank did not reach the barrier').  The library requests eager module loading when it is loaded."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, time\n"
+        "sys.path[:0] = [%r, %r]\n"
+        "import rbslam\n"
+        "pr = rbslam.synth.dense_mag_problem(N_T=6, m=64, seed=3, m_sim=300)\n"
+        "gm = rbslam.models.from_problem(pr)\n"
+        "a = (pr['odometry'], pr['y'], pr['x0_nonLin'], pr['x0_lin'], pr['P0_lin'], pr['Q'], pr['R'])\n"
+        "t0 = time.time()\n"
+        "with rbslam.Context(gm, 32, 6, rng_mode=1, seed=5, kalman_variant=2, devices=[0, 0]) as ctx:\n"
+        "    o = ctx.filter_run(*a, pr['dt'])\n"
+        "print('GROUP_OK', float(o['xl_mean'][0]), round(time.time() - t0, 2))\n" % (ROOT, PKG))
+    env = {k: v for k, v in os.environ.items() if k != "CUDA_MODULE_LOADING"}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0 and "GROUP_OK" in r.stdout, (r.stdout[-400:], r.stderr[-1200:])
