@@ -365,3 +365,79 @@ def test_localization_oracle_pieces():
     sd = np.sqrt(0.4)
     assert abs(w[0] - 3.0 / (sd * np.sqrt(2 * np.pi))) < 1e-12       # zero residual: three density peaks added up
     assert w[0] > w[1] > 0
+
+
+# ---------------------------------------------------------------------------
+# the error bound behind the device's parallel resampling path (csrc/step_kernels.cuh: k_scan_approx,
+# k_search_checked): a NumPy restatement of the blocked summation order, against the strict
+# left-to-right cumsum (np.cumsum: tools/sample.m:30)
+# ---------------------------------------------------------------------------
+def _scan_approx_numpy(w):
+    """k_scan_approx, operation by operation: 1024 threads with contiguous segments (sequential sums), a
+    Hillis-Steele inclusive scan inside each warp (shfl_up by 1, 2, 4, 8, 16), the same over the 32 warp
+    totals, then every thread walks its segment from its exclusive prefix."""
+    N = len(w)
+    per = (N + 1023) // 1024
+    seg = [w[min(N, t * per):min(N, (t + 1) * per)] for t in range(1024)]
+    s = np.array([np.cumsum(x)[-1] if len(x) else 0.0 for x in seg])     # sequential within a thread
+
+    def warp_scan(x):                      # x: [n_warps, 32]
+        x = x.copy()
+        for o in (1, 2, 4, 8, 16):
+            y = np.zeros_like(x)
+            y[:, o:] = x[:, :-o]
+            x[:, o:] = x[:, o:] + y[:, o:]
+        return x
+    x = warp_scan(s.reshape(32, 32))
+    tot = warp_scan(x[:, 31].reshape(1, 32))[0]
+    excl = np.zeros_like(x)
+    excl[:, 1:] = x[:, :-1]
+    base = np.concatenate([[0.0], tot[:-1]])[:, None] + excl           # exclusive prefix of every thread
+    out = np.empty(N)
+    for t in range(1024):
+        b, e = min(N, t * per), min(N, (t + 1) * per)
+        if e > b:
+            run = base[t // 32, t % 32]
+            for i in range(b, e):
+                run = run + w[i]
+                out[i] = run
+    return out
+
+
+@pytest.mark.parametrize("N", [4096, 10000, 80000])
+@pytest.mark.parametrize("kind", ["uniform", "heavy", "zeros", "dominant", "ascending", "descending"])
+def test_parallel_scan_stays_inside_the_bound_the_device_uses(N, kind):
+    """|blocked prefix sum - sequential cumsum| <= delta(j) for every j, with the delta of k_search_checked:
+    1.05 eps ((j+2) wc'(j) + (2 ceil(N/1024) + 16) sum(w)).  That inequality is what lets a draw prove that
+    count(wc < u) does not depend on the rounding order (wc'(idx-1) + delta < u <= wc'(idx) - delta)."""
+    rng = np.random.default_rng(N + len(kind))
+    w = rng.random(N)
+    if kind == "heavy":
+        w = w ** 12
+    elif kind == "zeros":
+        w[rng.random(N) < 0.7] = 0.0
+    elif kind == "dominant":
+        w = w * 1e-9
+        w[N // 3] = 1.0
+    elif kind == "ascending":
+        w = np.sort(w ** 4)
+    elif kind == "descending":
+        w = np.sort(w ** 4)[::-1].copy()
+    w = w / w.sum()
+    seq = np.cumsum(w)                      # strict left-to-right: the contract
+    par = _scan_approx_numpy(w)
+    eps = 2.0 ** -53
+    per = (N + 1023) // 1024
+    j = np.arange(N)
+    delta = 1.05 * eps * ((j + 2) * par + (2 * per + 16) * par[-1])
+    assert np.all(np.abs(par - seq) <= delta)
+    # the decision rule is not vacuous: for random draws almost every one proves itself
+    u = rng.random(2000)
+    idx = np.searchsorted(par, u, side="left")               # count(par < u)
+    jj = np.minimum(idx, N - 1)
+    d = 1.05 * eps * ((idx + 2) * par[jj] + (2 * per + 16) * par[-1])
+    below = (idx == 0) | (par[np.maximum(idx - 1, 0)] + d < u)
+    above = (idx == N) | (par[jj] - d >= u)
+    sure = below & above
+    assert sure.mean() > 0.99
+    assert np.array_equal(idx[sure], np.searchsorted(seq, u, side="left")[sure])
